@@ -67,10 +67,10 @@ class FakeVariant:
 
     def __init__(self, view: "_VcfView", g: int):
         t = view.table
-        row = int(view.g_row[g])
-        blk = int(view.g_blk[g])
+        rows = view.rows[view.g_lo[g]: view.g_lo[g + 1]]
+        row = int(rows[0])
         self._row = row
-        self.CHROM = t.contigs[int(t.blk_contig[blk])]
+        self.CHROM = t.contigs[int(view.g_contig[g])]
         self.start = int(t.pos[row])
         self.POS = self.start + 1
         ref, alts = t.ref_alts(row)
@@ -83,33 +83,42 @@ class FakeVariant:
         rd = np.full(ns, -1, dtype=np.int32)
         ad = np.full(ns, -1, dtype=np.int32)
         gq = np.full(ns, -1.0, dtype=np.float32)
-        b = 3 * int(t.blk_trio[blk])
-        gt[b:b + 3] = t.gt[:, row]
-        rd[b:b + 3] = t.rd[:, row]
-        ad[b:b + 3] = t.ad[:, row]
-        gq[b:b + 3] = t.gq[:, row]
+        for row in rows:
+            b = 3 * int(t.blk_trio[view.row_blk[row]])
+            gt[b:b + 3] = t.gt[:, row]
+            rd[b:b + 3] = t.rd[:, row]
+            ad[b:b + 3] = t.ad[:, row]
+            gq[b:b + 3] = t.gq[:, row]
         self.gt_types, self.gt_ref_depths, self.gt_alt_depths, self.gt_quals = gt, rd, ad, gq
 
 
 class _VcfView:
-    """Joint-VCF view of a trio-major SiteTable: records sorted by (contig, pos, block)."""
+    """Joint-VCF view of a trio-major SiteTable: one record per rec_id, sorted by (contig, pos)."""
 
     def __init__(self, table: SiteTable):
         self.table = table
         V = table.n_rows
         blk = np.repeat(np.arange(table.n_blocks), np.diff(table.blk_off))
+        self.row_blk = blk
         contig = table.blk_contig[blk].astype(np.int64)
-        order = np.lexsort((blk, table.pos.astype(np.int64), contig))
-        self.g_row = np.arange(V)[order]
-        self.g_blk = blk[order]
-        self.g_contig = contig[order]
-        self.g_pos = table.pos[order].astype(np.int64)
+        rid = table.record_ids().astype(np.int64)
+        order = np.lexsort((blk, rid, table.pos.astype(np.int64), contig))
+        self.rows = np.arange(V)[order]
+        srid = rid[order]
+        first = np.ones(V, dtype=bool)
+        first[1:] = (srid[1:] != srid[:-1]) | (contig[order][1:] != contig[order][:-1])
+        g_first = np.nonzero(first)[0]
+        self.g_lo = np.concatenate([g_first, [V]]).astype(np.int64)
+        lead = self.rows[g_first]
+        self.g_contig = contig[lead]
+        self.g_pos = table.pos[lead].astype(np.int64)
         self.g_key = (self.g_contig << 40) + self.g_pos
         reflen = np.ones(V, dtype=np.int64)
         for r, (ref, _alts) in table.extras.items():
             reflen[r] = len(ref)
-        self.g_reflen = reflen[order]
+        self.g_reflen = reflen[lead]
         self.max_reflen = int(reflen.max()) if V else 1
+        self.n = int(g_first.shape[0])
 
 
 def _view(table: SiteTable) -> _VcfView:
@@ -133,7 +142,7 @@ class VCF:
         return self
 
     def __next__(self):
-        if self._cursor >= self._view.g_row.shape[0]:
+        if self._cursor >= self._view.n:
             raise StopIteration
         v = FakeVariant(self._view, self._cursor)
         self._cursor += 1

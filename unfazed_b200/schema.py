@@ -80,10 +80,19 @@ class SiteTable:
     ad: np.ndarray                             # i32[3,V]
     # host-only: full REF / ALT strings of rows that are not simple SNVs
     extras: Dict[int, Tuple[str, List[str]]] = field(default_factory=dict)
+    # host-only: identity of the VCF record a row was extracted from.  A joint VCF packed
+    # trio-major repeats every record once per trio block; rows sharing a rec_id are ONE record
+    # (matters only for get_refalt, snv_phaser.py:73-84).  None = every row is its own record.
+    rec_id: Optional[np.ndarray] = None
 
     @property
     def n_rows(self) -> int:
         return int(self.pos.shape[0])
+
+    def record_ids(self) -> np.ndarray:
+        if self.rec_id is None:
+            return np.arange(self.n_rows, dtype=np.int64)
+        return self.rec_id
 
     @property
     def n_blocks(self) -> int:

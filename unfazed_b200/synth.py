@@ -115,7 +115,7 @@ def _place_dnms(cfg: SynthConfig, rng: np.random.Generator, trio: int):
         if contig[i] != prev_c:
             # sex chromosomes: start beyond PAR1 of either table (utils.py:26-43)
             cur = 3_000_000 if contig[i] >= ncont else 100 * sp
-            cur += cfg.search_dist + cfg.read_margin
+            cur += cfg.search_dist + cfg.read_margin + int(rng.integers(0, 64)) * sp
             prev_c = contig[i]
             first = True
         else:

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+nvidia-smi -L
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -40

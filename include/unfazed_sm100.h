@@ -1,0 +1,271 @@
+/*
+ * unfazed_sm100.h -- C ABI of libunfazed_sm100.so, the B200 (sm_100a) phasing hot path.
+ *
+ * The reference (jbelyeu/unfazed) is pure Python and has no FFI: its boundary for this path is the
+ * module interface informative_site_finder.find / read_collector.collect_reads_* /
+ * site_searcher.match_informative_sites / {snv,sv}_phaser.phase_by_reads / unfazed.summarize_record.
+ * Each entry point below names the reference code it replaces (paths relative to the reference
+ * repo).  The Python drop-in modules in unfazed_b200/ bind these with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with h_;
+ *   - the caller owns all buffers and passes sizes explicitly; nothing is allocated here;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, negative = error; text via unfz_last_error();
+ *   - no globals: thresholds are passed by value per call (the reference keeps them in module
+ *     globals, informative_site_finder.py:187-204, read_collector.py:361-370).
+ */
+#ifndef UNFAZED_SM100_H
+#define UNFAZED_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNFZ_ABI_VERSION 1
+
+/* ---- class code of one (DNM x site) pair, written by unfz_classify_sites ------------------- */
+#define UNFZ_CLS_HET        0x01  /* usable for extended read-backed phasing (het_sites)         */
+#define UNFZ_CLS_CAND       0x02  /* informative site (candidate_sites)                          */
+#define UNFZ_CLS_ALT_IS_DAD 0x04  /* candidate: alt_parent is the father                         */
+#define UNFZ_CLS_KID_ALT    0x08  /* CNV mode: kid_allele == "alt_parent" (else "ref_parent")    */
+
+/* ---- segment modes ------------------------------------------------------------------------- */
+#define UNFZ_MODE_READ    0   /* whole_region=False: kid must be HET and high quality            */
+#define UNFZ_MODE_CNV_DEL 1   /* whole_region=True, vartype DEL                                  */
+#define UNFZ_MODE_CNV_DUP 2   /* whole_region=True, vartype DUP                                  */
+#define UNFZ_MODE_CNV_NA  3   /* whole_region=True, any other vartype: never a candidate         */
+
+/* ---- per-read summary flags (UnfzReadSum.flags) -------------------------------------------- */
+#define UNFZ_RS_GOOD_CONC 0x01  /* goodread(read)                (read_collector.py:28-53)       */
+#define UNFZ_RS_GOOD_DISC 0x02  /* goodread(read, True)                                          */
+#define UNFZ_RS_NONE_OK   0x04  /* <= 5 None reference positions (:200, :407)                    */
+#define UNFZ_RS_EXT_OK    0x08  /* <= 5 CIGAR ops other than M/= (:190-196)                      */
+#define UNFZ_RS_INS_OK    0x10  /* abs(tlen - 2*readlen) <= concordant_upper_len (:181-183,:395) */
+#define UNFZ_RS_HAS_MATE  0x20  /* bamfile.mate(read) would not raise                            */
+
+/* ---- DNM kinds for unfz_chain_tally ---------------------------------------------------------- */
+#define UNFZ_KIND_SKIP  0   /* nothing to do (autophased, no candidates, no usable REF/ALT)       */
+#define UNFZ_KIND_SNV   1   /* len(ref) == len(alt): snv_match_alleles                            */
+#define UNFZ_KIND_INDEL 2   /* indel_match_alleles                                               */
+#define UNFZ_KIND_SV    3   /* collect_reads_sv seeds                                            */
+
+/* ---- final call codes (UnfzCall.origin) ------------------------------------------------------ */
+#define UNFZ_ORIGIN_NONE 0
+#define UNFZ_ORIGIN_DAD  1
+#define UNFZ_ORIGIN_MOM  2
+#define UNFZ_ORIGIN_BOTH 3   /* "dad|mom": AMBIGUOUS_READBACKED                                  */
+
+#define UNFZ_EV_READBACKED        0x01
+#define UNFZ_EV_ALLELE_BALANCE    0x02
+#define UNFZ_EV_AMBIG_READBACKED  0x04
+#define UNFZ_EV_AMBIG_ALLELE_BAL  0x08
+#define UNFZ_EV_AMBIG_BOTH        0x10
+#define UNFZ_EV_SEX_CHROM         0x20
+
+/* Trio-major site columns (schema.SiteTable).  44 B per row: pos 4 + flag 1 + 3*(gt 1+gq 4+rd 4+ad 4). */
+typedef struct {
+    int64_t        n_rows;
+    int32_t        n_blocks;
+    int32_t        _pad;
+    const int64_t* blk_off;      /* [n_blocks+1] */
+    const int32_t* pos;
+    const uint8_t* flag;         /* bit0: simple biallelic SNV record */
+    const uint8_t* ref;          /* ASCII */
+    const uint8_t* alt;          /* ASCII */
+    const uint8_t* gt[3];        /* kid, dad, mom: cyvcf2 gt_types 0/1/2/3 */
+    const float*   gq[3];
+    const int32_t* rd[3];
+    const int32_t* ad[3];
+} UnfzSiteCols;
+
+/* 32-byte read header (schema.READ_HDR) */
+typedef struct {
+    int32_t  start;
+    int32_t  tlen;
+    int32_t  mate;        /* global read index or -1 */
+    uint32_t cigar_off;
+    uint32_t qoff_lo;
+    int32_t  l_seq;
+    uint16_t flag;
+    uint16_t n_cigar;
+    uint8_t  mapq;
+    uint8_t  aux;         /* bit0 next_ref==ref, bit1 has SA tag */
+    uint8_t  qoff_hi;
+    uint8_t  pad;
+} UnfzRead;
+
+typedef struct {
+    int64_t         n_reads;
+    int32_t         n_blocks;
+    int32_t         _pad;
+    const int64_t*  blk_off;     /* [n_blocks+1] */
+    const int32_t*  blk_sblk;    /* [n_blocks] site block holding this kid's trio on this contig, or -1 */
+    const double*   blk_cul;     /* [n_blocks] concordant_upper_len of the kid */
+    const UnfzRead* hdr;
+    const uint32_t* cigar;       /* BAM encoding len<<4|op */
+    const uint8_t*  qual;        /* bit7: base is not ACGT */
+    const uint8_t*  seq2;        /* 2-bit bases, base i at bits 2*(i&3) of byte i>>2 */
+    int64_t         n_qual;
+    int64_t         n_cigar;
+} UnfzReadCols;
+
+/* per-read summary written by unfz_read_scan (16 B) */
+typedef struct {
+    int32_t  end;         /* reference_end (exclusive) */
+    int32_t  fmark;       /* number of marked site rows before the first row with pos >= start */
+    uint16_t flags;       /* UNFZ_RS_* */
+    uint16_t cnt;         /* marked site rows with start <= pos < end */
+    uint32_t hoff;        /* first hit word of this read (filled by the exclusive scan of cnt) */
+} UnfzReadSum;
+
+typedef struct {
+    double  ab_homref[2];
+    double  ab_homalt[2];
+    double  ab_het[2];
+    double  min_gt_qual;         /* --min-gt-qual; also the minimum base quality */
+    int32_t min_depth;
+    int32_t min_map_qual;
+    int32_t readlen;
+    int32_t ext_read_goal;       /* --insert-size-max-sample (Q2) */
+    int32_t no_extended;
+    int32_t evidence_min_ratio;
+    int32_t split_error_margin;
+    int32_t _pad;
+} UnfzParams;
+
+/* one window of one DNM; produced by the host planner from find()/find_many() semantics */
+typedef struct {
+    int32_t sblk;         /* site block or -1 */
+    int32_t lo_pos;       /* inclusive bounds on the 0-based site position */
+    int32_t hi_pos;
+    int32_t mult;         /* how many times each site is appended (Q9, find_many duplicates) */
+    int32_t dnm;          /* owning DNM entry */
+    int32_t excl_lo;      /* small-event rule: skip sites with excl_lo <= pos < excl_hi */
+    int32_t excl_hi;
+    int32_t mode;         /* UNFZ_MODE_* */
+} UnfzSegIn;
+
+typedef struct {
+    int32_t pos;          /* denovo["start"] */
+    int32_t end;          /* denovo["end"] */
+    int32_t rblk;         /* read block or -1 */
+    int32_t kind;         /* UNFZ_KIND_* */
+    int32_t seg_lo;       /* segments [seg_lo, seg_hi) belong to this DNM entry */
+    int32_t seg_hi;
+    int32_t ref_off;      /* allele blob offsets / lengths (REF and ALT of the DNM) */
+    int32_t ref_len;
+    int32_t alt_off;
+    int32_t alt_len;
+    int32_t cnv_entry;    /* index of the CNV-mode entry of the same DNM, or -1 */
+    int32_t flags;        /* bit0: autophased (SEX-CHROM), bit1: autophased on Y, bit2: SV autophase quirk (Q8), bit3: seed fetch window is (pos,pos+1) (Q24) */
+} UnfzDnm;
+
+/* per-DNM output of unfz_chain_tally / unfz_summarize */
+typedef struct {
+    int32_t n_dad_sites, n_mom_sites;   /* unique informative-site positions per parent */
+    int32_t n_dad_reads, n_mom_reads;   /* unique read names per parent */
+    int32_t cnv_dad, cnv_mom;           /* allele-balance votes (with duplicates) */
+    int32_t has_record;                 /* 1: a read-backed record exists (matches non-empty) */
+    int32_t status;                     /* 0 ok, >0 capacity / consistency problems */
+} UnfzTally;
+
+typedef struct {
+    int32_t origin;                     /* UNFZ_ORIGIN_* */
+    int32_t evidence_count;
+    int32_t evidence_types;             /* UNFZ_EV_* bitmask */
+    int32_t emitted;                    /* 0: summarize_record returns None for include_ambiguous=False */
+} UnfzCall;
+
+typedef struct UnfzCtx UnfzCtx;
+
+int         unfz_abi_version(void);
+int         unfz_ctx_create(int device, UnfzCtx** out);
+void        unfz_ctx_destroy(UnfzCtx* ctx);
+const char* unfz_last_error(UnfzCtx* ctx);
+
+/* Exclusive prefix sums (device-wide).  `work` needs unfz_scan_work_bytes(n) bytes. */
+int64_t unfz_scan_work_bytes(int64_t n);
+int unfz_exclusive_scan_i64(UnfzCtx*, const int64_t* in, int64_t* out, int64_t n, void* work, void* stream);
+int unfz_exclusive_scan_u16_u32(UnfzCtx*, const uint16_t* in, int64_t in_stride_bytes, uint32_t* out,
+                                int64_t out_stride_bytes, int64_t n, int64_t* total_out, void* work, void* stream);
+int unfz_exclusive_scan_u8_i32(UnfzCtx*, const uint8_t* in, int32_t* out, int64_t n, void* work, void* stream);
+
+/* Window membership: informative_site_finder.py get_position :10-43 / get_close_vars :399-420.
+ * For every segment: seg_row_lo = first row of the block with pos >= lo_pos, seg_count =
+ * mult * #rows with lo_pos <= pos <= hi_pos. */
+int unfz_window_search(UnfzCtx*, const UnfzSiteCols* sites, const UnfzSegIn* segs, int32_t n_segs,
+                       int32_t* seg_row_lo, int64_t* seg_count, void* stream);
+
+/* Informative-site classification of every (DNM x site) pair:
+ * is_high_quality_site :46-73, get_kid_allele :76-134, find :252-339 == add_good_candidate_variant
+ * :457-542.  seg_pair_off is the exclusive scan of seg_count (n_segs+1 entries). */
+int unfz_classify_sites(UnfzCtx*, const UnfzSiteCols* sites, const UnfzSegIn* segs,
+                        const int32_t* seg_row_lo, const int64_t* seg_pair_off, int32_t n_segs,
+                        int64_t n_pairs, const UnfzParams* h_params, uint8_t* out_class, void* stream);
+
+/* Stable compaction of the class codes into per-DNM het_sites / candidate_sites lists (the sorted
+ * lists find() returns, :341-342) + CNV votes (sv_phaser.py phase_by_snvs :71-85) + site marks.
+ * Lists live at [seg_pair_off[dnm.seg_lo], ...): het_list[i] = row, cand_list[i] = row |
+ * alt_is_dad<<31 | kid_alt<<30.  row_mark[row] = 1 for every het/candidate row of a READ-mode
+ * segment. */
+int unfz_compact_sites(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
+                       const int32_t* seg_row_lo, const int64_t* seg_pair_off, const uint8_t* cls,
+                       int32_t* het_list, int32_t* n_het, uint32_t* cand_list, int32_t* n_cand,
+                       int32_t* cnv_dad, int32_t* cnv_mom, uint8_t* row_mark, void* stream);
+
+/* Read scan: goodread :28-53, insert-size / None-count / CIGAR-op filters :181-203 :395-408,
+ * reference_end, and the number of marked site rows each read overlaps.
+ * mark_prefix = exclusive scan of row_mark (n_rows+1 entries). */
+int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
+                   const int32_t* mark_prefix, const UnfzParams* h_params, UnfzReadSum* out,
+                   int32_t* blk_maxspan /* [n_blocks], zeroed by the caller: max(end-start) */,
+                   void* stream);
+
+/* Read-by-site allele lookup: get_reference_positions(full_length=True).index(pos) + base +
+ * quality for every (read x marked site) overlap (get_allele_at :56-73, phase_by_reads
+ * snv_phaser.py:16-70).  Hit word: bits0-15 query index+1 (0: position not aligned),
+ * bits16-23 raw quality byte, bits24-25 base code, bit26: index+1 < l_seq. */
+int unfz_read_site_alleles(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
+                           const uint8_t* row_mark, const int32_t* mark_prefix,
+                           const UnfzReadSum* rsum, uint32_t* hits, void* stream);
+
+/* Sizing pass of unfz_chain_tally: per DNM read window and scratch needs (need[6][n_dnms] int64:
+ * window slots, het incidences, seed entries, seed incidences, het sites, candidate sites). */
+int unfz_chain_size(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
+                    const int64_t* seg_pair_off, const UnfzSiteCols* sites,
+                    const UnfzReadCols* reads, const UnfzReadSum* rsum, const int32_t* blk_maxspan,
+                    const int32_t* het_list, const int32_t* n_het, const uint32_t* cand_list,
+                    const int32_t* n_cand, int32_t* win_lo, int32_t* win_hi, int64_t* need,
+                    void* stream);
+
+/* Seed reads (collect_reads_snv :339-432), extended chaining (group_reads_by_haplotype :155-263,
+ * connect_reads :76-152), site matching (site_searcher.py:6-78), phase_by_reads and the per-parent
+ * evidence tally (snv_phaser.py:168-203).  One CTA per DNM.  slot_label / slot_evid / cand_evid must be
+ * zero-filled by the caller (cand_evid padded to a multiple of 4 bytes).
+ * off[6][n_dnms+1] are the exclusive scans of need[6][n_dnms] from unfz_chain_size. */
+int unfz_chain_tally(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
+                     const int64_t* seg_pair_off, const UnfzSiteCols* sites,
+                     const UnfzReadCols* reads, const UnfzReadSum* rsum, const int32_t* blk_maxspan,
+                     const uint32_t* hits, const int32_t* mark_prefix,
+                     const int32_t* het_list, const int32_t* n_het, const uint32_t* cand_list,
+                     const int32_t* n_cand, const uint8_t* alleles, const int32_t* win_lo,
+                     const int32_t* win_hi, const int64_t* off, const int64_t* h_totals /* off[k][n_dnms], k<6 */,
+                     const UnfzParams* h_params, void* scratch, int64_t scratch_bytes,
+                     uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid,
+                     UnfzTally* tally, void* stream);
+int64_t unfz_chain_scratch_bytes(int64_t slots, int64_t incs, int64_t seeds, int64_t seed_incs,
+                                 int64_t het_sites, int64_t cand_sites, int64_t n_dnms);
+
+/* Final call per DNM: unfazed.py summarize_record :190-334 on the tallies (+ autophase :162-187). */
+int unfz_summarize(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzTally* tally,
+                   const int32_t* cnv_dad, const int32_t* cnv_mom, const int32_t* n_cand,
+                   const UnfzParams* h_params,
+                   UnfzCall* calls_strict, UnfzCall* calls_ambiguous, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNFAZED_SM100_H */

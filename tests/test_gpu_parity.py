@@ -1,0 +1,125 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle port on seeded synthetic trios.
+
+Bit-exact bar: candidate/het site lists incl. duplicates, read->haplotype labels, per-parent site
+and read-name sets, evidence counts and calls (SURVEY.md 8(c) parity definition)."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import port
+from unfazed_b200 import _lib as L
+from unfazed_b200.synth import SynthConfig, make_dataset
+from tests.util import gpu_kwargs, norm_record, port_params, run_port, summarize_all
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from unfazed_b200.engine import Engine
+    return Engine(0)
+
+
+CASES = [
+    ("clean", SynthConfig(dnms_per_trio=40, seed=21, noise=False), {}),
+    ("noisy", SynthConfig(dnms_per_trio=60, seed=22), {}),
+    ("find_many", SynthConfig(dnms_per_trio=40, seed=23), dict(multiread_proc_min=1)),
+    ("clustered_indel", SynthConfig(dnms_per_trio=50, seed=24, cluster_frac=0.4, indel_frac=0.25), {}),
+    ("two_trios_many", SynthConfig(dnms_per_trio=30, seed=25, n_trios=2, cluster_frac=0.3, indel_frac=0.2),
+     dict(multiread_proc_min=1, threads=2)),
+    ("no_extended", SynthConfig(dnms_per_trio=40, seed=26), dict(no_extended=True)),
+    ("sex_chr_prefix", SynthConfig(dnms_per_trio=40, seed=27, sex_chrom_frac=0.4, male_frac=1.0, chr_prefix="chr"), {}),
+    ("prefix_mismatch_many", SynthConfig(dnms_per_trio=30, seed=28, chr_prefix="chr", dnm_chr_prefix=""),
+     dict(multiread_proc_min=1)),
+    ("prefix_mismatch_find", SynthConfig(dnms_per_trio=30, seed=29, chr_prefix="chr", dnm_chr_prefix=""), {}),
+    ("thresholds", SynthConfig(dnms_per_trio=40, seed=30),
+     dict(min_gt_qual=30, min_depth=25, ab_het=(0.3, 0.7), ab_homref=(0.0, 0.1), min_map_qual=20, readlen=150)),
+    ("deep_long_range", SynthConfig(dnms_per_trio=6, seed=31, search_dist=20000, coverage=45.0), dict(search_dist=20000)),
+    ("svs_cnv", SynthConfig(dnms_per_trio=40, seed=32, sv_frac=0.6, sv_max_len=100000, indel_frac=0.1), {}),
+]
+
+
+@pytest.mark.parametrize("name,cfg,params", CASES, ids=[c[0] for c in CASES])
+def test_records_labels_and_sites(engine, name, cfg, params):
+    from unfazed_b200.phaser import BatchPhaser, dnm_key
+    ds = make_dataset(cfg)
+    want, ph = run_port(ds, **params)
+    bp = BatchPhaser(engine, ds.sites, ds.reads, ds.pedigrees)
+    kids = set(ds.pedigrees)
+    svs = [d for d in ds.dnms if d["vartype"].upper() in port.SV_TYPES and d["kid"] in kids]
+    snvs = [d for d in ds.dnms if d["vartype"].upper() in port.SNV_TYPES and d["kid"] in kids]
+    res, layout = bp.run(snvs, svs, **gpu_kwargs(**params))
+    got = bp.records(res, layout)
+    assert not res.tally["status"].any(), "capacity problems reported by the chain kernel"
+
+    # site lists of the SNV read-mode entries against port.find
+    p = port_params(**params)
+    if snvs:
+        ann = port.find(copy.deepcopy(snvs), ds.pedigrees, ds.sites, p, p.search_dist, whole_region=False)
+        by_key = {port._key(d): d for d in ann}
+        a, b = layout["snv"]
+        for d in range(a, b):
+            dn = res.plan.entries[d]
+            w = by_key[dnm_key(dn)]
+            if res.plan.trio[d] < 0:
+                assert "candidate_sites" not in w
+                continue
+            cands, hets = bp.site_dicts(res, d, int(res.plan.trio[d]), False)
+            assert cands == w.get("candidate_sites", []), (name, dnm_key(dn))
+            assert hets == w.get("het_sites", []), (name, dnm_key(dn))
+
+    # read -> haplotype labels
+    for key, lab in ph.labels.items():
+        ds_ = [d for d in range(*layout["snv"]) if dnm_key(res.plan.entries[d]) == key]
+        if not ds_:
+            continue
+        mine = bp.labels(res, ds_[0])
+        assert mine == lab, (name, key)
+
+    # records and calls
+    assert set(got) == set(want), (name, sorted(set(got) ^ set(want))[:5])
+    for k in want:
+        assert norm_record(got[k]) == norm_record(want[k]), (name, k)
+    for amb in (True, False):
+        sw = summarize_all(want, amb)
+        sg = summarize_all(got, amb)
+        for k in sw:
+            a_, b_ = sw[k], sg[k]
+            if a_ is None or b_ is None:
+                assert a_ is None and b_ is None
+                continue
+            for f in ("origin_parent", "other_parent", "evidence_count", "evidence_types", "origin_parent_sites", "other_parent_sites"):
+                assert a_[f] == b_[f], (name, k, f)
+
+
+def test_device_calls_match_summarize_record(engine):
+    """unfz_summarize (device) == summarize_record on the records, strict and ambiguous."""
+    from unfazed_b200.phaser import BatchPhaser, dnm_key
+    ds = make_dataset(SynthConfig(dnms_per_trio=60, seed=41, sv_frac=0.4, sv_max_len=60000, sex_chrom_frac=0.2, male_frac=1.0))
+    bp = BatchPhaser(engine, ds.sites, ds.reads, ds.pedigrees)
+    kids = set(ds.pedigrees)
+    svs = [d for d in ds.dnms if d["vartype"].upper() in port.SV_TYPES]
+    snvs = [d for d in ds.dnms if d["vartype"].upper() in port.SNV_TYPES]
+    res, layout = bp.run(snvs, svs)
+    recs = bp.records(res, layout)
+    names = {L.ORIGIN_NONE: None}
+    for rng_name in ("sv_read", "snv"):
+        for d in range(*layout[rng_name]):
+            dn = res.plan.entries[d]
+            key = dnm_key(dn)
+            dad, mom = ds.pedigrees[dn["kid"]]["dad"], ds.pedigrees[dn["kid"]]["mom"]
+            for amb, calls in ((False, res.calls_strict), (True, res.calls_ambiguous)):
+                want = port.summarize_record(copy.deepcopy(recs[key]), amb, False, 10) if key in recs else None
+                c = calls[d]
+                if want is None:
+                    assert c["emitted"] == 0, (key, amb)
+                    continue
+                assert c["emitted"] == 1, (key, amb)
+                origin = {L.ORIGIN_NONE: None, L.ORIGIN_DAD: dad, L.ORIGIN_MOM: mom, L.ORIGIN_BOTH: dad + "|" + mom}[int(c["origin"])]
+                assert origin == want["origin_parent"], (key, amb)
+                assert int(c["evidence_count"]) == want["evidence_count"], (key, amb)
+                types = set(want["evidence_types"])
+                bits = {"READBACKED": 1, "ALLELE-BALANCE": 2, "AMBIGUOUS_READBACKED": 4, "AMBIGUOUS_ALLELE-BALANCE": 8,
+                        "AMBIGUOUS_BOTH": 16, "SEX-CHROM": 32}
+                assert int(c["evidence_types"]) == sum(bits[t] for t in types), (key, amb)

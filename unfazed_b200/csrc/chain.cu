@@ -1,0 +1,825 @@
+// Read path, part 2: seed reads, extended read-backed chaining, site matching and the evidence tally.
+// One CTA per DNM.
+//
+// The reference chains reads with a recursive, order-dependent breadth-first 2-colouring
+// (read_collector.py connect_reads :76-152).  It is reproduced exactly as a level-synchronous BFS:
+// inside one level a still-unlabelled read pair is claimed by the FIRST (finder, site) visit of the
+// sequential order, and that order is a total order on keys (haplotype order, position of the
+// finder in its list, index of the site in the finder's site list).  Because the first finder that
+// visits a site labels every eligible pair registered there, only the minimum key per site matters:
+//   best[site]  = min key over this level's finders that can read an allele at the site
+//   claim[pair] = min best[site] over the sites where the pair is an eligible target
+// The order of the next level's lists is (claiming key, position in the site's read list), which is
+// recovered with per-site ballot ranks and a rank of the sites by key -- no global sort.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CH_THREADS = 128;
+constexpr int CH_WARPS = CH_THREADS / 32;
+constexpr unsigned long long KEY_NONE = ~0ull;
+
+struct Scratch {
+    // per window slot
+    int32_t* prim; uint32_t* ord; int32_t* lvl; int32_t* fpos; int32_t* icnt;
+    unsigned long long* minkey; int32_t* tmp;
+    // per het-site incidence
+    int32_t* inc_r; int32_t* inc_x; int32_t* inc_site; int32_t* inc_sidx; uint8_t* inc_al;
+    // seeds
+    int32_t* seed_r; uint8_t* seed_hap;
+    // seed incidences
+    int32_t* sinc_x; int32_t* sinc_site; int32_t* sinc_sidx; uint8_t* sinc_al;
+    // per het site (site_off has one extra entry per DNM)
+    int32_t* spos; uint8_t* sref; uint8_t* salt; int32_t* site_off;
+    unsigned long long* bestkey; uint8_t* best_info; int32_t* site_cnt; int32_t* site_base;
+    // per candidate site
+    int32_t* cpos;
+};
+
+struct ChainArgs {
+    const UnfzDnm* dnms; int32_t n_dnms;
+    const UnfzSegIn* segs; const int64_t* seg_pair_off;
+    UnfzSiteCols sites; UnfzReadCols reads;
+    const UnfzReadSum* rsum; const int32_t* blk_maxspan; const uint32_t* hits; const int32_t* mp;
+    const int32_t* het_list; const int32_t* n_het; const uint32_t* cand_list; const int32_t* n_cand;
+    const uint8_t* alleles; const int32_t* win_lo; const int32_t* win_hi; const int64_t* off;  // off[6][n+1]
+    int32_t readlen, min_bq, ext_goal, no_extended;
+    uint8_t* slot_label; uint8_t* slot_evid; uint8_t* cand_evid; UnfzTally* tally;
+    Scratch S;
+};
+
+__device__ __forceinline__ int32_t rd_start(const UnfzReadCols& R, int64_t r) { return __ldg(&R.hdr[r].start); }
+__device__ __forceinline__ int32_t rd_mate(const UnfzReadCols& R, int64_t r) { return __ldg(&R.hdr[r].mate); }
+
+// first read index in [lo,hi) with start >= v
+__device__ __forceinline__ int64_t lb_start(const UnfzReadCols& R, int64_t lo, int64_t hi, int64_t v) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)rd_start(R, mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int cigar_qpos2(const uint32_t* __restrict__ cg, int n_cigar, int32_t start, int32_t p) {
+    int32_t cur = start;
+    int q = 0;
+    for (int k = 0; k < n_cigar; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        const uint32_t op = w & 15u;
+        const int32_t ln = (int32_t)(w >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            if (p < cur + ln) return p >= cur ? q + (p - cur) : -1;
+            cur += ln; q += ln;
+        } else if (op == 1 || op == 4) {
+            q += ln;
+        } else if (op == 2 || op == 3) {
+            if (p < cur + ln) return -1;
+            cur += ln;
+        }
+    }
+    return -1;
+}
+
+__device__ __forceinline__ char base_char(const UnfzReadCols& R, int64_t g) {
+    const uint32_t qb = __ldg(R.qual + g);
+    const uint32_t code = (__ldg(R.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
+    if (qb & 0x80u) return code == 0 ? 'N' : '?';
+    return "ACGT"[code];
+}
+__device__ __forceinline__ char hit_char(uint32_t w) {
+    const uint32_t code = (w >> 24) & 3u;
+    if (w & (0x80u << 16)) return code == 0 ? 'N' : '?';
+    return "ACGT"[code];
+}
+
+// hit word of (read e, site row) or 0
+__device__ __forceinline__ uint32_t hit_lookup(const ChainArgs& A, int64_t e, int64_t row) {
+    const UnfzReadSum s = load_rsum(A.rsum + e);
+    const int k = __ldg(A.mp + row) - s.fmark;
+    if (k < 0 || k >= (int)s.cnt) return 0;
+    return __ldg(A.hits + (int64_t)s.hoff + k);
+}
+
+// goodread + insert + mate + None-count + mate-overlap (read_collector.py:181-214, :395-418)
+__device__ bool pair_ok(const ChainArgs& A, int64_t r, bool ext) {
+    const UnfzReadSum s = load_rsum(A.rsum + r);
+    uint32_t need = UNFZ_RS_GOOD_CONC | UNFZ_RS_INS_OK | UNFZ_RS_HAS_MATE | UNFZ_RS_NONE_OK;
+    if (ext) need |= UNFZ_RS_EXT_OK;
+    if ((s.flags & need) != need) return false;
+    const int64_t m = rd_mate(A.reads, r);
+    const UnfzReadSum sm = load_rsum(A.rsum + m);
+    const uint32_t needm = UNFZ_RS_GOOD_CONC | UNFZ_RS_NONE_OK;
+    if ((sm.flags & needm) != needm) return false;
+    const int32_t r0 = rd_start(A.reads, r), r1 = s.end, m0 = rd_start(A.reads, m), m1 = sm.end;
+    if ((m0 <= r0 && r0 <= m1) || (m0 <= r1 && r1 <= m1)) return false;
+    return true;
+}
+
+// snv_match_alleles (:296-336) through get_allele_at (:56-73): 0 none, 1 ref, 2 alt
+__device__ int seed_snv(const ChainArgs& A, const UnfzDnm& dn, int64_t r) {
+    int64_t e = r;
+    UnfzRead h = load_read(A.reads.hdr + e);
+    int q = cigar_qpos2(A.reads.cigar + h.cigar_off, h.n_cigar, h.start, dn.pos);
+    if (q < 0) {
+        e = h.mate;
+        h = load_read(A.reads.hdr + e);
+        q = cigar_qpos2(A.reads.cigar + h.cigar_off, h.n_cigar, h.start, dn.pos);
+        if (q < 0) return 0;
+    }
+    if (q < 4 || q > A.readlen - 4) return 0;
+    const int n = dn.ref_len > dn.alt_len ? dn.ref_len : dn.alt_len;
+    if (!(h.l_seq > q + n)) return 0;
+    const int64_t g = read_qoff(h) + q;
+    bool is_ref = true;
+    for (int i = 0; i < dn.ref_len; ++i)
+        if (base_char(A.reads, g + i) != (char)A.alleles[dn.ref_off + i]) { is_ref = false; break; }
+    if (is_ref) return 1;
+    bool is_alt = true;
+    for (int i = 0; i < dn.alt_len; ++i)
+        if (base_char(A.reads, g + i) != (char)A.alleles[dn.alt_off + i]) { is_alt = false; break; }
+    return is_alt ? 2 : 0;
+}
+
+// indel_match_alleles (:266-293), Q21: the CIGAR is expanded over ALL operations
+__device__ int seed_indel(const ChainArgs& A, const UnfzDnm& dn, int64_t r) {
+    const UnfzRead h = load_read(A.reads.hdr + r);
+    const uint32_t* cg = A.reads.cigar + h.cigar_off;
+    const int q = cigar_qpos2(cg, h.n_cigar, h.start, dn.pos);
+    if (q < 0) return 0;
+    const int n = dn.ref_len > dn.alt_len ? dn.ref_len : dn.alt_len;
+    const int64_t g0 = read_qoff(h);
+    for (int i = q; i < q + n && i < h.l_seq; ++i)
+        if ((int)(__ldg(A.reads.qual + g0 + i) & 0x7fu) < A.min_bq) return 0;
+    bool has_id = false;
+    int64_t eo = 0, npos = 0;
+    for (int k = 0; k < h.n_cigar; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        const uint32_t op = w & 15u;
+        const int64_t ln = w >> 4;
+        if ((op == 1 || op == 2) && eo < (int64_t)q + n && eo + ln > q) has_id = true;
+        eo += ln;
+        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) npos += ln;
+    }
+    if (has_id) return 2;
+    if (7 < q && q < npos - 7) return 1;
+    return 0;
+}
+
+// exclusive prefix of `flag` over the CTA in thread order + total
+__device__ __forceinline__ int block_prefix(bool flag, int* total) {
+    __shared__ int wsum[CH_WARPS];
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(b);
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < CH_WARPS; ++i) { if (i < w) base += wsum[i]; tot += wsum[i]; }
+    __syncthreads();
+    *total = tot;
+    return base + __popc(b & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ int block_sum(int v) {
+    __shared__ int wsum2[CH_WARPS];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) wsum2[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int i = 0; i < CH_WARPS; ++i) tot += wsum2[i];
+    __syncthreads();
+    return tot;
+}
+
+// site_searcher.binary_search pivot (:6-47); -1 when no site has start <= pos < end
+__device__ int bisect_pivot(const int32_t* __restrict__ spos, int n, int32_t start, int32_t end) {
+    int lo = 0, hi = n - 1, plo = -1, phi = -1;
+    while (hi > -1) {
+        if (lo > hi) break;
+        if (lo == plo && hi == phi) break;
+        plo = lo; phi = hi;
+        const int mid = (hi + lo) / 2;
+        const int32_t x = spos[mid];
+        if (start <= x && x < end) return mid;
+        else if (x > start) hi = mid - 1;
+        else if (x < start) lo = mid + 1;
+    }
+    return -1;
+}
+
+// allele code of pair x at het site i relative to the site: bits0-1 finder (0 none,1 ref,2 alt),
+// bits2-3 target (needs the position in the PRIMARY read and base quality >= min)
+__device__ uint8_t allele_info(const ChainArgs& A, const Scratch& S, int64_t e0, int64_t row, char ref, char alt) {
+    if (e0 < 0) return 0;
+    const uint32_t h0 = hit_lookup(A, e0, row);
+    uint32_t h = h0;
+    if (!(h0 & 0xffffu)) {
+        const int64_t e1 = rd_mate(A.reads, e0);
+        if (e1 < 0) return 0;
+        h = hit_lookup(A, e1, row);
+        if (!(h & 0xffffu)) return 0;
+    }
+    const int q = (int)(h & 0xffffu) - 1;
+    if (q < 4 || q > A.readlen - 4) return 0;
+    if (!(h & (1u << 26))) return 0;                 // len(seq) > q + 1
+    const char c = hit_char(h);
+    const uint8_t code = c == ref ? 1 : (c == alt ? 2 : 0);
+    if (!code) return 0;
+    uint8_t out = code;
+    if ((h0 & 0xffffu) && (int)((h0 >> 16) & 0x7fu) >= A.min_bq) out |= code << 2;
+    return out;
+}
+
+__global__ void __launch_bounds__(CH_THREADS)
+chain_kernel(ChainArgs A) {
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const UnfzDnm dn = A.dnms[d];
+    const Scratch& S0 = A.S;
+    __shared__ int s_n, s_n2;
+
+    UnfzTally T;
+    T.n_dad_sites = T.n_mom_sites = T.n_dad_reads = T.n_mom_reads = 0;
+    T.cnv_dad = T.cnv_mom = 0;
+    T.has_record = 0;
+    T.status = 0;
+    const int nh = A.n_het[d], nc = A.n_cand[d];
+    if (dn.kind == UNFZ_KIND_SKIP || dn.rblk < 0 || nc <= 0 || dn.seg_hi <= dn.seg_lo) {
+        if (tid == 0) A.tally[d] = T;
+        return;
+    }
+    const int64_t lbase = A.seg_pair_off[dn.seg_lo];
+    const int32_t* H = A.het_list + lbase;
+    const uint32_t* C = A.cand_list + lbase;
+    const int64_t* off = A.off;
+    const int64_t n1 = (int64_t)A.n_dnms + 1;
+    const int64_t o_slot = off[0 * n1 + d], o_inc = off[1 * n1 + d], o_seed = off[2 * n1 + d];
+    const int64_t o_sinc = off[3 * n1 + d], o_het = off[4 * n1 + d], o_cand = off[5 * n1 + d];
+    const int64_t cap_inc = off[1 * n1 + d + 1] - o_inc, cap_seed = off[2 * n1 + d + 1] - o_seed;
+    const int64_t cap_sinc = off[3 * n1 + d + 1] - o_sinc;
+
+    // per-DNM views
+    int32_t* prim = S0.prim + o_slot; uint32_t* ord = S0.ord + o_slot; int32_t* lvl = S0.lvl + o_slot;
+    int32_t* fpos = S0.fpos + o_slot; int32_t* icnt = S0.icnt + o_slot;
+    unsigned long long* minkey = S0.minkey + o_slot; int32_t* tmp = S0.tmp + o_slot;
+    uint8_t* label = A.slot_label + o_slot; uint8_t* evid = A.slot_evid + o_slot;
+    int32_t* inc_r = S0.inc_r + o_inc; int32_t* inc_x = S0.inc_x + o_inc; int32_t* inc_site = S0.inc_site + o_inc;
+    int32_t* inc_sidx = S0.inc_sidx + o_inc; uint8_t* inc_al = S0.inc_al + o_inc;
+    int32_t* seed_r = S0.seed_r + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed;
+    int32_t* sinc_x = S0.sinc_x + o_sinc; int32_t* sinc_site = S0.sinc_site + o_sinc;
+    int32_t* sinc_sidx = S0.sinc_sidx + o_sinc; uint8_t* sinc_al = S0.sinc_al + o_sinc;
+    int32_t* spos = S0.spos + o_het; uint8_t* sref = S0.sref + o_het; uint8_t* salt = S0.salt + o_het;
+    int32_t* site_off = S0.site_off + o_het + d;
+    unsigned long long* bestkey = S0.bestkey + o_het; uint8_t* best_info = S0.best_info + o_het;
+    int32_t* site_cnt = S0.site_cnt + o_het; int32_t* site_base = S0.site_base + o_het;
+    int32_t* cpos = S0.cpos + o_cand;
+    uint8_t* cev = A.cand_evid + lbase;
+
+    const UnfzReadCols& R = A.reads;
+    const int64_t blk_lo = R.blk_off[dn.rblk], blk_hi = R.blk_off[dn.rblk + 1];
+    const int64_t maxspan = A.blk_maxspan[dn.rblk];
+    const int64_t wlo = A.win_lo[d], whi = A.win_hi[d];
+    const int W = (int)(whi - wlo);
+
+    // canonical window slot of the pair a read belongs to
+    auto canon = [&](int64_t r) -> int {
+        const int64_t m = rd_mate(R, r);
+        const int64_t c = (m >= wlo && m < whi && m < r) ? m : r;
+        return (int)(c - wlo);
+    };
+
+    for (int x = tid; x < W; x += CH_THREADS) { label[x] = 0; evid[x] = 0; prim[x] = -1; lvl[x] = -1; icnt[x] = 0; fpos[x] = -1; ord[x] = 0; tmp[x] = 0; }
+    for (int i = tid; i < nh; i += CH_THREADS) {
+        const int64_t row = H[i];
+        spos[i] = __ldg(A.sites.pos + row);
+        sref[i] = __ldg(A.sites.ref + row);
+        salt[i] = __ldg(A.sites.alt + row);
+    }
+    for (int j = tid; j < nc; j += CH_THREADS) {
+        cpos[j] = __ldg(A.sites.pos + (int64_t)(C[j] & 0x3fffffffu));   // cand_evid is zeroed by the caller
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase 1: seed reads
+    int n_seed = 0;
+    if (dn.kind == UNFZ_KIND_SNV || dn.kind == UNFZ_KIND_INDEL) {
+        // fetch(chrom, pos-1, pos+1); after a failed fetch the reference retries with (pos, pos+1) (Q24)
+        const int64_t flo = (dn.flags & 8) ? (int64_t)dn.pos : (int64_t)dn.pos - 1;
+        const int64_t lo = lb_start(R, blk_lo, blk_hi, flo - maxspan + 1);
+        const int64_t hi = lb_start(R, lo, blk_hi, (int64_t)dn.pos + 1);
+        for (int64_t base = lo; base < hi; base += CH_THREADS) {
+            const int64_t r = base + tid;
+            int hap = 0;
+            if (r < hi && (int64_t)A.rsum[r].end > flo && pair_ok(A, r, false))
+                hap = dn.kind == UNFZ_KIND_SNV ? seed_snv(A, dn, r) : seed_indel(A, dn, r);
+            int tot;
+            const int k = block_prefix(hap != 0, &tot);
+            if (hap && n_seed + k < cap_seed) { seed_r[n_seed + k] = (int32_t)r; seed_hap[n_seed + k] = (uint8_t)hap; }
+            n_seed += tot;
+        }
+        if (n_seed > cap_seed) { n_seed = (int)cap_seed; T.status |= 1; }
+    }
+    __syncthreads();
+
+    int n_inc = 0, n_sinc = 0;
+    if (A.no_extended) {
+        for (int k = tid; k < n_seed; k += CH_THREADS) {
+            const int64_t r = seed_r[k];
+            const int x = canon(r);
+            label[x] |= seed_hap[k];       // one seed entry per pair in practice; benign if repeated
+            prim[x] = (int32_t)r;
+        }
+        __syncthreads();
+    } else {
+        // ------------------------------------------------------------ phase 2: het-site incidences
+        for (int i = 0; i < nh; ++i) {
+            const int32_t p = spos[i];
+            if (tid == 0) site_off[i] = n_inc;
+            const int64_t lo = lb_start(R, blk_lo, blk_hi, (int64_t)p - maxspan + 1);
+            const int64_t hi = lb_start(R, lo, blk_hi, (int64_t)p + 1);
+            int n_fetched = 0;
+            for (int64_t base = lo; base < hi; base += CH_THREADS) {
+                const int64_t r = base + tid;
+                const bool ov = r < hi && A.rsum[r].end > p;
+                int tot_ov;
+                const int idx = n_fetched + block_prefix(ov, &tot_ov);
+                n_fetched += tot_ov;
+                const bool ok = ov && idx <= A.ext_goal && pair_ok(A, r, true);
+                int tot;
+                const int k = n_inc + block_prefix(ok, &tot);
+                if (ok && k < cap_inc) {
+                    const int x = canon(r);
+                    inc_r[k] = (int32_t)r;
+                    inc_x[k] = x;
+                    inc_site[k] = i;
+                    inc_sidx[k] = icnt[x];
+                    icnt[x] += 1;
+                    prim[x] = (int32_t)r;          // last writer wins (Q18); sites are sequential
+                }
+                n_inc += tot;
+                __syncthreads();
+            }
+        }
+        if (n_inc > cap_inc) { n_inc = (int)cap_inc; T.status |= 2; }
+        if (tid == 0) site_off[nh] = n_inc;
+        __syncthreads();
+
+        // ------------------------------------------------------------ phase 3: seed registration
+        if (tid == 0) {
+            int ns = 0;
+            uint32_t order_alt = 0, order_ref = 0;
+            // level-0 iteration order: "alt" list first, then "ref" (Q19); position = first entry
+            for (int k = 0; k < n_seed; ++k) {
+                const int x = canon(seed_r[k]);
+                if (seed_hap[k] == 2 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (0u << 24) | order_alt++; }
+            }
+            for (int k = 0; k < n_seed; ++k) {
+                const int x = canon(seed_r[k]);
+                if (seed_hap[k] == 1 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (1u << 24) | order_ref++; }
+            }
+            // registration order: "ref" seeds, then "alt" seeds; each fetched read then its mate
+            for (int pass = 1; pass <= 2; ++pass) {
+                for (int k = 0; k < n_seed; ++k) {
+                    if (seed_hap[k] != pass) continue;
+                    const int64_t r = seed_r[k];
+                    const int x = canon(r);
+                    label[x] |= (uint8_t)pass;
+                    const int64_t ents[2] = {r, (int64_t)rd_mate(R, r)};
+                    for (int t = 0; t < 2; ++t) {
+                        const int64_t e = ents[t];
+                        prim[x] = (int32_t)e;
+                        if (nh == 0) continue;
+                        const int32_t st = rd_start(R, e), en = A.rsum[e].end;
+                        const int piv = bisect_pivot(spos, nh, st, en);
+                        if (piv < 0) continue;
+                        auto push = [&](int i) {
+                            if (ns < cap_sinc) { sinc_x[ns] = x; sinc_site[ns] = i; sinc_sidx[ns] = icnt[x]; }
+                            icnt[x] += 1;
+                            ++ns;
+                        };
+                        push(piv);
+                        for (int j = piv + 1; j < nh && st <= spos[j] && spos[j] <= en; ++j) push(j);
+                        for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) push(j);
+                    }
+                }
+            }
+            s_n = ns;
+        }
+        __syncthreads();
+        n_sinc = s_n;
+        if (n_sinc > cap_sinc) { n_sinc = (int)cap_sinc; T.status |= 4; }
+
+        // ------------------------------------------------------------ phase 3.5: allele codes
+        for (int k = tid; k < n_inc; k += CH_THREADS) {
+            const int i = inc_site[k];
+            inc_al[k] = allele_info(A, S0, (int64_t)prim[inc_x[k]], (int64_t)H[i], (char)sref[i], (char)salt[i]);
+        }
+        for (int k = tid; k < n_sinc; k += CH_THREADS) {
+            const int i = sinc_site[k];
+            sinc_al[k] = allele_info(A, S0, (int64_t)prim[sinc_x[k]], (int64_t)H[i], (char)sref[i], (char)salt[i]);
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------ phase 4: level-synchronous BFS
+        for (int level = 0;; ++level) {
+            for (int i = tid; i < nh; i += CH_THREADS) { bestkey[i] = KEY_NONE; site_cnt[i] = 0; }
+            for (int x = tid; x < W; x += CH_THREADS) minkey[x] = KEY_NONE;
+            __syncthreads();
+            // a. best finder key per site
+            for (int k = tid; k < n_inc + n_sinc; k += CH_THREADS) {
+                const bool sd = k >= n_inc;
+                const int kk = sd ? k - n_inc : k;
+                const int x = sd ? sinc_x[kk] : inc_x[kk];
+                if (lvl[x] != level) continue;
+                const uint8_t al = sd ? sinc_al[kk] : inc_al[kk];
+                if (!(al & 3)) continue;
+                const int i = sd ? sinc_site[kk] : inc_site[kk];
+                if (spos[i] == fpos[x]) continue;
+                const unsigned long long key = ((unsigned long long)ord[x] << 20) | (unsigned)(sd ? sinc_sidx[kk] : inc_sidx[kk]);
+                atomicMin(bestkey + i, key);
+            }
+            __syncthreads();
+            for (int k = tid; k < n_inc + n_sinc; k += CH_THREADS) {
+                const bool sd = k >= n_inc;
+                const int kk = sd ? k - n_inc : k;
+                const int x = sd ? sinc_x[kk] : inc_x[kk];
+                if (lvl[x] != level) continue;
+                const uint8_t al = sd ? sinc_al[kk] : inc_al[kk];
+                if (!(al & 3)) continue;
+                const int i = sd ? sinc_site[kk] : inc_site[kk];
+                if (spos[i] == fpos[x]) continue;
+                const unsigned long long key = ((unsigned long long)ord[x] << 20) | (unsigned)(sd ? sinc_sidx[kk] : inc_sidx[kk]);
+                if (key == bestkey[i]) {
+                    const uint8_t lab = label[x];
+                    const uint8_t fh = (lab & 2) ? 2 : 1;       // level 0: the "alt" visit comes first
+                    best_info[i] = (uint8_t)((fh << 2) | (al & 3));
+                }
+            }
+            __syncthreads();
+            // b. earliest claiming key per unlabelled pair
+            for (int k = tid; k < n_inc; k += CH_THREADS) {
+                const int x = inc_x[k];
+                if (label[x] != 0 || !(inc_al[k] >> 2)) continue;
+                const unsigned long long bk = bestkey[inc_site[k]];
+                if (bk != KEY_NONE) atomicMin(minkey + x, bk);
+            }
+            __syncthreads();
+            // c. claim, one warp per site, in the order of the site's read list
+            for (int i = warp; i < nh; i += CH_WARPS) {
+                const unsigned long long bk = bestkey[i];
+                if (bk == KEY_NONE) continue;
+                const int k0 = site_off[i], k1 = site_off[i + 1];
+                int cnt = 0;
+                for (int kb = k0; kb < k1; kb += 32) {
+                    const int k = kb + lane;
+                    bool claim = false;
+                    int x = 0;
+                    if (k < k1) {
+                        x = inc_x[k];
+                        claim = label[x] == 0 && (inc_al[k] >> 2) && minkey[x] == bk;
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, claim);
+                    if (claim) {
+                        const uint8_t info = best_info[i];
+                        const uint8_t fh = info >> 2, fa = info & 3, ta = inc_al[k] >> 2;
+                        const uint8_t nh_ = (ta == fa) ? fh : (uint8_t)(3 - fh);
+                        tmp[x] = (i << 8) | (nh_ << 4) | 1;
+                        ord[x] = (uint32_t)(cnt + __popc(b & ((1u << lane) - 1u)));   // rank inside the site
+                    }
+                    cnt += __popc(b);
+                }
+                if (lane == 0) site_cnt[i] = cnt;
+            }
+            __syncthreads();
+            // d. order of the sites by key -> base offsets
+            int assigned = 0;
+            for (int i = tid; i < nh; i += CH_THREADS) {
+                int base = 0;
+                const unsigned long long bk = bestkey[i];
+                if (site_cnt[i] > 0)
+                    for (int j = 0; j < nh; ++j)
+                        if (site_cnt[j] > 0 && bestkey[j] < bk) base += site_cnt[j];
+                site_base[i] = base;
+                assigned += site_cnt[i];
+            }
+            assigned = block_sum(assigned);
+            if (assigned == 0) break;
+            // e. commit the new level
+            for (int k = tid; k < n_inc; k += CH_THREADS) {
+                const int x = inc_x[k];
+                if (label[x] != 0) continue;
+                const int t = tmp[x];
+                if (!(t & 1) || (t >> 8) != inc_site[k] || minkey[x] != bestkey[inc_site[k]] || !(inc_al[k] >> 2)) continue;
+                const int i = t >> 8;
+                const uint8_t nhap = (t >> 4) & 3;
+                const uint32_t seq = (uint32_t)site_base[i] + ord[x];
+                ord[x] = ((nhap == 1 ? 0u : 1u) << 24) | seq;       // deeper levels: "ref" list first
+                lvl[x] = level + 1;
+                fpos[x] = spos[i];
+                tmp[x] = 0;
+                label[x] = nhap;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+
+    // ---------------------------------------------------------------- phase 5: matching + evidence
+    int has_rec = 0;
+    for (int x = tid; x < W; x += CH_THREADS) {
+        const uint8_t lab = label[x];
+        if (!lab || prim[x] < 0) continue;
+        const int64_t e0 = prim[x];
+        const int64_t ents[2] = {e0, (int64_t)rd_mate(R, e0)};
+        uint8_t ev = 0;
+        for (int t = 0; t < 2; ++t) {
+            const int64_t e = ents[t];
+            if (e < 0) continue;
+            const int32_t st = rd_start(R, e), en = A.rsum[e].end;
+            int lb = 0, hi = nc;
+            while (lb < hi) { const int mid = (lb + hi) >> 1; if (cpos[mid] < st) lb = mid + 1; else hi = mid; }
+            if (lb >= nc || cpos[lb] >= en) continue;           // binary_search finds nothing
+            int ub = lb;
+            while (ub < nc && cpos[ub] <= en) ++ub;              // neighbour rule (Q16)
+            bool consistent = true;
+            for (int j = lb + 1; j < ub; ++j)
+                if ((C[j] ^ C[lb]) & 0x80000000u) { consistent = false; break; }
+            if (!consistent) continue;
+            has_rec = 1;
+            for (int j = lb; j < ub; ++j) {
+                const uint32_t cw = C[j];
+                const int64_t row = cw & 0x3fffffffu;
+                const uint32_t h = hit_lookup(A, e, row);
+                if (!(h & 0xffffu)) continue;
+                const char c = hit_char(h);
+                bool origin_ref;
+                if (c == (char)__ldg(A.sites.ref + row)) origin_ref = true;
+                else if (c == (char)__ldg(A.sites.alt + row)) origin_ref = false;
+                else continue;
+                const bool alt_is_dad = (cw & 0x80000000u) != 0;
+                uint8_t bits = 0;
+                for (int hp = 1; hp <= 2; ++hp) {
+                    if (!(lab & hp)) continue;
+                    const bool to_alt = origin_ref == (hp == 1);
+                    bits |= (to_alt == alt_is_dad) ? 1 : 2;       // 1: dad, 2: mom
+                }
+                ev |= bits;
+                unsigned* wp = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(cev + j) & ~(uintptr_t)3);
+                atomicOr(wp, (unsigned)bits << (8 * (reinterpret_cast<uintptr_t>(cev + j) & 3)));
+            }
+        }
+        evid[x] = ev;
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase 6: tally
+    int ds = 0, ms = 0, dr = 0, mr = 0;
+    for (int j = tid; j < nc; j += CH_THREADS) {
+        const uint8_t b = cev[j];
+        for (int bit = 1; bit <= 2; ++bit) {
+            if (!(b & bit)) continue;
+            bool first = true;                      // unique str(pos): count the first duplicate only
+            for (int j2 = j - 1; j2 >= 0 && cpos[j2] == cpos[j]; --j2)
+                if (cev[j2] & bit) { first = false; break; }
+            if (first) { if (bit == 1) ++ds; else ++ms; }
+        }
+    }
+    for (int x = tid; x < W; x += CH_THREADS) {
+        dr += evid[x] & 1;
+        mr += (evid[x] >> 1) & 1;
+    }
+    ds = block_sum(ds); ms = block_sum(ms); dr = block_sum(dr); mr = block_sum(mr);
+    has_rec = block_sum(has_rec);
+    if (tid == 0) {
+        T.n_dad_sites = ds; T.n_mom_sites = ms; T.n_dad_reads = dr; T.n_mom_reads = mr;
+        T.has_record = has_rec > 0;
+        A.tally[d] = T;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sizing: read window and scratch needs per DNM (one thread per DNM)
+// ------------------------------------------------------------------------------------------------
+__global__ void chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_t* __restrict__ seg_pair_off,
+                                  UnfzSiteCols sites, UnfzReadCols reads, const UnfzReadSum* __restrict__ rsum,
+                                  const int32_t* __restrict__ blk_maxspan, const int32_t* __restrict__ het_list,
+                                  const int32_t* __restrict__ n_het, const uint32_t* __restrict__ cand_list,
+                                  const int32_t* __restrict__ n_cand, int32_t* __restrict__ win_lo,
+                                  int32_t* __restrict__ win_hi, int64_t* __restrict__ need) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_dnms) return;
+    const UnfzDnm dn = dnms[d];
+    int64_t nd[6] = {0, 0, 0, 0, 0, 0};
+    int32_t wl = 0, wh = 0;
+    const int nh = n_het[d], nc = n_cand[d];
+    if (!(dn.kind == UNFZ_KIND_SKIP || dn.rblk < 0 || nc <= 0 || dn.seg_hi <= dn.seg_lo)) {
+        const int64_t lbase = seg_pair_off[dn.seg_lo];
+        const int32_t* H = het_list + lbase;
+        const uint32_t* C = cand_list + lbase;
+        const int64_t blk_lo = reads.blk_off[dn.rblk], blk_hi = reads.blk_off[dn.rblk + 1];
+        const int64_t maxspan = blk_maxspan[dn.rblk];
+        int64_t minp = (int64_t)dn.pos - 1, maxp = (int64_t)dn.pos + 1;
+        if (nh > 0) {
+            minp = min(minp, (int64_t)sites.pos[H[0]]);
+            maxp = max(maxp, (int64_t)sites.pos[H[nh - 1]] + 1);
+        }
+        minp = min(minp, (int64_t)sites.pos[C[0] & 0x3fffffffu]);
+        maxp = max(maxp, (int64_t)sites.pos[C[nc - 1] & 0x3fffffffu] + 1);
+        const int64_t lo = lb_start(reads, blk_lo, blk_hi, minp - maxspan + 1);
+        const int64_t hi = lb_start(reads, lo, blk_hi, maxp);
+        wl = (int32_t)lo; wh = (int32_t)hi;
+        nd[0] = hi - lo;
+        for (int i = 0; i < nh; ++i) {
+            const int64_t p = sites.pos[H[i]];
+            const int64_t a = lb_start(reads, lo, hi, p - maxspan + 1);
+            const int64_t b = lb_start(reads, a, hi, p + 1);
+            nd[1] += b - a;
+        }
+        const int64_t a = lb_start(reads, lo, hi, (int64_t)dn.pos - 1 - maxspan + 1);
+        const int64_t b = lb_start(reads, a, hi, (int64_t)dn.pos + 1);
+        nd[2] = b - a;
+        // every seed entry (read and mate) registers the het sites with start <= pos <= end
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t ents[2] = {r, (int64_t)reads.hdr[r].mate};
+            for (int t = 0; t < 2; ++t) {
+                const int64_t e = ents[t];
+                if (e < 0) continue;
+                const int64_t st = reads.hdr[e].start, en = rsum[e].end;
+                int l = 0, h = nh;
+                while (l < h) { const int mid = (l + h) >> 1; if (sites.pos[H[mid]] < st) l = mid + 1; else h = mid; }
+                int u = l; h = nh;
+                while (u < h) { const int mid = (u + h) >> 1; if (sites.pos[H[mid]] <= en) u = mid + 1; else h = mid; }
+                nd[3] += u - l;
+            }
+        }
+        nd[4] = nh;
+        nd[5] = nc;
+    }
+    win_lo[d] = wl;
+    win_hi[d] = wh;
+    for (int k = 0; k < 6; ++k) need[(int64_t)k * n_dnms + d] = nd[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// final call: unfazed.py summarize_record :190-334 on counts
+// ------------------------------------------------------------------------------------------------
+__device__ UnfzCall summarize_one(const UnfzDnm& dn, int nd_reads, int nm_reads, int nd_sites, int nm_sites,
+                                  int cd, int cm, bool has_read_rec, bool has_cnv_rec, int ratio, bool include_ambiguous) {
+    UnfzCall c;
+    c.origin = UNFZ_ORIGIN_NONE; c.evidence_count = 0; c.evidence_types = 0; c.emitted = 0;
+    const bool autoph = dn.flags & 1;
+    const bool sv_quirk = dn.flags & 4;      // Q8: "SEX-CHROM,SEX-CHROM", cnv sites "NA" (len 2)
+    if (autoph && !sv_quirk) {
+        c.origin = (dn.flags & 2) ? UNFZ_ORIGIN_DAD : UNFZ_ORIGIN_MOM;
+        c.evidence_count = 1;
+        c.evidence_types = UNFZ_EV_SEX_CHROM;
+        c.emitted = 1;
+        return c;
+    }
+    if (!autoph && !has_read_rec && !has_cnv_rec) return c;
+    if (sv_quirk) { nd_reads = nm_reads = nd_sites = nm_sites = 0; cd = cm = 2; }
+    if (!has_read_rec && !sv_quirk) nd_reads = nm_reads = nd_sites = nm_sites = 0;
+    if (!has_cnv_rec && !sv_quirk) cd = cm = 0;
+    int origin = UNFZ_ORIGIN_NONE, count = 0, types = 0;
+    bool ambig = false;
+    if (nd_reads > 0 && nd_reads >= ratio * nm_reads) { origin = UNFZ_ORIGIN_DAD; count = nd_sites; types |= UNFZ_EV_READBACKED; }
+    else if (nm_reads > 0 && nm_reads >= ratio * nd_reads) { origin = UNFZ_ORIGIN_MOM; count = nm_sites; types |= UNFZ_EV_READBACKED; }
+    else if (nd_reads > 0 && nm_reads > 0) { origin = UNFZ_ORIGIN_BOTH; count = nd_reads + nm_reads; types |= UNFZ_EV_AMBIG_READBACKED; ambig = true; }
+    if (cd > 0 && cd >= ratio * cm) {
+        if (origin == UNFZ_ORIGIN_MOM && !(types & UNFZ_EV_READBACKED)) {
+            origin = UNFZ_ORIGIN_NONE; count += cd + cm; types = UNFZ_EV_AMBIG_BOTH; ambig = true;
+        } else {
+            origin = UNFZ_ORIGIN_DAD; count = cd;
+            if (types & UNFZ_EV_AMBIG_READBACKED) { types &= ~UNFZ_EV_AMBIG_READBACKED; ambig = false; }
+            types |= UNFZ_EV_ALLELE_BALANCE;
+        }
+    } else if (cm > 0 && cm >= ratio * cd) {
+        if (origin == UNFZ_ORIGIN_DAD && !(types & UNFZ_EV_READBACKED)) {
+            origin = UNFZ_ORIGIN_NONE; count += cd + cm; types = UNFZ_EV_AMBIG_BOTH; ambig = true;
+        } else {
+            origin = UNFZ_ORIGIN_MOM; count = cm;
+            if (types & UNFZ_EV_AMBIG_READBACKED) types &= ~UNFZ_EV_AMBIG_READBACKED;
+            types |= UNFZ_EV_ALLELE_BALANCE;
+        }
+    } else if ((cd + cm) > 0 && !(types & UNFZ_EV_READBACKED)) {
+        origin = UNFZ_ORIGIN_NONE; count += cd + cm; types |= UNFZ_EV_AMBIG_ALLELE_BAL; ambig = true;
+    }
+    c.origin = origin; c.evidence_count = count; c.evidence_types = types;
+    c.emitted = ((origin == UNFZ_ORIGIN_NONE || ambig) && !include_ambiguous) ? 0 : 1;
+    return c;
+}
+
+__global__ void summarize_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const UnfzTally* __restrict__ tally,
+                                 const int32_t* __restrict__ cnv_dad, const int32_t* __restrict__ cnv_mom,
+                                 const int32_t* __restrict__ n_cand, int ratio, UnfzCall* __restrict__ strict,
+                                 UnfzCall* __restrict__ ambiguous) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_dnms) return;
+    const UnfzDnm dn = dnms[d];
+    const UnfzTally t = tally[d];
+    int cd = 0, cm = 0;
+    bool has_cnv = false;
+    if (dn.cnv_entry >= 0) {
+        cd = cnv_dad[dn.cnv_entry];
+        cm = cnv_mom[dn.cnv_entry];
+        has_cnv = n_cand[dn.cnv_entry] > 0;
+    }
+    strict[d] = summarize_one(dn, t.n_dad_reads, t.n_mom_reads, t.n_dad_sites, t.n_mom_sites, cd, cm,
+                              t.has_record != 0, has_cnv, ratio, false);
+    ambiguous[d] = summarize_one(dn, t.n_dad_reads, t.n_mom_reads, t.n_dad_sites, t.n_mom_sites, cd, cm,
+                                 t.has_record != 0, has_cnv, ratio, true);
+}
+
+template <typename T>
+char* carve(char*& p, int64_t n) {
+    char* out = p;
+    p += ((n * (int64_t)sizeof(T)) + 15) & ~(int64_t)15;
+    return out;
+}
+
+Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_t sincs, int64_t hets, int64_t cands,
+                  int64_t n_dnms, int64_t* total) {
+    Scratch S;
+    char* p = base;
+    S.prim = (int32_t*)carve<int32_t>(p, slots); S.ord = (uint32_t*)carve<uint32_t>(p, slots);
+    S.lvl = (int32_t*)carve<int32_t>(p, slots); S.fpos = (int32_t*)carve<int32_t>(p, slots);
+    S.icnt = (int32_t*)carve<int32_t>(p, slots); S.minkey = (unsigned long long*)carve<unsigned long long>(p, slots);
+    S.tmp = (int32_t*)carve<int32_t>(p, slots);
+    S.inc_r = (int32_t*)carve<int32_t>(p, incs); S.inc_x = (int32_t*)carve<int32_t>(p, incs);
+    S.inc_site = (int32_t*)carve<int32_t>(p, incs); S.inc_sidx = (int32_t*)carve<int32_t>(p, incs);
+    S.inc_al = (uint8_t*)carve<uint8_t>(p, incs);
+    S.seed_r = (int32_t*)carve<int32_t>(p, seeds); S.seed_hap = (uint8_t*)carve<uint8_t>(p, seeds);
+    S.sinc_x = (int32_t*)carve<int32_t>(p, sincs); S.sinc_site = (int32_t*)carve<int32_t>(p, sincs);
+    S.sinc_sidx = (int32_t*)carve<int32_t>(p, sincs); S.sinc_al = (uint8_t*)carve<uint8_t>(p, sincs);
+    S.spos = (int32_t*)carve<int32_t>(p, hets); S.sref = (uint8_t*)carve<uint8_t>(p, hets);
+    S.salt = (uint8_t*)carve<uint8_t>(p, hets); S.site_off = (int32_t*)carve<int32_t>(p, hets + n_dnms + 1);
+    S.bestkey = (unsigned long long*)carve<unsigned long long>(p, hets); S.best_info = (uint8_t*)carve<uint8_t>(p, hets);
+    S.site_cnt = (int32_t*)carve<int32_t>(p, hets); S.site_base = (int32_t*)carve<int32_t>(p, hets);
+    S.cpos = (int32_t*)carve<int32_t>(p, cands);
+    *total = (int64_t)(p - base);
+    return S;
+}
+
+}  // namespace
+
+extern "C" int64_t unfz_chain_scratch_bytes(int64_t slots, int64_t incs, int64_t seeds, int64_t seed_incs,
+                                            int64_t het_sites, int64_t cand_sites, int64_t n_dnms) {
+    int64_t total = 0;
+    carve_all(nullptr, slots, incs, seeds, seed_incs, het_sites, cand_sites, n_dnms, &total);
+    return total + 256;
+}
+
+extern "C" int unfz_chain_size(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
+                               const int64_t* seg_pair_off, const UnfzSiteCols* sites, const UnfzReadCols* reads,
+                               const UnfzReadSum* rsum, const int32_t* blk_maxspan, const int32_t* het_list,
+                               const int32_t* n_het, const uint32_t* cand_list, const int32_t* n_cand,
+                               int32_t* win_lo, int32_t* win_hi, int64_t* need, void* stream) {
+    (void)segs;
+    if (n_dnms <= 0) return 0;
+    chain_size_kernel<<<(n_dnms + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        dnms, n_dnms, seg_pair_off, *sites, *reads, rsum, blk_maxspan, het_list, n_het, cand_list, n_cand, win_lo, win_hi, need);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
+                                const int64_t* seg_pair_off, const UnfzSiteCols* sites, const UnfzReadCols* reads,
+                                const UnfzReadSum* rsum, const int32_t* blk_maxspan, const uint32_t* hits,
+                                const int32_t* mark_prefix, const int32_t* het_list, const int32_t* n_het,
+                                const uint32_t* cand_list, const int32_t* n_cand, const uint8_t* alleles,
+                                const int32_t* win_lo, const int32_t* win_hi, const int64_t* off,
+                                const int64_t* h_totals, const UnfzParams* hp, void* scratch, int64_t scratch_bytes,
+                                uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid, UnfzTally* tally,
+                                void* stream) {
+    if (n_dnms <= 0) return 0;
+    ChainArgs A;
+    A.dnms = dnms; A.n_dnms = n_dnms; A.segs = segs; A.seg_pair_off = seg_pair_off;
+    A.sites = *sites; A.reads = *reads; A.rsum = rsum; A.blk_maxspan = blk_maxspan; A.hits = hits; A.mp = mark_prefix;
+    A.het_list = het_list; A.n_het = n_het; A.cand_list = cand_list; A.n_cand = n_cand; A.alleles = alleles;
+    A.win_lo = win_lo; A.win_hi = win_hi; A.off = off;
+    A.readlen = hp->readlen;
+    const double bq = hp->min_gt_qual;
+    A.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));
+    A.ext_goal = hp->ext_read_goal;
+    A.no_extended = hp->no_extended;
+    A.slot_label = slot_label; A.slot_evid = slot_evid; A.cand_evid = cand_evid; A.tally = tally;
+    int64_t total = 0;
+    uintptr_t base = ((uintptr_t)scratch + 255) & ~(uintptr_t)255;
+    A.S = carve_all((char*)base, h_totals[0], h_totals[1], h_totals[2], h_totals[3], h_totals[4], h_totals[5], n_dnms, &total);
+    if ((int64_t)(base - (uintptr_t)scratch) + total > scratch_bytes) return unfz_fail(ctx, -20, "chain scratch too small");
+    chain_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int unfz_summarize(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms, const UnfzTally* tally,
+                              const int32_t* cnv_dad, const int32_t* cnv_mom, const int32_t* n_cand,
+                              const UnfzParams* hp, UnfzCall* calls_strict, UnfzCall* calls_ambiguous, void* stream) {
+    if (n_dnms <= 0) return 0;
+    summarize_kernel<<<(n_dnms + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        dnms, n_dnms, tally, cnv_dad, cnv_mom, n_cand, hp->evidence_min_ratio, calls_strict, calls_ambiguous);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}

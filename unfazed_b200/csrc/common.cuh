@@ -1,0 +1,69 @@
+// Shared helpers for the sm_100a kernels of libunfazed_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/unfazed_sm100.h"
+
+struct UnfzCtx {
+    int device;
+    int sm_count;
+    char err[512];
+};
+
+#define UNFZ_CHECK(ctx, expr)                                                                   \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #expr, \
+                     cudaGetErrorString(_e));                                                   \
+            return -(int)_e - 1000;                                                             \
+        }                                                                                       \
+    } while (0)
+
+#define UNFZ_LAUNCH_CHECK(ctx) UNFZ_CHECK(ctx, cudaGetLastError())
+
+static inline int unfz_fail(UnfzCtx* ctx, int code, const char* msg) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    return code;
+}
+
+// first index i in [lo, hi) with a[i] >= v
+template <typename T, typename V>
+__device__ __forceinline__ int64_t lower_bound_dev(const T* __restrict__ a, int64_t lo, int64_t hi, V v) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first index i in [lo, hi) with a[i] > v
+template <typename T, typename V>
+__device__ __forceinline__ int64_t upper_bound_dev(const T* __restrict__ a, int64_t lo, int64_t hi, V v) {
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int64_t read_qoff(const UnfzRead& h) {
+    return (int64_t)h.qoff_lo | ((int64_t)h.qoff_hi << 32);
+}
+
+// 16-byte header halves through the read-only path
+__device__ __forceinline__ UnfzRead load_read(const UnfzRead* __restrict__ p) {
+    union { UnfzRead r; int4 v[2]; } u;
+    const int4* q = reinterpret_cast<const int4*>(p);
+    u.v[0] = __ldg(q);
+    u.v[1] = __ldg(q + 1);
+    return u.r;
+}
+
+__device__ __forceinline__ UnfzReadSum load_rsum(const UnfzReadSum* __restrict__ p) {
+    union { UnfzReadSum r; int4 v; } u;
+    u.v = __ldg(reinterpret_cast<const int4*>(p));
+    return u.r;
+}

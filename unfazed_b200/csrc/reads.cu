@@ -1,0 +1,324 @@
+// Read path, part 1: the streaming read scan (goodread + pair-independent filters + overlap counts)
+// and the read-by-site allele lookup.
+//
+// read_scan is the bandwidth kernel of the read path: per read it must see the 32 B header, the
+// CIGAR words and every quality byte.  Reads are stored in file order, so the quality bytes of a
+// tile of consecutive reads are one contiguous span: a single elected thread moves that span into
+// shared memory with TMA bulk copies (cp.async.bulk, completion on an mbarrier) while the other
+// threads walk their CIGARs; then every thread counts the low-quality bases of its own read out of
+// shared memory with 4-byte SIMD compares.  Several CTAs are resident per SM, so one CTA's bulk
+// copy overlaps the others' compute.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy wrappers (sm_90+; on sm_100a these lower to UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: read scan
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;                 // reads per tile
+constexpr int RS_QBUF = 48 * 1024;              // staged quality bytes per round
+constexpr int RS_SPOS = 128;                    // site positions staged per tile
+
+struct ScanParams {
+    int32_t min_mapq;
+    int32_t min_bq;      // clamped to [0,128]
+    int32_t readlen;
+};
+
+__device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, int beg, int end, uint32_t minq) {
+    // number of bytes b in s[beg,end) with (b & 0x7f) < minq; minq in [0,128]
+    int cnt = 0, i = beg;
+    const uint32_t m4 = minq * 0x01010101u;
+    while (i < end && (i & 3)) { cnt += (uint32_t)(s[i] & 0x7f) < minq; ++i; }
+    for (; i + 4 <= end; i += 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(s + i) & 0x7f7f7f7fu;
+        cnt += __popc(__vcmpltu4(w, m4)) >> 3;
+    }
+    for (; i < end; ++i) cnt += (uint32_t)(s[i] & 0x7f) < minq;
+    return cnt;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
+                 UnfzReadSum* __restrict__ out, int32_t* __restrict__ blk_maxspan) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* qbuf = smem;                                             // RS_QBUF + 16
+    int32_t* spos = reinterpret_cast<int32_t*>(smem + RS_QBUF + 16);  // RS_SPOS
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int64_t s_qa, s_qb, s_row_base, s_row_end;
+    __shared__ int32_t s_rb0;
+    __shared__ int32_t s_maxspan;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    const int64_t n = reads.n_reads;
+    const int64_t n_tiles = (n + RS_THREADS - 1) / RS_THREADS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r0 = tile * RS_THREADS;
+        const int64_t r = r0 + threadIdx.x;
+        const bool live = r < n;
+        UnfzRead h;
+        if (live) h = load_read(reads.hdr + r);
+        const int64_t q0 = live ? read_qoff(h) : 0;
+        const int L = live ? h.l_seq : 0;
+        if (threadIdx.x == 0) {
+            s_qa = q0;
+            s_rb0 = (int32_t)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r0) - 1);
+            s_maxspan = 0;
+        }
+        const int64_t last = min(r0 + RS_THREADS, n) - 1;
+        if (r == last) s_qb = q0 + L;
+        __syncthreads();
+        const int64_t qa = s_qa, qb = s_qb;
+        const int64_t ga = qa & ~(int64_t)15;
+        // round 0 of the quality staging is issued now so it overlaps the CIGAR walk below
+        int64_t chunk_lo = qb > qa ? ga : qb;
+        if (threadIdx.x == 0 && qb > qa) {
+            const uint32_t bytes = (uint32_t)min((int64_t)RS_QBUF, ((qb - chunk_lo) + 15) & ~(int64_t)15);
+            fence_proxy_async();
+            mbar_expect_tx(&bar, bytes);
+            tma_bulk_g2s(qbuf, reads.qual + chunk_lo, bytes, &bar);
+        }
+
+        // ---- block of this read, site rows of the tile ------------------------------------
+        int rb = s_rb0;
+        if (live && r >= reads.blk_off[rb + 1])
+            rb = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb, (int64_t)reads.n_blocks + 1, r) - 1);
+        const int sb = live ? reads.blk_sblk[rb] : -1;
+        if (threadIdx.x == 0) {
+            int64_t rowb = 0, rowe = 0;
+            if (sb >= 0) {
+                rowe = sites.blk_off[sb + 1];
+                rowb = lower_bound_dev(sites.pos, sites.blk_off[sb], rowe, h.start);
+            }
+            s_row_base = rowb;
+            s_row_end = rowe;
+        }
+        __syncthreads();
+        const int64_t row_base = s_row_base, row_end = s_row_end;
+        for (int i = threadIdx.x; i < RS_SPOS; i += RS_THREADS)
+            spos[i] = (row_base + i < row_end) ? __ldg(sites.pos + row_base + i) : 0x7fffffff;
+
+        // ---- header flags + CIGAR walk -----------------------------------------------------
+        int32_t end = 0;
+        uint32_t flags = 0;
+        int none_cnt = 0, non_m = 0;
+        if (live) {
+            end = h.start;
+            const uint32_t* cg = reads.cigar + h.cigar_off;
+            for (int k = 0; k < h.n_cigar; ++k) {
+                const uint32_t w = __ldg(cg + k);
+                const uint32_t op = w & 15u, ln = w >> 4;
+                if (op == 0 || op == 7 || op == 8 || op == 2 || op == 3) end += (int32_t)ln;
+                if (op == 1 || op == 4) none_cnt += (int)ln;
+                if (op != 0 && op != 7) ++non_m;
+            }
+            const uint32_t f = h.flag;
+            const bool base_ok = !(f & (0x200u | 0x4u | 0x400u | 0x100u | 0x800u | 0x8u)) &&
+                                 (int)h.mapq >= P.min_mapq && (h.aux & 1u);
+            if (base_ok) flags |= UNFZ_RS_GOOD_DISC;
+            if (none_cnt <= 5) flags |= UNFZ_RS_NONE_OK;
+            if (non_m <= 5) flags |= UNFZ_RS_EXT_OK;
+            long long ins = (long long)h.tlen - 2ll * P.readlen;
+            if (ins < 0) ins = -ins;
+            if ((double)ins <= reads.blk_cul[rb]) flags |= UNFZ_RS_INS_OK;
+            if ((f & 1u) && !(f & 8u) && h.mate >= 0) flags |= UNFZ_RS_HAS_MATE;
+            atomicMax(&s_maxspan, end - h.start);
+        }
+        __syncthreads();   // spos visible
+
+        // ---- marked-site overlap count -------------------------------------------------------
+        int32_t fmark = 0, cnt = 0;
+        if (live && sb >= 0) {
+            int64_t lbs, lbe;
+            if (rb == s_rb0) {
+                int lo = 0, hi = RS_SPOS;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h.start) lo = mid + 1; else hi = mid; }
+                int lo2 = lo; hi = RS_SPOS;
+                while (lo2 < hi) { int mid = (lo2 + hi) >> 1; if (spos[mid] < end) lo2 = mid + 1; else hi = mid; }
+                lbs = row_base + lo;
+                lbe = row_base + lo2;
+                if (lo2 == RS_SPOS) {     // ran off the staged window: finish in global memory
+                    if (lo == RS_SPOS) lbs = lower_bound_dev(sites.pos, row_base + RS_SPOS - 1, row_end, h.start);
+                    lbe = lower_bound_dev(sites.pos, lbs, row_end, end);
+                }
+            } else {
+                const int64_t a = sites.blk_off[sb], b = sites.blk_off[sb + 1];
+                lbs = lower_bound_dev(sites.pos, a, b, h.start);
+                lbe = lower_bound_dev(sites.pos, lbs, b, end);
+            }
+            fmark = __ldg(mark_prefix + lbs);
+            const int32_t c = __ldg(mark_prefix + lbe) - fmark;
+            cnt = c > 0xffff ? 0xffff : c;
+        }
+
+        // ---- low-quality bases out of the staged span ---------------------------------------
+        int low = 0;
+        while (chunk_lo < qb) {
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            const int64_t chunk_hi = chunk_lo + RS_QBUF;
+            if (live && L > 0) {
+                const int64_t a = max(q0, chunk_lo), b = min(q0 + (int64_t)L, min(chunk_hi, qb));
+                if (a < b) low += count_low_quals(qbuf, (int)(a - chunk_lo), (int)(b - chunk_lo), (uint32_t)P.min_bq);
+            }
+            chunk_lo = chunk_hi;
+            __syncthreads();     // everyone is done with qbuf
+            if (threadIdx.x == 0 && chunk_lo < qb) {
+                const uint32_t bytes = (uint32_t)min((int64_t)RS_QBUF, ((qb - chunk_lo) + 15) & ~(int64_t)15);
+                fence_proxy_async();
+                mbar_expect_tx(&bar, bytes);
+                tma_bulk_g2s(qbuf, reads.qual + chunk_lo, bytes, &bar);
+            }
+        }
+        if (live) {
+            // goodread(read): <= 10 low-quality bases and (Q3) <= 10 CIGAR operations
+            if ((flags & UNFZ_RS_GOOD_DISC) && low <= 10 && h.n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
+            UnfzReadSum o;
+            o.end = end;
+            o.fmark = fmark;
+            o.flags = (uint16_t)flags;
+            o.cnt = (uint16_t)cnt;
+            o.hoff = 0;
+            *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_maxspan > 0) {
+            // a tile can straddle blocks; attribute the span to every block it touches (conservative)
+            const int rb_last = (int)(upper_bound_dev(reads.blk_off, (int64_t)s_rb0, (int64_t)reads.n_blocks + 1, last) - 1);
+            for (int b = s_rb0; b <= rb_last; ++b) atomicMax(blk_maxspan + b, s_maxspan);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: read x marked-site allele lookup
+// ------------------------------------------------------------------------------------------------
+// query index of reference position p, or -1 (pysam get_reference_positions(full_length=True).index)
+__device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n_cigar, int32_t start, int32_t p) {
+    int32_t cur = start;
+    int q = 0;
+    for (int k = 0; k < n_cigar; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        const uint32_t op = w & 15u;
+        const int32_t ln = (int32_t)(w >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            if (p < cur + ln) return p >= cur ? q + (p - cur) : -1;
+            cur += ln; q += ln;
+        } else if (op == 1 || op == 4) {
+            q += ln;
+        } else if (op == 2 || op == 3) {
+            if (p < cur + ln) return -1;
+            cur += ln;
+        }
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256)
+read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
+                         const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
+                         uint32_t* __restrict__ hits) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= reads.n_reads) return;
+    const UnfzReadSum s = load_rsum(rsum + r);
+    if (s.cnt == 0) return;
+    const UnfzRead h = load_read(reads.hdr + r);
+    const int rb = (int)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r) - 1);
+    const int sb = reads.blk_sblk[rb];
+    if (sb < 0) return;
+    const int64_t b = sites.blk_off[sb + 1];
+    int64_t row = lower_bound_dev(sites.pos, sites.blk_off[sb], b, h.start);
+    const uint32_t* cg = reads.cigar + h.cigar_off;
+    const int64_t q0 = read_qoff(h);
+    int written = 0;
+    for (; row < b && written < s.cnt; ++row) {
+        const int32_t p = __ldg(sites.pos + row);
+        if (p >= s.end) break;
+        if (!__ldg(row_mark + row)) continue;
+        const int k = __ldg(mark_prefix + row) - s.fmark;
+        uint32_t word = 0;
+        const int q = cigar_qpos(cg, h.n_cigar, h.start, p);
+        if (q >= 0 && q < 0xffff) {
+            const int64_t g = q0 + q;
+            const uint32_t qb = __ldg(reads.qual + g);
+            const uint32_t code = (__ldg(reads.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
+            word = (uint32_t)(q + 1) | (qb << 16) | (code << 24) | ((q + 1 < h.l_seq) ? (1u << 26) : 0u);
+        }
+        if (k >= 0 && k < s.cnt) hits[(int64_t)s.hoff + k] = word;
+        ++written;
+    }
+}
+
+}  // namespace
+
+extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
+                              const int32_t* mark_prefix, const UnfzParams* hp, UnfzReadSum* out,
+                              int32_t* blk_maxspan, void* stream) {
+    if (reads->n_reads <= 0) return 0;
+    ScanParams P;
+    P.min_mapq = hp->min_map_qual;
+    double bq = hp->min_gt_qual;
+    P.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));
+    P.readlen = hp->readlen;
+    const size_t smem = RS_QBUF + 16 + RS_SPOS * sizeof(int32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        UNFZ_CHECK(ctx, cudaFuncSetAttribute(read_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t n_tiles = (reads->n_reads + RS_THREADS - 1) / RS_THREADS;
+    int64_t grid = (int64_t)ctx->sm_count * 4;     // 4 x ~49 KB of staging per SM
+    if (grid > n_tiles) grid = n_tiles;
+    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, blk_maxspan);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int unfz_read_site_alleles(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
+                                      const uint8_t* row_mark, const int32_t* mark_prefix,
+                                      const UnfzReadSum* rsum, uint32_t* hits, void* stream) {
+    if (reads->n_reads <= 0) return 0;
+    const int64_t blocks = (reads->n_reads + 255) / 256;
+    read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, hits);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}

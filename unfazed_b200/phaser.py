@@ -1,0 +1,193 @@
+"""Batch phasing over columnar tables: plan -> engine -> the reference's record dicts.
+
+This is the host-side mirror of ``snv_phaser.run_read_phasing`` (reference :206-299),
+``sv_phaser.phase_svs`` (:427-493) and ``informative_site_finder.find`` (:167-344) for a whole DNM
+list at once.  All arithmetic happens in the CUDA kernels; this file only plans windows and
+reshapes results.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib as L
+from .engine import BatchResult, DeviceReads, DeviceSites, Engine, make_params
+from .plan import (SNV_TYPES, SV_TYPES, Plan, SiteIndex, concat_plans, concordant_upper_lens,
+                   plan_find)
+from .schema import ReadTable, SiteTable
+
+
+def dnm_key(dn: dict) -> str:
+    """records key, snv_phaser.py:202."""
+    return "_".join([str(dn["chrom"]), str(dn["start"]), str(dn["end"]), dn["kid"], dn["vartype"]])
+
+
+class BatchPhaser:
+    def __init__(self, engine: Engine, sites: SiteTable, reads: Optional[ReadTable], pedigrees: dict,
+                 dsites: Optional[DeviceSites] = None, dreads: Optional[DeviceReads] = None):
+        self.engine = engine
+        self.sites, self.reads, self.ped = sites, reads, pedigrees
+        self.sidx = SiteIndex(sites)
+        self.dsites = dsites if dsites is not None else engine.upload_sites(sites)
+        self.dreads = dreads if dreads is not None else (engine.upload_reads(reads) if reads is not None else None)
+        self._cul_cache: Dict[tuple, np.ndarray] = {}
+
+    # -------------------------------------------------------------------------------------
+    def cul(self, readlen, insert_size_max_sample, stdevs) -> Optional[np.ndarray]:
+        if self.reads is None:
+            return None
+        key = (readlen, insert_size_max_sample, stdevs)
+        if key not in self._cul_cache:
+            self._cul_cache[key] = concordant_upper_lens(self.reads, readlen, insert_size_max_sample, stdevs)
+        return self._cul_cache[key]
+
+    def site_dicts(self, res: BatchResult, d: int, trio: int, with_kid_allele: bool):
+        """candidate_sites / het_sites of entry d in the reference's dict form."""
+        s = self.sites
+        kid, dad, mom = s.trios[trio]
+        hets = [{"pos": int(s.pos[r]), "ref_allele": chr(s.ref[r]), "alt_allele": chr(s.alt[r])}
+                for r in res.het_rows(d).tolist()]
+        cands = []
+        for w in res.cand_words(d).view(np.uint32).tolist():
+            r = w & 0x3FFFFFFF
+            c = {"pos": int(s.pos[r]), "ref_allele": chr(s.ref[r]), "alt_allele": chr(s.alt[r])}
+            if with_kid_allele:
+                c["kid_allele"] = "alt_parent" if (w & 0x40000000) else "ref_parent"
+            if w & 0x80000000:
+                c["alt_parent"], c["ref_parent"] = dad, mom
+            else:
+                c["alt_parent"], c["ref_parent"] = mom, dad
+            cands.append(c)
+        return cands, hets
+
+    # -------------------------------------------------------------------------------------
+    def run(self, snvs: List[dict], svs: List[dict], *, threads=2, build="38", no_extended=False,
+            multiread_proc_min=1000, ab_homref=(0.0, 0.2), ab_homalt=(0.8, 1.0), ab_het=(0.2, 0.8),
+            min_gt_qual=20, min_depth=10, search_dist=5000, insert_size_max_sample=1000000, stdevs=3,
+            min_map_qual=1, readlen=151, split_error_margin=5, evidence_min_ratio=10,
+            time_stages=False):
+        """Plan + run all entries of one call.  Returns (result, layout) where layout gives the
+        entry ranges: cnv entries of the SVs, read entries of the SVs, read entries of the SNVs."""
+        common = dict(build=build, multiread_proc_min=multiread_proc_min, threads=threads)
+        plans: List[Plan] = []
+        n0 = 0
+        a0 = 0
+
+        def add(dnms, **kw):
+            nonlocal n0, a0
+            p = plan_find(dnms, self.ped, self.sidx, self.reads, first_entry=n0, alleles_base=a0, **common, **kw)
+            plans.append(p)
+            n0 += len(dnms)
+            a0 += int(p.alleles.shape[0])
+            return p
+
+        layout = {"sv_cnv": (0, 0), "sv_read": (0, 0), "snv": (0, 0)}
+        if svs:
+            add(svs, search_dist=0, whole_region=True, with_reads=False)
+            layout["sv_cnv"] = (0, len(svs))
+            p = add(svs, search_dist=search_dist, whole_region=False, with_reads=True, sv_quirk=True)
+            p.dnm["cnv_entry"] = np.arange(len(svs), dtype=np.int32)
+            layout["sv_read"] = (len(svs), 2 * len(svs))
+        if snvs:
+            add(snvs, search_dist=search_dist, whole_region=False, with_reads=True)
+            layout["snv"] = (n0 - len(snvs), n0)
+        plan = concat_plans(plans)
+        params = make_params(ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, min_map_qual, readlen,
+                             insert_size_max_sample, no_extended, evidence_min_ratio, split_error_margin)
+        res = self.engine.run(self.dsites, self.dreads, plan, params,
+                              blk_cul=self.cul(readlen, insert_size_max_sample, stdevs), time_stages=time_stages)
+        return res, layout
+
+    # -------------------------------------------------------------------------------------
+    def _read_record(self, res: BatchResult, d: int, dn: dict):
+        kid = dn["kid"]
+        dad, mom = self.ped[kid]["dad"], self.ped[kid]["mom"]
+        s = self.sites
+        ev = res.cand_evidence(d)
+        rows = res.cand_words(d).view(np.uint32) & 0x3FFFFFFF
+        pos = s.pos[rows.astype(np.int64)]
+        dad_sites = sorted({str(int(p)) for p, e in zip(pos, ev) if e & 1})
+        mom_sites = sorted({str(int(p)) for p, e in zip(pos, ev) if e & 2})
+        wlo = int(res.win_lo[d])
+        sev = res.slot_evidence(d)
+        nm = self.reads.name_of
+        dad_reads = sorted({nm(wlo + int(x)) for x in np.nonzero(sev & 1)[0]})
+        mom_reads = sorted({nm(wlo + int(x)) for x in np.nonzero(sev & 2)[0]})
+        return {
+            "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
+            "vartype": dn["vartype"], "kid": kid, "dad": dad, "mom": mom,
+            "dad_sites": dad_sites, "mom_sites": mom_sites, "evidence_type": "readbacked",
+            "dad_reads": dad_reads, "mom_reads": mom_reads,
+            "cnv_dad_sites": "", "cnv_mom_sites": "", "cnv_evidence_type": "",
+        }
+
+    @staticmethod
+    def _auto_record(dn, dad, mom):
+        return {
+            "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
+            "vartype": dn["vartype"], "kid": dn["kid"], "dad": dad, "mom": mom,
+            "cnv_dad_sites": "NA", "cnv_mom_sites": "NA", "cnv_evidence_type": "SEX-CHROM",
+            "dad_sites": "", "mom_sites": "", "evidence_type": "SEX-CHROM",
+            "dad_reads": [], "mom_reads": [],
+        }
+
+    def records(self, res: BatchResult, layout) -> Dict[str, dict]:
+        """The dict ``phase_snvs``/``phase_svs`` return, merged as unfazed.py:648-649 does."""
+        plan = res.plan
+        out_sv: Dict[str, dict] = {}
+        out_snv: Dict[str, dict] = {}
+        s = self.sites
+        a, b = layout["sv_cnv"]
+        cnv: Dict[str, dict] = {}
+        for d in range(a, b):
+            dn = plan.entries[d]
+            dad, mom = self.ped[dn["kid"]]["dad"], self.ped[dn["kid"]]["mom"]
+            if plan.dnm["flags"][d] & L.DNM_AUTOPHASE:
+                cnv[dnm_key(dn)] = self._auto_record(dn, dad, mom)
+                continue
+            if dn["vartype"] not in ("DEL", "DUP") or res.n_cand[d] == 0:
+                continue
+            vd, vm = [], []
+            for w in res.cand_words(d).view(np.uint32).tolist():
+                votes_dad = bool(w & 0x80000000) == bool(w & 0x40000000)
+                (vd if votes_dad else vm).append(str(int(s.pos[w & 0x3FFFFFFF])))
+            cnv[dnm_key(dn)] = {
+                "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
+                "vartype": dn["vartype"], "kid": dn["kid"], "dad": dad, "mom": mom,
+                "cnv_dad_sites": vd, "cnv_mom_sites": vm, "cnv_evidence_type": "ALLELE-BALANCE",
+                "dad_sites": "", "mom_sites": "", "evidence_type": "", "dad_reads": [], "mom_reads": [],
+            }
+        for name, out in (("sv_read", out_sv), ("snv", out_snv)):
+            a, b = layout[name]
+            for d in range(a, b):
+                dn = plan.entries[d]
+                dad, mom = self.ped[dn["kid"]]["dad"], self.ped[dn["kid"]]["mom"]
+                if plan.dnm["flags"][d] & L.DNM_AUTOPHASE:
+                    out[dnm_key(dn)] = self._auto_record(dn, dad, mom)
+                    continue
+                if res.tally is not None and res.tally["has_record"][d]:
+                    out[dnm_key(dn)] = self._read_record(res, d, dn)
+        for k, c in cnv.items():                                  # sv_phaser.py:484-492
+            if k not in out_sv:
+                out_sv[k] = c
+            else:
+                out_sv[k]["cnv_dad_sites"] = c["cnv_dad_sites"]
+                out_sv[k]["cnv_mom_sites"] = c["cnv_mom_sites"]
+                out_sv[k]["evidence_type"] += "," + c["cnv_evidence_type"]
+        out_snv.update(out_sv)
+        return out_snv
+
+    def labels(self, res: BatchResult, d: int) -> Dict[str, str]:
+        """read name -> haplotype ('ref' | 'alt' | 'ref+alt') of entry d (parity checks)."""
+        lab = res.slot_labels(d)
+        wlo = int(res.win_lo[d])
+        names = {1: "ref", 2: "alt", 3: "ref+alt"}
+        return {self.reads.name_of(wlo + int(x)): names[int(lab[x])] for x in np.nonzero(lab)[0]}
+
+    def phase(self, dnms: List[dict], **params) -> Dict[str, dict]:
+        kids = set(self.ped)
+        svs = [d for d in dnms if d["vartype"].upper() in SV_TYPES and d["kid"] in kids]
+        snvs = [d for d in dnms if d["vartype"].upper() in SNV_TYPES and d["kid"] in kids]
+        res, layout = self.run(snvs, svs, **params)
+        return self.records(res, layout)

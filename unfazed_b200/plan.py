@@ -1,0 +1,324 @@
+"""Host-side window planner: turns the reference's site-finding *membership* rules into segments.
+
+``informative_site_finder.find`` (reference :167-344) and ``find_many`` (:601-661) differ in which
+sites a DNM sees and how often.  Neither difference involves genotype arithmetic,
+so it is resolved here, per DNM, into position windows with a multiplicity; the GPU then does the
+binary searches, classifies every (DNM x site) pair and compacts the lists.
+
+The planner also resolves, per DNM: autophasing (:137-164), the DNM's own REF/ALT as seen in the
+sites table (snv_phaser.get_refalt :73-84), the read block to fetch from (with the reference's
+``chr`` toggling on a failed fetch, read_collector.py:384-392) and the kid's concordant insert
+size (read_collector.py:11-25).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .schema import ReadTable, SITE_FLAG_SIMPLE, SiteTable
+
+SV_TYPES = ["DEL", "DUP", "INV", "CNV", "DUP:TANDEM", "DEL:ME", "CPX", "CTX"]
+SNV_TYPES = ["POINT", "SNV", "INDEL"]
+
+# PAR tables exactly as the reference spells them (utils.py:26-43; the build labels are swapped, Q6)
+_PAR = {
+    "37": ({"x": (10001, 2781479), "y": (10001, 2781479)},
+           {"x": (155701383, 156030895), "y": (56887903, 57217415)}),
+    "38": ({"x": (60001, 2699520), "y": (10001, 2649520)},
+           {"x": (154931044, 155260560), "y": (59034050, 59363566)}),
+}
+
+
+class FindManyKeyError(KeyError):
+    """find_many in CNV mode hits the reference's KeyError (Q12) and threads == 1."""
+
+
+def strip_chr(s: str) -> str:
+    return s.strip("chr")
+
+
+def is_autophaseable(dn: dict, pedigrees: dict, build: str) -> bool:
+    chrom = strip_chr(dn["chrom"].lower())
+    if chrom not in ("x", "y"):
+        return False
+    if int(pedigrees[dn["kid"]]["sex"]) != 1 or build not in _PAR:
+        return False
+    par1, par2 = _PAR[build]
+    s = dn["start"]
+    return not (par1[chrom][0] <= s <= par1[chrom][1] or par2[chrom][0] <= s <= par2[chrom][1])
+
+
+class SiteIndex:
+    """Host lookups over a SiteTable that the planner needs (no genotype math)."""
+
+    def __init__(self, sites: SiteTable):
+        self.sites = sites
+        self.trio_of = {trio: t for t, trio in enumerate(sites.trios)}
+        self._contig_rows: Dict[str, tuple] = {}
+        self.prefix = self._prefix()
+
+    def _prefix(self) -> str:
+        """utils.get_prefix on the first record of the joint VCF (Q26: treated as constant)."""
+        s = self.sites
+        best = None
+        for b in range(s.n_blocks):
+            lo, hi = int(s.blk_off[b]), int(s.blk_off[b + 1])
+            if hi > lo:
+                k = (int(s.blk_contig[b]), int(s.pos[lo]), b)
+                if best is None or k < best:
+                    best = k
+        if best is None:
+            return ""
+        name = s.contigs[best[0]]
+        return name[:3] if "chr" in name.lower() else ""
+
+    def trio(self, pedigrees: dict, kid: str) -> int:
+        ped = pedigrees.get(kid)
+        if ped is None:
+            return -1
+        return self.trio_of.get((kid, ped["dad"], ped["mom"]), -1)
+
+    def contig_rows(self, contig: str):
+        """(pos, rec_id, row) of every row on a contig over all trio blocks, sorted by pos."""
+        c = self._contig_rows.get(contig)
+        if c is None:
+            s = self.sites
+            rows = [np.arange(int(s.blk_off[b]), int(s.blk_off[b + 1]))
+                    for b in range(s.n_blocks) if s.contigs[int(s.blk_contig[b])] == contig]
+            rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+            order = np.argsort(s.pos[rows], kind="stable")
+            rows = rows[order]
+            ext = sorted((int(s.pos[r]), len(s.extras[r][0]), r) for r in rows.tolist() if r in s.extras)
+            c = (s.pos[rows].astype(np.int64), s.record_ids()[rows], rows, ext)
+            self._contig_rows[contig] = c
+        return c
+
+    def any_simple_row(self, contig: str, lo: int, hi: int) -> bool:
+        pos, _rid, rows, _ext = self.contig_rows(contig)
+        a, b = np.searchsorted(pos, lo, "left"), np.searchsorted(pos, hi, "right")
+        return bool(np.any(self.sites.flag[rows[a:b]] & SITE_FLAG_SIMPLE))
+
+    def refalt(self, chrom: str, start: int):
+        """snv_phaser.get_refalt :73-84: records overlapping 0-based [start-1, start+1)."""
+        contig = self.prefix + strip_chr(chrom)
+        pos, rid, rows, ext = self.contig_rows(contig)
+        a, b = np.searchsorted(pos, start - 1, "left"), np.searchsorted(pos, start, "right")
+        found = {}
+        for i in range(a, b):
+            found.setdefault((int(pos[i]), int(rid[i])), int(rows[i]))
+        for p, ln, r in ext:                      # long REFs reaching into the interval
+            if p >= start - 1:
+                break
+            if p + ln > start - 1:
+                found.setdefault((p, int(self.sites.record_ids()[r])), r)
+        ref, alts = None, []
+        for key in sorted(found):
+            rr, aa = self.sites.ref_alts(found[key])
+            if ref is None:
+                ref = rr
+            alts += list(aa)
+        return ref, alts
+
+
+@dataclass
+class Plan:
+    """Everything the engine uploads for one batch of DNM entries."""
+    dnm: np.ndarray                  # L.DNM_DTYPE[n]
+    seg: np.ndarray                  # L.SEG_DTYPE[s]
+    alleles: np.ndarray              # u8 blob
+    entries: List[dict]              # the DNM dict behind every entry (shared objects)
+    trio: np.ndarray                 # i32[n] trio index or -1
+    found: np.ndarray                # bool[n]: False -> find() leaves the DNM untouched
+    rblk_sblk: Dict[int, int] = field(default_factory=dict)
+
+
+def _find_windows(dn, sd, whole_region):
+    """Segments (lo_pos, hi_pos, mult) of find(): get_position :10-43 as 0-based site positions."""
+    s, e = int(dn["start"]), int(dn["end"])
+    if whole_region:
+        return [(s - sd - 1, e + sd - 1, 1)]
+    w1 = (s - sd - 1, s + sd - 1)
+    if (e - s) <= sd:
+        return [(w1[0], w1[1], 1)]
+    w2 = (e - sd - 1, e + sd - 1)
+    if w2[0] > w1[1]:
+        return [(w1[0], w1[1], 1), (w2[0], w2[1], 1)]
+    # overlapping tabix regions return the shared records twice (Q9)
+    out = []
+    if w2[0] - 1 >= w1[0]:
+        out.append((w1[0], w2[0] - 1, 1))
+    out.append((w2[0], w1[1], 2))
+    out.append((w1[1] + 1, w2[1], 1))
+    return out
+
+
+def plan_find(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Optional[ReadTable], *,
+              search_dist: int, whole_region: bool, build: str, multiread_proc_min: int, threads: int,
+              with_reads: bool, first_entry: int = 0, alleles_base: int = 0,
+              sv_quirk: bool = False) -> Plan:
+    """One entry per DNM, in input order, with the windows ``find``/``find_many`` would search."""
+    sites = sidx.sites
+    n = len(dnms)
+    dnm = np.zeros(n, dtype=L.DNM_DTYPE)
+    dnm["rblk"] = -1
+    dnm["cnv_entry"] = -1
+    trio = np.full(n, -1, dtype=np.int32)
+    found = np.zeros(n, dtype=bool)
+    segs: List[tuple] = []
+    blob = bytearray()
+    rblk_sblk: Dict[int, int] = {}
+    use_many = n >= multiread_proc_min
+    auto = [is_autophaseable(d, pedigrees, build) for d in dnms]
+
+    # ---- find_many lookups (create_lookups :347-396) -------------------------------------
+    dead_chroms = set()
+    if use_many:
+        by_loc: Dict[str, Dict[int, List[str]]] = {}
+        starts: Dict[tuple, List[int]] = {}
+        ranges: Dict[str, List[int]] = {}
+        for i, d in enumerate(dnms):
+            if auto[i]:
+                continue
+            c, s, e, k = d["chrom"], int(d["start"]), int(d["end"]), d["kid"]
+            r = ranges.setdefault(c, [s, e])
+            r[0], r[1] = min(r[0], s), max(r[1], e)
+            by_loc.setdefault(c, {}).setdefault(s, []).append(k)
+            starts.setdefault((k, c, s), []).append(i)
+            if (e - s) > 2:
+                by_loc[c].setdefault(e, []).append(k)
+        if whole_region:
+            for c, locs in by_loc.items():                      # Q12
+                contig = sidx.prefix + strip_chr(c)
+                broken = any((k, c, loc) not in starts for loc, kids in locs.items() for k in kids)
+                if broken and contig == c and contig in sites.contigs and \
+                        sidx.any_simple_row(contig, ranges[c][0] - search_dist - 1, ranges[c][1] + search_dist - 1):
+                    if threads == 1:
+                        raise FindManyKeyError("find_many: end location without a DNM starting there on %s" % c)
+                    dead_chroms.add(c)
+
+    for i, d in enumerate(dnms):
+        s, e = int(d["start"]), int(d["end"])
+        rec = dnm[i]
+        rec["pos"], rec["end"] = s, e
+        rec["seg_lo"] = len(segs)
+        if auto[i]:
+            rec["flags"] = L.DNM_AUTOPHASE | (L.DNM_AUTOPHASE_Y if strip_chr(d["chrom"].lower()) == "y" else 0) \
+                | (L.DNM_SV_QUIRK if sv_quirk else 0)
+            rec["seg_hi"] = len(segs)
+            continue
+        t = sidx.trio(pedigrees, d["kid"])
+        trio[i] = t
+        if t < 0:
+            rec["seg_hi"] = len(segs)
+            continue
+        found[i] = True
+        contig = sidx.prefix + strip_chr(d["chrom"])
+        sblk = sites.block_of(t, contig)
+        vt = d.get("vartype")
+        if whole_region and vt is not None:
+            mode = L.MODE_CNV_DEL if vt == "DEL" else (L.MODE_CNV_DUP if vt == "DUP" else L.MODE_CNV_NA)
+        else:
+            mode = L.MODE_READ
+        excl = (s, e) if (e - s) < 20 else (0, 0)
+        if not use_many:
+            wins = _find_windows(d, search_dist, whole_region)
+        else:
+            c, k = d["chrom"], d["kid"]
+            wins = []
+            if contig == c and c not in dead_chroms:            # Q11: CHROM must equal the DNM's spelling
+                m = by_loc[c][s].count(k)
+                if not whole_region:
+                    wins = [(s - search_dist - 1, s + search_dist - 1, m)]
+                else:
+                    ends = sorted(int(dnms[j]["end"]) for j in starts[(k, c, s)])
+                    lo = s - search_dist - 1
+                    nleft = len(ends)
+                    for ee in ends:
+                        hi = ee + search_dist - 1
+                        if hi >= lo:
+                            wins.append((lo, hi, m * nleft))
+                            lo = hi + 1
+                        nleft -= 1
+        for lo, hi, mult in wins:
+            if hi >= lo and mult > 0:
+                segs.append((sblk, lo, hi, mult, first_entry + i, excl[0], excl[1], mode))
+        rec["seg_hi"] = len(segs)
+
+        if with_reads and reads is not None:
+            kid_idx = reads.kids.index(d["kid"]) if d["kid"] in reads.kids else -1
+            chrom = d["chrom"]
+            flags = 0
+            if kid_idx >= 0:
+                if chrom not in reads.contigs:                    # fetch() raised -> toggled spelling (Q24)
+                    chrom = strip_chr(chrom) if "chr" in chrom else "chr" + chrom
+                    flags |= L.DNM_FALLBACK_FETCH
+                rb = reads.block_of(kid_idx, chrom) if chrom in reads.contigs else -1
+                rec["rblk"] = rb
+                rec["flags"] |= flags
+                if rb >= 0 and sblk >= 0:
+                    rblk_sblk[rb] = sblk
+            if vt is not None and vt.upper() in SV_TYPES:
+                rec["kind"] = L.KIND_SV
+            else:
+                ref, alts = sidx.refalt(d["chrom"], s)
+                if len(alts) == 1 and ref is not None:
+                    alt = alts[0]
+                    rec["ref_off"], rec["ref_len"] = alleles_base + len(blob), len(ref)
+                    blob += ref.encode("ascii")
+                    rec["alt_off"], rec["alt_len"] = alleles_base + len(blob), len(alt)
+                    blob += alt.encode("ascii")
+                    rec["kind"] = L.KIND_SNV if len(ref) == len(alt) else L.KIND_INDEL
+    seg = np.array(segs, dtype=L.SEG_DTYPE) if segs else np.zeros(0, dtype=L.SEG_DTYPE)
+    return Plan(dnm=dnm, seg=seg, alleles=np.frombuffer(bytes(blob), dtype=np.uint8).copy(),
+                entries=list(dnms), trio=trio, found=found, rblk_sblk=rblk_sblk)
+
+
+def concat_plans(plans: List[Plan]) -> Plan:
+    """Entries of several plans back to back (segment / entry indices were made global by the
+    caller through first_entry / alleles_base)."""
+    off_seg = 0
+    dn_parts, seg_parts = [], []
+    rs: Dict[int, int] = {}
+    for p in plans:
+        d = p.dnm.copy()
+        d["seg_lo"] += off_seg
+        d["seg_hi"] += off_seg
+        dn_parts.append(d)
+        seg_parts.append(p.seg)
+        off_seg += p.seg.shape[0]
+        rs.update(p.rblk_sblk)
+    return Plan(dnm=np.concatenate(dn_parts), seg=np.concatenate(seg_parts),
+                alleles=np.concatenate([p.alleles for p in plans]),
+                entries=[e for p in plans for e in p.entries],
+                trio=np.concatenate([p.trio for p in plans]),
+                found=np.concatenate([p.found for p in plans]), rblk_sblk=rs)
+
+
+def concordant_upper_lens(reads: ReadTable, readlen: int, insert_size_max_sample: int, stdevs: int) -> np.ndarray:
+    """Per read block: estimate_concordant_insert_len of the block's kid (read_collector.py:11-25).
+    np.percentile returns a scalar, so the result is int(p99.5) + 0.0 whatever ``stdevs`` is (Q14)."""
+    out = np.zeros(reads.n_blocks, dtype=np.float64)
+    per_kid: Dict[int, float] = {}
+    tl = reads.hdr["tlen"]
+    for k in range(len(reads.kids)):
+        blocks = [b for b in range(reads.n_blocks) if int(reads.blk_kid[b]) == k]
+        parts, left = [], insert_size_max_sample + 1
+        for b in blocks:
+            if left <= 0:
+                break
+            lo, hi = int(reads.blk_off[b]), int(reads.blk_off[b + 1])
+            take = min(left, hi - lo)
+            parts.append(tl[lo:lo + take])
+            left -= take
+        if not parts or sum(p.shape[0] for p in parts) == 0:
+            per_kid[k] = 0.0
+            continue
+        ins = np.abs(np.concatenate(parts).astype(np.int64) - 2 * readlen)
+        pct = np.percentile(ins, 99.5)
+        per_kid[k] = float(int(np.mean(pct)) + (np.std(pct) * stdevs))
+    for b in range(reads.n_blocks):
+        out[b] = per_kid[int(reads.blk_kid[b])]
+    return out

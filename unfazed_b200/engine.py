@@ -71,13 +71,13 @@ class DeviceReads:
     def __init__(self, table: ReadTable, device: torch.device, pin: bool = False):
         self.table = table
         self.n_reads = table.n_reads
-        up = lambda a: _to_device(np.ascontiguousarray(a), device, pin)
+        up = lambda a, pad=0: _to_device(np.ascontiguousarray(a), device, pin, pad)
         self.blk_off = up(table.blk_off.astype(np.int64))
         self.hdr = up(table.hdr.view(np.uint8).reshape(-1))
         self.cigar = up(table.cigar)
-        # 16 B of tail padding: the TMA bulk copies round the staged span up to 16 B
-        self.qual = up(np.concatenate([table.qual, np.zeros(32, dtype=np.uint8)]))
-        self.seq2 = up(np.concatenate([table.seq2, np.zeros(16, dtype=np.uint8)]))
+        # tail padding: the TMA bulk copies round the staged span up to 16 B
+        self.qual = up(table.qual, 32)
+        self.seq2 = up(table.seq2, 16)
         self.blk_sblk = torch.full((max(table.n_blocks, 1),), -1, dtype=torch.int32, device=device)
         self.blk_cul = torch.zeros((max(table.n_blocks, 1),), dtype=torch.float64, device=device)
         c = L.ReadCols()
@@ -92,11 +92,19 @@ class DeviceReads:
         return sum(t.numel() * t.element_size() for t in (self.hdr, self.cigar, self.qual, self.seq2))
 
 
-def _to_device(a: np.ndarray, device, pin: bool) -> torch.Tensor:
+def _to_device(a: np.ndarray, device, pin: bool, pad: int = 0) -> torch.Tensor:
+    """Host array -> device tensor (+ ``pad`` zero elements).  Arrays that already live in pinned
+    memory are copied asynchronously; ``pin`` stages pageable arrays through a pinned copy."""
     t = torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.dtype.fields is not None else torch.from_numpy(a)
-    if pin:
+    if pin and not t.is_pinned():
         t = t.pin_memory()
-    return t.to(device, non_blocking=pin)
+    out = torch.empty(t.shape[:-1] + (t.shape[-1] + pad,), dtype=t.dtype, device=device) if pad else torch.empty_like(t, device=device)
+    if pad:
+        out[..., t.shape[-1]:].zero_()
+        out[..., : t.shape[-1]].copy_(t, non_blocking=True)
+    else:
+        out.copy_(t, non_blocking=True)
+    return out
 
 
 @dataclass

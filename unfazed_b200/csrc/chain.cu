@@ -26,7 +26,7 @@ struct Scratch {
     // per het-site incidence
     int32_t* inc_r; int32_t* inc_x; int32_t* inc_site; int32_t* inc_sidx; uint8_t* inc_al;
     // seeds
-    int32_t* seed_r; uint8_t* seed_hap;
+    int32_t* seed_e; uint8_t* seed_hap;
     // seed incidences
     int32_t* sinc_x; int32_t* sinc_site; int32_t* sinc_sidx; uint8_t* sinc_al;
     // per het site (site_off has one extra entry per DNM)
@@ -42,7 +42,8 @@ struct ChainArgs {
     UnfzSiteCols sites; UnfzReadCols reads;
     const UnfzReadSum* rsum; const int32_t* blk_maxspan; const uint32_t* hits; const int32_t* mp;
     const int32_t* het_list; const int32_t* n_het; const uint32_t* cand_list; const int32_t* n_cand;
-    const uint8_t* alleles; const int32_t* win_lo; const int32_t* win_hi; const int64_t* off;  // off[6][n+1]
+    const uint8_t* alleles; const int32_t* win; const int64_t* off;  // win[4][n], off[6][n+1]
+    int32_t split_margin;
     int32_t readlen, min_bq, ext_goal, no_extended;
     uint8_t* slot_label; uint8_t* slot_evid; uint8_t* cand_evid; UnfzTally* tally;
     Scratch S;
@@ -165,6 +166,88 @@ __device__ int seed_indel(const ChainArgs& A, const UnfzDnm& dn, int64_t r) {
     return 0;
 }
 
+
+// collect_reads_sv (:515-522): fewer than 7 of the first 10 AND of the last 10 expanded CIGAR
+// operations are M/= -> the read name is banned
+__device__ bool sv_bad_ends(const uint32_t* __restrict__ cg, int n) {
+    int s_m = 0, left = 10;
+    for (int k = 0; k < n && left > 0; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        const int take = min(left, (int)(w >> 4));
+        if ((w & 15u) == 0 || (w & 15u) == 7) s_m += take;
+        left -= take;
+    }
+    int e_m = 0;
+    left = 10;
+    for (int k = n - 1; k >= 0 && left > 0; --k) {
+        const uint32_t w = __ldg(cg + k);
+        const int take = min(left, (int)(w >> 4));
+        if ((w & 15u) == 0 || (w & 15u) == 7) e_m += take;
+        left -= take;
+    }
+    return e_m < 7 && s_m < 7;
+}
+
+// goodread(read, True), mate found, goodread(mate, True)  (:503-513)
+__device__ bool sv_goodok(const ChainArgs& A, int64_t r) {
+    const UnfzReadSum s = load_rsum(A.rsum + r);
+    const uint32_t need = UNFZ_RS_GOOD_DISC | UNFZ_RS_HAS_MATE;
+    if ((s.flags & need) != need) return false;
+    const int64_t m = rd_mate(A.reads, r);
+    return (load_rsum(A.rsum + m).flags & UNFZ_RS_GOOD_DISC) != 0;
+}
+
+__device__ bool sv_banned(const ChainArgs& A, int64_t r) {
+    if (!sv_goodok(A, r)) return false;
+    const UnfzRead h = load_read(A.reads.hdr + r);
+    return sv_bad_ends(A.reads.cigar + h.cigar_off, h.n_cigar);
+}
+
+// split / discordant / clipped support of an SV breakpoint (:524-586): 0 none, 1 [read, mate], 2 [mate, read]
+__device__ int sv_support(const ChainArgs& A, const UnfzDnm& dn, int64_t r, int64_t position, double cul) {
+    const UnfzRead h = load_read(A.reads.hdr + r);
+    const UnfzReadSum s = load_rsum(A.rsum + r);
+    const int64_t r0 = h.start, r1 = s.end;
+    if (h.aux & 2u) {
+        const int64_t em = A.split_margin;
+        if ((position - em <= r0 && r0 <= position + em) || (position - em <= r1 && r1 <= position + em)) return 1;
+        return 0;
+    }
+    long long ins = (long long)h.tlen - 2ll * A.readlen;
+    if (ins < 0) ins = -ins;
+    const double var_len = fabs((double)dn.end - (double)dn.pos);
+    if ((double)ins > cul) {
+        const double ratio = fabs(var_len / (double)ins);
+        if (0.7 < ratio && ratio < 1.3) {
+            const int64_t m0 = rd_start(A.reads, h.mate);
+            const int64_t left0 = min(m0, r0), right0 = max(m0, r0);
+            const int64_t w = (int64_t)cul;
+            if ((dn.pos - w) < left0 && left0 < (dn.pos + w) && (dn.end - w) < right0 && right0 < (dn.end + w)) return 2;
+            return 0;
+        }
+    }
+    // clipped read that is not a split alignment
+    const uint32_t* cg = A.reads.cigar + h.cigar_off;
+    int k = cigar_qpos2(cg, h.n_cigar, h.start, (int32_t)position);
+    if (k < 0) k = cigar_qpos2(cg, h.n_cigar, h.start, (int32_t)position - 1);
+    if (k < 0) k = cigar_qpos2(cg, h.n_cigar, h.start, (int32_t)position + 1);
+    if (k < 0) return 0;
+    int64_t npos = 0, lead = 0, trail = 0;
+    bool seen = false;
+    for (int i = 0; i < h.n_cigar; ++i) {
+        const uint32_t w = __ldg(cg + i);
+        const uint32_t op = w & 15u;
+        const int64_t ln = w >> 4;
+        if (op == 0 || op == 7 || op == 8) { npos += ln; seen = true; trail = 0; }
+        else if (op == 1 || op == 4) { npos += ln; if (!seen) lead += ln; else trail += ln; }
+    }
+    if (k < 2 || k > npos - 4) return 0;
+    const int64_t first_al = lead, last_al = npos - 1 - trail;
+    const bool before_none = first_al >= k - 1;                 // positions[:k-1] are all None (k-1 >= 1)
+    const bool after_none = (k + 1 < npos) && last_al <= k;     // positions[k+1:] non-empty and all None
+    return (before_none || after_none) ? 2 : 0;
+}
+
 // exclusive prefix of `flag` over the CTA in thread order + total
 __device__ __forceinline__ int block_prefix(bool flag, int* total) {
     __shared__ int wsum[CH_WARPS];
@@ -267,7 +350,7 @@ chain_kernel(ChainArgs A) {
     uint8_t* label = A.slot_label + o_slot; uint8_t* evid = A.slot_evid + o_slot;
     int32_t* inc_r = S0.inc_r + o_inc; int32_t* inc_x = S0.inc_x + o_inc; int32_t* inc_site = S0.inc_site + o_inc;
     int32_t* inc_sidx = S0.inc_sidx + o_inc; uint8_t* inc_al = S0.inc_al + o_inc;
-    int32_t* seed_r = S0.seed_r + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed;
+    int32_t* seed_e = S0.seed_e + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed;
     int32_t* sinc_x = S0.sinc_x + o_sinc; int32_t* sinc_site = S0.sinc_site + o_sinc;
     int32_t* sinc_sidx = S0.sinc_sidx + o_sinc; uint8_t* sinc_al = S0.sinc_al + o_sinc;
     int32_t* spos = S0.spos + o_het; uint8_t* sref = S0.sref + o_het; uint8_t* salt = S0.salt + o_het;
@@ -280,15 +363,24 @@ chain_kernel(ChainArgs A) {
     const UnfzReadCols& R = A.reads;
     const int64_t blk_lo = R.blk_off[dn.rblk], blk_hi = R.blk_off[dn.rblk + 1];
     const int64_t maxspan = A.blk_maxspan[dn.rblk];
-    const int64_t wlo = A.win_lo[d], whi = A.win_hi[d];
-    const int W = (int)(whi - wlo);
-
-    // canonical window slot of the pair a read belongs to
+    // the read window is the union of two index ranges (second one only for far-apart SV breakpoints)
+    const int64_t nd_ = A.n_dnms;
+    const int64_t a_lo = A.win[d], a_hi = A.win[nd_ + d], b_lo = A.win[2 * nd_ + d], b_hi = A.win[3 * nd_ + d];
+    const int W = (int)((a_hi - a_lo) + (b_hi - b_lo));
+    auto slot_of = [&](int64_t r) -> int {
+        if (r >= a_lo && r < a_hi) return (int)(r - a_lo);
+        if (r >= b_lo && r < b_hi) return (int)((a_hi - a_lo) + (r - b_lo));
+        return -1;
+    };
+    // canonical window slot of the pair a read belongs to (the lower read index inside the window)
     auto canon = [&](int64_t r) -> int {
         const int64_t m = rd_mate(R, r);
-        const int64_t c = (m >= wlo && m < whi && m < r) ? m : r;
-        return (int)(c - wlo);
+        const int sr = slot_of(r), sm = m >= 0 ? slot_of(m) : -1;
+        if (sr < 0) return sm;
+        if (sm < 0) return sr;
+        return m < r ? sm : sr;
     };
+    const double cul = R.blk_cul[dn.rblk];
 
     for (int x = tid; x < W; x += CH_THREADS) { label[x] = 0; evid[x] = 0; prim[x] = -1; lvl[x] = -1; icnt[x] = 0; fpos[x] = -1; ord[x] = 0; tmp[x] = 0; }
     for (int i = tid; i < nh; i += CH_THREADS) {
@@ -303,6 +395,7 @@ chain_kernel(ChainArgs A) {
     __syncthreads();
 
     // ---------------------------------------------------------------- phase 1: seed reads
+    // seeds are kept as ENTRIES (one read per entry) in the order the reference appends them
     int n_seed = 0;
     if (dn.kind == UNFZ_KIND_SNV || dn.kind == UNFZ_KIND_INDEL) {
         // fetch(chrom, pos-1, pos+1); after a failed fetch the reference retries with (pos, pos+1) (Q24)
@@ -315,22 +408,80 @@ chain_kernel(ChainArgs A) {
             if (r < hi && (int64_t)A.rsum[r].end > flo && pair_ok(A, r, false))
                 hap = dn.kind == UNFZ_KIND_SNV ? seed_snv(A, dn, r) : seed_indel(A, dn, r);
             int tot;
-            const int k = block_prefix(hap != 0, &tot);
-            if (hap && n_seed + k < cap_seed) { seed_r[n_seed + k] = (int32_t)r; seed_hap[n_seed + k] = (uint8_t)hap; }
-            n_seed += tot;
+            const int k = n_seed + 2 * block_prefix(hap != 0, &tot);
+            if (hap && k + 1 < cap_seed) {
+                seed_e[k] = (int32_t)r; seed_hap[k] = (uint8_t)hap;
+                seed_e[k + 1] = rd_mate(R, r); seed_hap[k + 1] = (uint8_t)hap;
+            }
+            n_seed += 2 * tot;
         }
-        if (n_seed > cap_seed) { n_seed = (int)cap_seed; T.status |= 1; }
+        if (n_seed > cap_seed) { n_seed = (int)cap_seed & ~1; T.status |= 1; }
+    } else if (dn.kind == UNFZ_KIND_SV) {
+        int64_t e_lo = 0, e_hi = 0, e_flo = 0, e_fhi = 0;
+        for (int wdx = 0; wdx < 2; ++wdx) {
+            const int64_t position = wdx == 0 ? dn.pos : dn.end;
+            const double dlo = (double)position - cul;
+            const int64_t flo = dlo > 0.0 ? (int64_t)dlo : 0;
+            const int64_t fhi = (int64_t)((double)position + cul);
+            const int64_t lo = lb_start(R, blk_lo, blk_hi, flo - maxspan + 1);
+            const int64_t hi = lb_start(R, lo, blk_hi, fhi);
+            if (wdx == 1) { e_lo = lo; e_hi = hi; e_flo = flo; e_fhi = fhi; }
+            for (int64_t base = lo; base < hi; base += CH_THREADS) {
+                const int64_t r = base + tid;
+                int sup = 0;
+                if (r < hi && (int64_t)A.rsum[r].end > flo && sv_goodok(A, r)) {
+                    const UnfzRead h = load_read(R.hdr + r);
+                    const int64_t m = h.mate;
+                    // name already banned by the mate earlier in this fetch?
+                    const bool skip = m < r && m >= lo && (int64_t)A.rsum[m].end > flo && sv_banned(A, m);
+                    if (!skip && !sv_bad_ends(R.cigar + h.cigar_off, h.n_cigar)) sup = sv_support(A, dn, r, position, cul);
+                }
+                int tot;
+                const int k = n_seed + 2 * block_prefix(sup != 0, &tot);
+                if (sup && k + 1 < cap_seed) {
+                    const int32_t m = rd_mate(R, r);
+                    seed_e[k] = sup == 1 ? (int32_t)r : m; seed_hap[k] = 2;
+                    seed_e[k + 1] = sup == 1 ? m : (int32_t)r; seed_hap[k + 1] = 2;
+                }
+                n_seed += 2 * tot;
+            }
+        }
+        if (n_seed > cap_seed) { n_seed = (int)cap_seed & ~1; T.status |= 1; }
+        __syncthreads();
+        // drop entries whose name was banned while scanning the END breakpoint (:588-591), in place
+        int kept = 0;
+        for (int base = 0; base < n_seed; base += CH_THREADS) {
+            const int k = base + tid;
+            bool keep = false;
+            int32_t e = 0;
+            if (k < n_seed) {
+                e = seed_e[k];
+                const int64_t m = rd_mate(R, e);
+                auto in_end_fetch = [&](int64_t z) {
+                    return z >= e_lo && z < e_hi && (int64_t)A.rsum[z].end > e_flo && (int64_t)rd_start(R, z) < e_fhi;
+                };
+                const bool banned = (in_end_fetch(e) && sv_banned(A, e)) || (m >= 0 && in_end_fetch(m) && sv_banned(A, m));
+                keep = !banned;
+            }
+            int tot;
+            const int kk = kept + block_prefix(keep, &tot);     // block_prefix syncs: all reads precede the writes
+            if (keep) { seed_e[kk] = e; seed_hap[kk] = 2; }
+            kept += tot;
+            __syncthreads();
+        }
+        n_seed = kept < 2 ? 0 : kept;
     }
     __syncthreads();
 
     int n_inc = 0, n_sinc = 0;
     if (A.no_extended) {
-        for (int k = tid; k < n_seed; k += CH_THREADS) {
-            const int64_t r = seed_r[k];
-            const int x = canon(r);
-            label[x] |= seed_hap[k];       // one seed entry per pair in practice; benign if repeated
-            prim[x] = (int32_t)r;
-        }
+        if (tid == 0)
+            for (int k = 0; k < n_seed; ++k) {
+                const int x = canon(seed_e[k]);
+                if (x < 0) continue;
+                label[x] |= seed_hap[k];
+                prim[x] = seed_e[k];
+            }
         __syncthreads();
     } else {
         // ------------------------------------------------------------ phase 2: het-site incidences
@@ -372,37 +523,34 @@ chain_kernel(ChainArgs A) {
             uint32_t order_alt = 0, order_ref = 0;
             // level-0 iteration order: "alt" list first, then "ref" (Q19); position = first entry
             for (int k = 0; k < n_seed; ++k) {
-                const int x = canon(seed_r[k]);
-                if (seed_hap[k] == 2 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (0u << 24) | order_alt++; }
+                const int x = canon(seed_e[k]);
+                if (x >= 0 && seed_hap[k] == 2 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (0u << 24) | order_alt++; }
             }
             for (int k = 0; k < n_seed; ++k) {
-                const int x = canon(seed_r[k]);
-                if (seed_hap[k] == 1 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (1u << 24) | order_ref++; }
+                const int x = canon(seed_e[k]);
+                if (x >= 0 && seed_hap[k] == 1 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (1u << 24) | order_ref++; }
             }
-            // registration order: "ref" seeds, then "alt" seeds; each fetched read then its mate
+            // registration order: "ref" entries, then "alt" entries (:226-249)
             for (int pass = 1; pass <= 2; ++pass) {
                 for (int k = 0; k < n_seed; ++k) {
                     if (seed_hap[k] != pass) continue;
-                    const int64_t r = seed_r[k];
-                    const int x = canon(r);
+                    const int64_t e = seed_e[k];
+                    const int x = canon(e);
+                    if (x < 0) continue;
                     label[x] |= (uint8_t)pass;
-                    const int64_t ents[2] = {r, (int64_t)rd_mate(R, r)};
-                    for (int t = 0; t < 2; ++t) {
-                        const int64_t e = ents[t];
-                        prim[x] = (int32_t)e;
-                        if (nh == 0) continue;
-                        const int32_t st = rd_start(R, e), en = A.rsum[e].end;
-                        const int piv = bisect_pivot(spos, nh, st, en);
-                        if (piv < 0) continue;
-                        auto push = [&](int i) {
-                            if (ns < cap_sinc) { sinc_x[ns] = x; sinc_site[ns] = i; sinc_sidx[ns] = icnt[x]; }
-                            icnt[x] += 1;
-                            ++ns;
-                        };
-                        push(piv);
-                        for (int j = piv + 1; j < nh && st <= spos[j] && spos[j] <= en; ++j) push(j);
-                        for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) push(j);
-                    }
+                    prim[x] = (int32_t)e;
+                    if (nh == 0) continue;
+                    const int32_t st = rd_start(R, e), en = A.rsum[e].end;
+                    const int piv = bisect_pivot(spos, nh, st, en);
+                    if (piv < 0) continue;
+                    auto push = [&](int i) {
+                        if (ns < cap_sinc) { sinc_x[ns] = x; sinc_site[ns] = i; sinc_sidx[ns] = icnt[x]; }
+                        icnt[x] += 1;
+                        ++ns;
+                    };
+                    push(piv);
+                    for (int j = piv + 1; j < nh && st <= spos[j] && spos[j] <= en; ++j) push(j);
+                    for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) push(j);
                 }
             }
             s_n = ns;
@@ -600,66 +748,106 @@ chain_kernel(ChainArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// sizing: read window and scratch needs per DNM (one thread per DNM)
+// sizing: read window (union of two index ranges) and scratch needs per DNM, one warp per DNM
 // ------------------------------------------------------------------------------------------------
-__global__ void chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_t* __restrict__ seg_pair_off,
-                                  UnfzSiteCols sites, UnfzReadCols reads, const UnfzReadSum* __restrict__ rsum,
-                                  const int32_t* __restrict__ blk_maxspan, const int32_t* __restrict__ het_list,
-                                  const int32_t* __restrict__ n_het, const uint32_t* __restrict__ cand_list,
-                                  const int32_t* __restrict__ n_cand, int32_t* __restrict__ win_lo,
-                                  int32_t* __restrict__ win_hi, int64_t* __restrict__ need) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ int64_t warp_sum64(int64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int64_t warp_min64(int64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int64_t warp_max64(int64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(128)
+chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_t* __restrict__ seg_pair_off,
+                  UnfzSiteCols sites, UnfzReadCols reads, const UnfzReadSum* __restrict__ rsum,
+                  const int32_t* __restrict__ blk_maxspan, const int32_t* __restrict__ het_list,
+                  const int32_t* __restrict__ n_het, const uint32_t* __restrict__ cand_list,
+                  const int32_t* __restrict__ n_cand, int32_t* __restrict__ win, int64_t* __restrict__ need) {
+    const int lane = threadIdx.x & 31;
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_dnms) return;
     const UnfzDnm dn = dnms[d];
     int64_t nd[6] = {0, 0, 0, 0, 0, 0};
-    int32_t wl = 0, wh = 0;
+    int64_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
     const int nh = n_het[d], nc = n_cand[d];
     if (!(dn.kind == UNFZ_KIND_SKIP || dn.rblk < 0 || nc <= 0 || dn.seg_hi <= dn.seg_lo)) {
         const int64_t lbase = seg_pair_off[dn.seg_lo];
         const int32_t* H = het_list + lbase;
-        const uint32_t* C = cand_list + lbase;
         const int64_t blk_lo = reads.blk_off[dn.rblk], blk_hi = reads.blk_off[dn.rblk + 1];
         const int64_t maxspan = blk_maxspan[dn.rblk];
-        int64_t minp = (int64_t)dn.pos - 1, maxp = (int64_t)dn.pos + 1;
-        if (nh > 0) {
-            minp = min(minp, (int64_t)sites.pos[H[0]]);
-            maxp = max(maxp, (int64_t)sites.pos[H[nh - 1]] + 1);
+        const double cul = reads.blk_cul[dn.rblk];
+        const bool sv = dn.kind == UNFZ_KIND_SV;
+        // seed fetch windows in position space
+        int64_t sa_lo, sa_hi, sb_lo = 0, sb_hi = 0;
+        if (sv) {
+            const double l0 = (double)dn.pos - cul, l1 = (double)dn.end - cul;
+            sa_lo = l0 > 0.0 ? (int64_t)l0 : 0; sa_hi = (int64_t)((double)dn.pos + cul);
+            sb_lo = l1 > 0.0 ? (int64_t)l1 : 0; sb_hi = (int64_t)((double)dn.end + cul);
+        } else {
+            sa_lo = (dn.flags & 8) ? (int64_t)dn.pos : (int64_t)dn.pos - 1;
+            sa_hi = (int64_t)dn.pos + 1;
         }
-        minp = min(minp, (int64_t)sites.pos[C[0] & 0x3fffffffu]);
-        maxp = max(maxp, (int64_t)sites.pos[C[nc - 1] & 0x3fffffffu] + 1);
-        const int64_t lo = lb_start(reads, blk_lo, blk_hi, minp - maxspan + 1);
-        const int64_t hi = lb_start(reads, lo, blk_hi, maxp);
-        wl = (int32_t)lo; wh = (int32_t)hi;
-        nd[0] = hi - lo;
-        for (int i = 0; i < nh; ++i) {
+        const int64_t mid = sv ? ((int64_t)dn.pos + (int64_t)dn.end) / 2 : (int64_t)1 << 40;
+        int64_t minA = sa_lo, maxA = sa_hi, minB = sv ? sb_lo : ((int64_t)1 << 40), maxB = sv ? sb_hi : -1;
+        int64_t incs = 0;
+        for (int i = lane; i < nh; i += 32) {
             const int64_t p = sites.pos[H[i]];
-            const int64_t a = lb_start(reads, lo, hi, p - maxspan + 1);
-            const int64_t b = lb_start(reads, a, hi, p + 1);
-            nd[1] += b - a;
+            if (p < mid) { minA = min(minA, p); maxA = max(maxA, p + 1); }
+            else { minB = min(minB, p); maxB = max(maxB, p + 1); }
+            const int64_t a = lb_start(reads, blk_lo, blk_hi, p - maxspan + 1);
+            const int64_t b = lb_start(reads, a, blk_hi, p + 1);
+            incs += b - a;
         }
-        const int64_t a = lb_start(reads, lo, hi, (int64_t)dn.pos - 1 - maxspan + 1);
-        const int64_t b = lb_start(reads, a, hi, (int64_t)dn.pos + 1);
-        nd[2] = b - a;
-        // every seed entry (read and mate) registers the het sites with start <= pos <= end
-        for (int64_t r = a; r < b; ++r) {
-            const int64_t ents[2] = {r, (int64_t)reads.hdr[r].mate};
-            for (int t = 0; t < 2; ++t) {
-                const int64_t e = ents[t];
-                if (e < 0) continue;
-                const int64_t st = reads.hdr[e].start, en = rsum[e].end;
-                int l = 0, h = nh;
-                while (l < h) { const int mid = (l + h) >> 1; if (sites.pos[H[mid]] < st) l = mid + 1; else h = mid; }
-                int u = l; h = nh;
-                while (u < h) { const int mid = (u + h) >> 1; if (sites.pos[H[mid]] <= en) u = mid + 1; else h = mid; }
-                nd[3] += u - l;
+        minA = warp_min64(minA); maxA = warp_max64(maxA); minB = warp_min64(minB); maxB = warp_max64(maxB);
+        nd[1] = warp_sum64(incs);
+        a_lo = lb_start(reads, blk_lo, blk_hi, minA - maxspan + 1);
+        a_hi = lb_start(reads, a_lo, blk_hi, maxA);
+        if (maxB > minB) {
+            b_lo = lb_start(reads, blk_lo, blk_hi, minB - maxspan + 1);
+            b_hi = lb_start(reads, b_lo, blk_hi, maxB);
+            if (b_lo <= a_hi) { a_hi = max(a_hi, b_hi); a_lo = min(a_lo, b_lo); b_lo = b_hi = 0; }
+        }
+        nd[0] = (a_hi - a_lo) + (b_hi - b_lo);
+        // seed entries and the het sites each entry registers (start <= pos <= end)
+        int64_t seeds = 0, sincs = 0;
+        for (int wdx = 0; wdx < (sv ? 2 : 1); ++wdx) {
+            const int64_t flo = wdx ? sb_lo : sa_lo, fhi = wdx ? sb_hi : sa_hi;
+            const int64_t a = lb_start(reads, blk_lo, blk_hi, flo - maxspan + 1);
+            const int64_t b = lb_start(reads, a, blk_hi, fhi);
+            seeds += 2 * (b - a);
+            for (int64_t r = a + lane; r < b; r += 32) {
+                const int64_t ents[2] = {r, (int64_t)reads.hdr[r].mate};
+                for (int t = 0; t < 2; ++t) {
+                    const int64_t e = ents[t];
+                    if (e < 0) continue;
+                    const int64_t st = reads.hdr[e].start, en = rsum[e].end;
+                    int l = 0, h = nh;
+                    while (l < h) { const int m2 = (l + h) >> 1; if (sites.pos[H[m2]] < st) l = m2 + 1; else h = m2; }
+                    int u = l; h = nh;
+                    while (u < h) { const int m2 = (u + h) >> 1; if (sites.pos[H[m2]] <= en) u = m2 + 1; else h = m2; }
+                    sincs += u - l;
+                }
             }
         }
+        nd[2] = seeds;
+        nd[3] = warp_sum64(sincs);
         nd[4] = nh;
         nd[5] = nc;
     }
-    win_lo[d] = wl;
-    win_hi[d] = wh;
-    for (int k = 0; k < 6; ++k) need[(int64_t)k * n_dnms + d] = nd[k];
+    if (lane == 0) {
+        win[d] = (int32_t)a_lo; win[(int64_t)n_dnms + d] = (int32_t)a_hi;
+        win[2 * (int64_t)n_dnms + d] = (int32_t)b_lo; win[3 * (int64_t)n_dnms + d] = (int32_t)b_hi;
+        for (int k = 0; k < 6; ++k) need[(int64_t)k * n_dnms + d] = nd[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -750,7 +938,7 @@ Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_
     S.inc_r = (int32_t*)carve<int32_t>(p, incs); S.inc_x = (int32_t*)carve<int32_t>(p, incs);
     S.inc_site = (int32_t*)carve<int32_t>(p, incs); S.inc_sidx = (int32_t*)carve<int32_t>(p, incs);
     S.inc_al = (uint8_t*)carve<uint8_t>(p, incs);
-    S.seed_r = (int32_t*)carve<int32_t>(p, seeds); S.seed_hap = (uint8_t*)carve<uint8_t>(p, seeds);
+    S.seed_e = (int32_t*)carve<int32_t>(p, seeds); S.seed_hap = (uint8_t*)carve<uint8_t>(p, seeds);
     S.sinc_x = (int32_t*)carve<int32_t>(p, sincs); S.sinc_site = (int32_t*)carve<int32_t>(p, sincs);
     S.sinc_sidx = (int32_t*)carve<int32_t>(p, sincs); S.sinc_al = (uint8_t*)carve<uint8_t>(p, sincs);
     S.spos = (int32_t*)carve<int32_t>(p, hets); S.sref = (uint8_t*)carve<uint8_t>(p, hets);
@@ -775,11 +963,11 @@ extern "C" int unfz_chain_size(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms
                                const int64_t* seg_pair_off, const UnfzSiteCols* sites, const UnfzReadCols* reads,
                                const UnfzReadSum* rsum, const int32_t* blk_maxspan, const int32_t* het_list,
                                const int32_t* n_het, const uint32_t* cand_list, const int32_t* n_cand,
-                               int32_t* win_lo, int32_t* win_hi, int64_t* need, void* stream) {
+                               int32_t* win, int64_t* need, void* stream) {
     (void)segs;
     if (n_dnms <= 0) return 0;
-    chain_size_kernel<<<(n_dnms + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        dnms, n_dnms, seg_pair_off, *sites, *reads, rsum, blk_maxspan, het_list, n_het, cand_list, n_cand, win_lo, win_hi, need);
+    chain_size_kernel<<<(n_dnms + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+        dnms, n_dnms, seg_pair_off, *sites, *reads, rsum, blk_maxspan, het_list, n_het, cand_list, n_cand, win, need);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -789,7 +977,7 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
                                 const UnfzReadSum* rsum, const int32_t* blk_maxspan, const uint32_t* hits,
                                 const int32_t* mark_prefix, const int32_t* het_list, const int32_t* n_het,
                                 const uint32_t* cand_list, const int32_t* n_cand, const uint8_t* alleles,
-                                const int32_t* win_lo, const int32_t* win_hi, const int64_t* off,
+                                const int32_t* win, const int64_t* off,
                                 const int64_t* h_totals, const UnfzParams* hp, void* scratch, int64_t scratch_bytes,
                                 uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid, UnfzTally* tally,
                                 void* stream) {
@@ -798,7 +986,7 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     A.dnms = dnms; A.n_dnms = n_dnms; A.segs = segs; A.seg_pair_off = seg_pair_off;
     A.sites = *sites; A.reads = *reads; A.rsum = rsum; A.blk_maxspan = blk_maxspan; A.hits = hits; A.mp = mark_prefix;
     A.het_list = het_list; A.n_het = n_het; A.cand_list = cand_list; A.n_cand = n_cand; A.alleles = alleles;
-    A.win_lo = win_lo; A.win_hi = win_hi; A.off = off;
+    A.win = win; A.off = off; A.split_margin = hp->split_error_margin;
     A.readlen = hp->readlen;
     const double bq = hp->min_gt_qual;
     A.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));

@@ -121,8 +121,7 @@ class BatchResult:
     tally: Optional[np.ndarray] = None
     calls_strict: Optional[np.ndarray] = None
     calls_ambiguous: Optional[np.ndarray] = None
-    win_lo: Optional[np.ndarray] = None
-    win_hi: Optional[np.ndarray] = None
+    win: Optional[np.ndarray] = None          # [4, n]: read-index ranges [a_lo,a_hi) U [b_lo,b_hi) of every entry
     slot_off: Optional[np.ndarray] = None
     timings_ms: Dict[str, float] = field(default_factory=dict)
     launches: int = 0
@@ -157,6 +156,13 @@ class BatchResult:
     def slot_evidence(self, d: int) -> np.ndarray:
         a, b = int(self.slot_off[d]), int(self.slot_off[d + 1])
         return self._np("slot_evid")[a:b]
+
+    def slot_reads(self, d: int, slots: np.ndarray) -> np.ndarray:
+        """Read index behind window slots of entry d."""
+        a_lo, a_hi, b_lo, _b_hi = (int(x) for x in self.win[:, d])
+        na = a_hi - a_lo
+        slots = np.asarray(slots, dtype=np.int64)
+        return np.where(slots < na, a_lo + slots, b_lo + (slots - na))
 
     def read_summaries(self) -> np.ndarray:
         return self._np("rsum").view(L.RSUM_DTYPE)
@@ -303,13 +309,12 @@ class Engine:
             mark("read_site_alleles")
             res.n_hits = n_hits
             # ---- chain sizing + scans ------------------------------------------------------------
-            win_lo = self._zeros(n_dnms, torch.int32)
-            win_hi = self._zeros(n_dnms, torch.int32)
+            win = self._zeros(4 * n_dnms, torch.int32)
             need = self._zeros(6 * n_dnms, torch.int64)
             off = self._zeros(6 * (n_dnms + 1), torch.int64)
             self._check(lib.unfz_chain_size(ctx, d_dnm.data_ptr(), n_dnms, d_seg.data_ptr(), seg_pair_off.data_ptr(), sc, rc_,
                                             rsum.data_ptr(), blk_maxspan.data_ptr(), het_list.data_ptr(), n_het.data_ptr(),
-                                            cand_list.data_ptr(), n_cand.data_ptr(), win_lo.data_ptr(), win_hi.data_ptr(),
+                                            cand_list.data_ptr(), n_cand.data_ptr(), win.data_ptr(),
                                             need.data_ptr(), s), "chain_size")
             for k in range(6):
                 self._check(lib.unfz_exclusive_scan_i64(ctx, need.data_ptr() + 8 * k * n_dnms, off.data_ptr() + 8 * k * (n_dnms + 1),
@@ -327,7 +332,7 @@ class Engine:
             self._check(lib.unfz_chain_tally(ctx, d_dnm.data_ptr(), n_dnms, d_seg.data_ptr(), seg_pair_off.data_ptr(), sc, rc_,
                                              rsum.data_ptr(), blk_maxspan.data_ptr(), hits.data_ptr(), mark_prefix.data_ptr(),
                                              het_list.data_ptr(), n_het.data_ptr(), cand_list.data_ptr(), n_cand.data_ptr(),
-                                             d_all.data_ptr(), win_lo.data_ptr(), win_hi.data_ptr(), off.data_ptr(),
+                                             d_all.data_ptr(), win.data_ptr(), off.data_ptr(),
                                              totals.ctypes.data, C.byref(params), scratch.data_ptr(), nbytes,
                                              slot_label.data_ptr(), slot_evid.data_ptr(), cand_evid.data_ptr(),
                                              tally.data_ptr(), s), "chain_tally")
@@ -337,7 +342,7 @@ class Engine:
                       blk_maxspan=blk_maxspan, row_mark=row_mark, mark_prefix=mark_prefix)
             res.slot_off = h_off[0].copy()
             if download:
-                res.win_lo, res.win_hi = win_lo.cpu().numpy()[:n_dnms], win_hi.cpu().numpy()[:n_dnms]
+                res.win = win.cpu().numpy()[: 4 * n_dnms].reshape(4, n_dnms)
         self._check(lib.unfz_summarize(ctx, d_dnm.data_ptr(), n_dnms, tally.data_ptr(), cnv_dad.data_ptr(), cnv_mom.data_ptr(),
                                        n_cand.data_ptr(), C.byref(params), calls_s.data_ptr(), calls_a.data_ptr(), s), "summarize")
         launches += 1

@@ -109,11 +109,10 @@ class BatchPhaser:
         pos = s.pos[rows.astype(np.int64)]
         dad_sites = sorted({str(int(p)) for p, e in zip(pos, ev) if e & 1})
         mom_sites = sorted({str(int(p)) for p, e in zip(pos, ev) if e & 2})
-        wlo = int(res.win_lo[d])
         sev = res.slot_evidence(d)
         nm = self.reads.name_of
-        dad_reads = sorted({nm(wlo + int(x)) for x in np.nonzero(sev & 1)[0]})
-        mom_reads = sorted({nm(wlo + int(x)) for x in np.nonzero(sev & 2)[0]})
+        dad_reads = sorted({nm(int(r)) for r in res.slot_reads(d, np.nonzero(sev & 1)[0])})
+        mom_reads = sorted({nm(int(r)) for r in res.slot_reads(d, np.nonzero(sev & 2)[0])})
         return {
             "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
             "vartype": dn["vartype"], "kid": kid, "dad": dad, "mom": mom,
@@ -181,9 +180,9 @@ class BatchPhaser:
     def labels(self, res: BatchResult, d: int) -> Dict[str, str]:
         """read name -> haplotype ('ref' | 'alt' | 'ref+alt') of entry d (parity checks)."""
         lab = res.slot_labels(d)
-        wlo = int(res.win_lo[d])
         names = {1: "ref", 2: "alt", 3: "ref+alt"}
-        return {self.reads.name_of(wlo + int(x)): names[int(lab[x])] for x in np.nonzero(lab)[0]}
+        xs = np.nonzero(lab)[0]
+        return {self.reads.name_of(int(r)): names[int(lab[x])] for x, r in zip(xs, res.slot_reads(d, xs))}
 
     def phase(self, dnms: List[dict], **params) -> Dict[str, dict]:
         kids = set(self.ped)

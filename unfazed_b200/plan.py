@@ -303,7 +303,16 @@ def concordant_upper_lens(reads: ReadTable, readlen: int, insert_size_max_sample
     out = np.zeros(reads.n_blocks, dtype=np.float64)
     per_kid: Dict[int, float] = {}
     tl = reads.hdr["tlen"]
+    head = getattr(reads, "head_tlen", None) or {}
     for k in range(len(reads.kids)):
+        if reads.kids[k] in head:                      # packed from a real file: the head of the BAM
+            h = head[reads.kids[k]][: insert_size_max_sample + 1]
+            if h.shape[0] == 0:
+                per_kid[k] = 0.0
+                continue
+            pct = np.percentile(np.abs(h.astype(np.int64) - 2 * readlen), 99.5)
+            per_kid[k] = float(int(np.mean(pct)) + (np.std(pct) * stdevs))
+            continue
         blocks = [b for b in range(reads.n_blocks) if int(reads.blk_kid[b]) == k]
         parts, left = [], insert_size_max_sample + 1
         for b in blocks:

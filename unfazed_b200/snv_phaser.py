@@ -1,0 +1,58 @@
+"""Drop-in for the reference's ``unfazed/snv_phaser.py``: ``phase_snvs`` keeps the 20 positional
+arguments of the reference (:356-377) and returns the same ``key -> record`` dict (:187-203), but
+the whole DNM list is phased in one batch on the GPU (site classification, seed reads, extended
+chaining, site matching, evidence tally) instead of one thread-pool task per DNM."""
+from __future__ import annotations
+
+import sys
+
+from . import datasource
+from .informative_site_finder import get_engine
+from .plan import FindManyKeyError
+
+QUIET_MODE = False
+
+
+def _say(msg):
+    if not QUIET_MODE:
+        print(msg, file=sys.stderr)
+
+
+def run_batch(snvs, svs, pedigrees, sites, threads, build, no_extended, multiread_proc_min, ab_homref, ab_homalt,
+              ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample, stdevs, min_map_qual, readlen,
+              split_error_margin):
+    from .phaser import BatchPhaser
+    dnms = list(svs) + list(snvs)
+    site_table = datasource.load_sites(sites, dnms, pedigrees, search_dist)
+    read_table = datasource.load_reads(dnms, search_dist, readlen, insert_size_max_sample)
+    bp = BatchPhaser(get_engine(), site_table, read_table, pedigrees)
+    try:
+        res, layout = bp.run(snvs, svs, threads=threads, build=build, no_extended=no_extended,
+                             multiread_proc_min=multiread_proc_min, ab_homref=ab_homref, ab_homalt=ab_homalt,
+                             ab_het=ab_het, min_gt_qual=min_gt_qual, min_depth=min_depth, search_dist=search_dist,
+                             insert_size_max_sample=insert_size_max_sample, stdevs=stdevs, min_map_qual=min_map_qual,
+                             readlen=readlen, split_error_margin=split_error_margin)
+    except FindManyKeyError as e:
+        raise KeyError(str(e))
+    for name in ("sv_read", "snv"):
+        for d in range(*layout[name]):
+            dn = res.plan.entries[d]
+            if res.plan.dnm["flags"][d] & 1 or not res.plan.found[d]:
+                continue
+            if res.n_cand[d] == 0:
+                _say("No usable informative sites for variant {}:{}-{}".format(dn["chrom"], dn["start"], dn["end"]))
+            elif res.plan.dnm["kind"][d] == 0:
+                _say("No usable genotype for variant {}:{}-{}".format(dn["chrom"], dn["start"], dn["end"]))
+            elif res.tally is not None and not res.tally["has_record"][d]:
+                _say("No reads overlap informative sites for variant {}:{}-{}".format(dn["chrom"], dn["start"], dn["end"]))
+    return bp.records(res, layout)
+
+
+def phase_snvs(dnms, kids, pedigrees, sites, threads, build, no_extended, multithread_proc_min, quiet_mode,
+               ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample,
+               stdevs, min_map_qual, readlen, split_error_margin):
+    global QUIET_MODE
+    QUIET_MODE = quiet_mode
+    return run_batch(dnms, [], pedigrees, sites, threads, build, no_extended, multithread_proc_min, ab_homref,
+                     ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample, stdevs,
+                     min_map_qual, readlen, split_error_margin)

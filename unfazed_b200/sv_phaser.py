@@ -1,0 +1,16 @@
+"""Drop-in for the reference's ``unfazed/sv_phaser.py``: ``phase_svs`` (:427-448) -- CNV
+allele-balance phasing over the sites inside DEL/DUP events (``run_cnv_phasing`` :357-423,
+``phase_by_snvs`` :71-85) plus read-backed phasing from breakpoint-supporting reads
+(``run_read_phasing`` :176-266), merged as :484-492 -- batched on the GPU."""
+from __future__ import annotations
+
+from . import snv_phaser
+
+
+def phase_svs(dnms, kids, pedigrees, sites, threads, build, no_extended, multiread_proc_min, quiet_mode,
+              ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample,
+              stdevs, min_map_qual, readlen, split_error_margin):
+    snv_phaser.QUIET_MODE = quiet_mode
+    return snv_phaser.run_batch([], dnms, pedigrees, sites, threads, build, no_extended, multiread_proc_min,
+                                ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, search_dist,
+                                insert_size_max_sample, stdevs, min_map_qual, readlen, split_error_margin)

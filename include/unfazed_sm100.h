@@ -220,7 +220,8 @@ int unfz_compact_sites(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const Unfz
  * reference_end, and the number of marked site rows each read overlaps.
  * mark_prefix = exclusive scan of row_mark (n_rows+1 entries). */
 int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
-                   const int32_t* mark_prefix, const UnfzParams* h_params, UnfzReadSum* out,
+                   const int32_t* mark_prefix, const UnfzParams* h_params,
+                   int32_t max_l_seq /* longest read, 0 = unknown: picks the staging strategy */, UnfzReadSum* out,
                    int32_t* blk_maxspan /* [n_blocks], zeroed by the caller: max(end-start) */,
                    void* stream);
 

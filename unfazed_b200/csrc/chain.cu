@@ -30,7 +30,7 @@ struct Scratch {
     // seed incidences
     int32_t* sinc_x; int32_t* sinc_site; int32_t* sinc_sidx; uint8_t* sinc_al;
     // per het site (site_off has one extra entry per DNM)
-    int32_t* spos; uint8_t* sref; uint8_t* salt; int32_t* site_off;
+    int32_t* spos; uint8_t* sref; uint8_t* salt; int32_t* site_off; int32_t* cand_off;
     unsigned long long* bestkey; uint8_t* best_info; int32_t* site_cnt; int32_t* site_base;
     // per candidate site
     int32_t* cpos;
@@ -263,6 +263,23 @@ __device__ __forceinline__ int block_prefix(bool flag, int* total) {
     return base + __popc(b & ((1u << lane) - 1u));
 }
 
+// exclusive prefix SUM of v over the CTA in thread order + total
+__device__ __forceinline__ int block_prefix_sum(int v, int* total) {
+    __shared__ int wsum3[CH_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum3[w] = x;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < CH_WARPS; ++i) { if (i < w) base += wsum3[i]; tot += wsum3[i]; }
+    __syncthreads();
+    *total = tot;
+    return base + x - v;
+}
+
 __device__ __forceinline__ int block_sum(int v) {
     __shared__ int wsum2[CH_WARPS];
 #pragma unroll
@@ -321,7 +338,6 @@ chain_kernel(ChainArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const UnfzDnm dn = A.dnms[d];
     const Scratch& S0 = A.S;
-    __shared__ int s_n, s_n2;
 
     UnfzTally T;
     T.n_dad_sites = T.n_mom_sites = T.n_dad_reads = T.n_mom_reads = 0;
@@ -345,7 +361,7 @@ chain_kernel(ChainArgs A) {
 
     // per-DNM views
     int32_t* prim = S0.prim + o_slot; uint32_t* ord = S0.ord + o_slot; int32_t* lvl = S0.lvl + o_slot;
-    int32_t* fpos = S0.fpos + o_slot; int32_t* icnt = S0.icnt + o_slot;
+    int32_t* fpos = S0.fpos + o_slot;
     unsigned long long* minkey = S0.minkey + o_slot; int32_t* tmp = S0.tmp + o_slot;
     uint8_t* label = A.slot_label + o_slot; uint8_t* evid = A.slot_evid + o_slot;
     int32_t* inc_r = S0.inc_r + o_inc; int32_t* inc_x = S0.inc_x + o_inc; int32_t* inc_site = S0.inc_site + o_inc;
@@ -355,7 +371,8 @@ chain_kernel(ChainArgs A) {
     int32_t* sinc_sidx = S0.sinc_sidx + o_sinc; uint8_t* sinc_al = S0.sinc_al + o_sinc;
     int32_t* spos = S0.spos + o_het; uint8_t* sref = S0.sref + o_het; uint8_t* salt = S0.salt + o_het;
     int32_t* site_off = S0.site_off + o_het + d;
-    unsigned long long* bestkey = S0.bestkey + o_het; uint8_t* best_info = S0.best_info + o_het;
+    int32_t* cand_off = S0.cand_off + o_het + d;
+    unsigned long long* bestkey = S0.bestkey + o_het;
     int32_t* site_cnt = S0.site_cnt + o_het; int32_t* site_base = S0.site_base + o_het;
     int32_t* cpos = S0.cpos + o_cand;
     uint8_t* cev = A.cand_evid + lbase;
@@ -382,7 +399,7 @@ chain_kernel(ChainArgs A) {
     };
     const double cul = R.blk_cul[dn.rblk];
 
-    for (int x = tid; x < W; x += CH_THREADS) { label[x] = 0; evid[x] = 0; prim[x] = -1; lvl[x] = -1; icnt[x] = 0; fpos[x] = -1; ord[x] = 0; tmp[x] = 0; }
+    for (int x = tid; x < W; x += CH_THREADS) { label[x] = 0; evid[x] = 0; prim[x] = -1; lvl[x] = -1; fpos[x] = -1; ord[x] = 0xffffffffu; tmp[x] = 0; minkey[x] = 0ull; }
     for (int i = tid; i < nh; i += CH_THREADS) {
         const int64_t row = H[i];
         spos[i] = __ldg(A.sites.pos + row);
@@ -474,91 +491,169 @@ chain_kernel(ChainArgs A) {
     __syncthreads();
 
     int n_inc = 0, n_sinc = 0;
-    if (A.no_extended) {
-        if (tid == 0)
-            for (int k = 0; k < n_seed; ++k) {
-                const int x = canon(seed_e[k]);
-                if (x < 0) continue;
-                label[x] |= seed_hap[k];
-                prim[x] = seed_e[k];
-            }
-        __syncthreads();
-    } else {
+    const int nh_reg = A.no_extended ? 0 : nh;     // --no-extended: seeds are the haplotype lists
+    if (!A.no_extended) {
         // ------------------------------------------------------------ phase 2: het-site incidences
-        for (int i = 0; i < nh; ++i) {
-            const int32_t p = spos[i];
-            if (tid == 0) site_off[i] = n_inc;
-            const int64_t lo = lb_start(R, blk_lo, blk_hi, (int64_t)p - maxspan + 1);
-            const int64_t hi = lb_start(R, lo, blk_hi, (int64_t)p + 1);
-            int n_fetched = 0;
-            for (int64_t base = lo; base < hi; base += CH_THREADS) {
-                const int64_t r = base + tid;
-                const bool ov = r < hi && A.rsum[r].end > p;
-                int tot_ov;
-                const int idx = n_fetched + block_prefix(ov, &tot_ov);
-                n_fetched += tot_ov;
-                const bool ok = ov && idx <= A.ext_goal && pair_ok(A, r, true);
-                int tot;
-                const int k = n_inc + block_prefix(ok, &tot);
-                if (ok && k < cap_inc) {
-                    const int x = canon(r);
-                    inc_r[k] = (int32_t)r;
-                    inc_x[k] = x;
-                    inc_site[k] = i;
-                    inc_sidx[k] = icnt[x];
-                    icnt[x] += 1;
-                    prim[x] = (int32_t)r;          // last writer wins (Q18); sites are sequential
-                }
-                n_inc += tot;
-                __syncthreads();
+        // (a) candidate read range of every het site: fetch(chrom, pos, pos+1) as index range
+        for (int i = tid; i < nh; i += CH_THREADS) {
+            const int64_t p = spos[i];
+            const int64_t lo = lb_start(R, blk_lo, blk_hi, p - maxspan + 1);
+            const int64_t hi = lb_start(R, lo, blk_hi, p + 1);
+            site_base[i] = (int32_t)(lo - blk_lo);
+            site_cnt[i] = (int32_t)(hi - lo);
+        }
+        __syncthreads();
+        // (b) exclusive scan of the range sizes (warp 0), candidates are flattened site-major
+        if (warp == 0) {
+            int run = 0;
+            for (int b0 = 0; b0 < nh; b0 += 32) {
+                const int i = b0 + lane;
+                const int v = i < nh ? site_cnt[i] : 0;
+                int x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                if (i < nh) cand_off[i] = run + x - v;
+                run += __shfl_sync(0xffffffffu, x, 31);
             }
+            if (lane == 0) cand_off[nh] = run;
+        }
+        for (int i = tid; i <= nh; i += CH_THREADS) site_off[i] = 0x7fffffff;
+        __syncthreads();
+        const int n_candidates = cand_off[nh];
+        // (c) one ordered pass over all (site, read) candidates
+        for (int base = 0; base < n_candidates; base += CH_THREADS) {
+            const int c = base + tid;
+            bool ok = false;
+            int i = 0;
+            int64_t r = 0;
+            if (c < n_candidates) {
+                int lo = 0, hi = nh;                               // last i with cand_off[i] <= c
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_off[mid] <= c) lo = mid; else hi = mid; }
+                i = lo;
+                r = blk_lo + site_base[i] + (c - cand_off[i]);
+                const int32_t p = spos[i];
+                bool ov = A.rsum[r].end > p;
+                if (ov && site_cnt[i] > A.ext_goal) {              // Q2: `i > EXTENDED_RB_READ_GOAL` (never in practice)
+                    int idx = 0;
+                    for (int64_t q = blk_lo + site_base[i]; q < r; ++q) idx += A.rsum[q].end > p;
+                    ov = idx <= A.ext_goal;
+                }
+                ok = ov && pair_ok(A, r, true);
+            }
+            int tot;
+            const int k = n_inc + block_prefix(ok, &tot);
+            if (ok && k < cap_inc) {
+                const int x = canon(r);
+                inc_r[k] = (int32_t)r;
+                inc_x[k] = x;
+                inc_site[k] = i;
+                inc_sidx[k] = i;      // order key inside read_sites[x]: registered sites come in site order
+                // fetched_reads[name] = [read, mate]: the last writer (highest site) wins (Q18)
+                atomicMax(minkey + x, ((unsigned long long)(uint32_t)(i + 1) << 32) | (uint32_t)r);
+            }
+            n_inc += tot;
         }
         if (n_inc > cap_inc) { n_inc = (int)cap_inc; T.status |= 2; }
-        if (tid == 0) site_off[nh] = n_inc;
         __syncthreads();
-
-        // ------------------------------------------------------------ phase 3: seed registration
-        if (tid == 0) {
-            int ns = 0;
-            uint32_t order_alt = 0, order_ref = 0;
-            // level-0 iteration order: "alt" list first, then "ref" (Q19); position = first entry
-            for (int k = 0; k < n_seed; ++k) {
-                const int x = canon(seed_e[k]);
-                if (x >= 0 && seed_hap[k] == 2 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (0u << 24) | order_alt++; }
-            }
-            for (int k = 0; k < n_seed; ++k) {
-                const int x = canon(seed_e[k]);
-                if (x >= 0 && seed_hap[k] == 1 && lvl[x] != 0) { lvl[x] = 0; ord[x] = (1u << 24) | order_ref++; }
-            }
-            // registration order: "ref" entries, then "alt" entries (:226-249)
-            for (int pass = 1; pass <= 2; ++pass) {
-                for (int k = 0; k < n_seed; ++k) {
-                    if (seed_hap[k] != pass) continue;
-                    const int64_t e = seed_e[k];
-                    const int x = canon(e);
-                    if (x < 0) continue;
-                    label[x] |= (uint8_t)pass;
-                    prim[x] = (int32_t)e;
-                    if (nh == 0) continue;
-                    const int32_t st = rd_start(R, e), en = A.rsum[e].end;
-                    const int piv = bisect_pivot(spos, nh, st, en);
-                    if (piv < 0) continue;
-                    auto push = [&](int i) {
-                        if (ns < cap_sinc) { sinc_x[ns] = x; sinc_site[ns] = i; sinc_sidx[ns] = icnt[x]; }
-                        icnt[x] += 1;
-                        ++ns;
-                    };
-                    push(piv);
-                    for (int j = piv + 1; j < nh && st <= spos[j] && spos[j] <= en; ++j) push(j);
-                    for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) push(j);
-                }
-            }
-            s_n = ns;
+        for (int k = tid; k < n_inc; k += CH_THREADS)
+            if (k == 0 || inc_site[k - 1] != inc_site[k]) site_off[inc_site[k]] = k;
+        for (int x = tid; x < W; x += CH_THREADS) {
+            const unsigned long long pk = minkey[x];
+            if (pk != 0ull) prim[x] = (int32_t)(uint32_t)pk;
         }
         __syncthreads();
-        n_sinc = s_n;
+        if (tid == 0) {                                             // empty sites inherit the next offset
+            int nxt = n_inc;
+            site_off[nh] = n_inc;
+            for (int i = nh - 1; i >= 0; --i) { if (site_off[i] == 0x7fffffff) site_off[i] = nxt; else nxt = site_off[i]; }
+        }
+        __syncthreads();
+    }
+    {
+        // ------------------------------------------------------------ phase 3: seed registration
+        // Entries register in the order "ref" list then "alt" list (:226-249); the level-0 visit order
+        // is "alt" list first (Q19).  Everything is resolved with order keys instead of a serial loop:
+        //   reg(k)   = position of entry k in the registration order
+        //   prim[x]  = entry with the largest reg  (last writer wins)
+        //   ord[x]   = smallest visit position of the pair
+        int n_ref_entries = 0;
+        for (int base = 0; base < n_seed; base += CH_THREADS) {
+            const int k = base + tid;
+            int tot;
+            block_prefix(k < n_seed && seed_hap[k] == 1, &tot);
+            n_ref_entries += tot;
+        }
+        for (int x = tid; x < W; x += CH_THREADS) minkey[x] = 0ull;
+        __syncthreads();
+        int ref_seen = 0, alt_seen = 0;
+        int ns_total = 0;
+        for (int base = 0; base < n_seed; base += CH_THREADS) {
+            const int k = base + tid;
+            const bool live = k < n_seed;
+            const int hap = live ? seed_hap[k] : 0;
+            int tot_ref, tot_alt;
+            const int pr = block_prefix(hap == 1, &tot_ref);
+            const int pa = block_prefix(hap == 2, &tot_alt);
+            int n_match = 0, piv = -1, x = -1;
+            int32_t st = 0, en = 0;
+            int64_t e = 0;
+            unsigned reg = 0;
+            if (live) {
+                e = seed_e[k];
+                x = canon(e);
+                reg = hap == 1 ? (unsigned)(ref_seen + pr) : (unsigned)(n_ref_entries + alt_seen + pa);
+                if (x >= 0) {
+                    // visit order at level 0: alt entries first, then ref entries
+                    const unsigned visit = hap == 2 ? (unsigned)(alt_seen + pa) : (unsigned)(ref_seen + pr);
+                    atomicMin(ord + x, (hap == 2 ? 0u : (1u << 24)) | (visit & 0xffffffu));
+                    atomicMax(minkey + x, ((unsigned long long)(reg + 1u) << 32) | (uint32_t)e);
+                    unsigned* lw = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(label + x) & ~(uintptr_t)3);
+                    atomicOr(lw, (unsigned)hap << (8 * (reinterpret_cast<uintptr_t>(label + x) & 3)));
+                    lvl[x] = 0;
+                    if (nh_reg > 0) {
+                        st = rd_start(R, e);
+                        en = A.rsum[e].end;
+                        piv = bisect_pivot(spos, nh_reg, st, en);
+                        if (piv >= 0) {
+                            n_match = 1;
+                            for (int j = piv + 1; j < nh_reg && st <= spos[j] && spos[j] <= en; ++j) ++n_match;
+                            for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) ++n_match;
+                        }
+                    }
+                }
+            }
+            // seed incidences may be stored in any order: their position in read_sites[x] is carried by
+            // the order key (after all registered sites, then by registration order, then by the
+            // pivot / right / left order of binary_search, Q16)
+            int tm;
+            const int off_m = block_prefix_sum(n_match, &tm);
+            if (live && n_match > 0) {
+                int w = 0;
+                const unsigned keybase = (unsigned)nh + reg * (unsigned)(nh + 1);
+                const int dst0 = ns_total + off_m;
+                auto push = [&](int i) {
+                    const int dst = dst0 + w;
+                    if (dst < cap_sinc) { sinc_x[dst] = x; sinc_site[dst] = i; sinc_sidx[dst] = (int32_t)(keybase + (unsigned)w); }
+                    ++w;
+                };
+                push(piv);
+                for (int j = piv + 1; j < nh_reg && st <= spos[j] && spos[j] <= en; ++j) push(j);
+                for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) push(j);
+            }
+            ref_seen += tot_ref;
+            alt_seen += tot_alt;
+            ns_total += tm;
+        }
+        __syncthreads();
+        for (int x = tid; x < W; x += CH_THREADS) {
+            const unsigned long long pk = minkey[x];
+            if (pk != 0ull) prim[x] = (int32_t)(uint32_t)pk;
+        }
+        n_sinc = ns_total;
         if (n_sinc > cap_sinc) { n_sinc = (int)cap_sinc; T.status |= 4; }
-
+        __syncthreads();
+    }
+    if (!A.no_extended) {
         // ------------------------------------------------------------ phase 3.5: allele codes
         for (int k = tid; k < n_inc; k += CH_THREADS) {
             const int i = inc_site[k];
@@ -575,7 +670,7 @@ chain_kernel(ChainArgs A) {
             for (int i = tid; i < nh; i += CH_THREADS) { bestkey[i] = KEY_NONE; site_cnt[i] = 0; }
             for (int x = tid; x < W; x += CH_THREADS) minkey[x] = KEY_NONE;
             __syncthreads();
-            // a. best finder key per site
+            // a. best finder per site; the finder's haplotype and allele ride in the low key bits
             for (int k = tid; k < n_inc + n_sinc; k += CH_THREADS) {
                 const bool sd = k >= n_inc;
                 const int kk = sd ? k - n_inc : k;
@@ -585,25 +680,11 @@ chain_kernel(ChainArgs A) {
                 if (!(al & 3)) continue;
                 const int i = sd ? sinc_site[kk] : inc_site[kk];
                 if (spos[i] == fpos[x]) continue;
-                const unsigned long long key = ((unsigned long long)ord[x] << 20) | (unsigned)(sd ? sinc_sidx[kk] : inc_sidx[kk]);
+                const uint8_t fh = (label[x] & 2) ? 2 : 1;          // level 0: the "alt" visit comes first
+                const unsigned long long key = ((unsigned long long)ord[x] << 36) |
+                                               ((unsigned long long)(uint32_t)(sd ? sinc_sidx[kk] : inc_sidx[kk]) << 4) |
+                                               (unsigned long long)((fh << 2) | (al & 3));
                 atomicMin(bestkey + i, key);
-            }
-            __syncthreads();
-            for (int k = tid; k < n_inc + n_sinc; k += CH_THREADS) {
-                const bool sd = k >= n_inc;
-                const int kk = sd ? k - n_inc : k;
-                const int x = sd ? sinc_x[kk] : inc_x[kk];
-                if (lvl[x] != level) continue;
-                const uint8_t al = sd ? sinc_al[kk] : inc_al[kk];
-                if (!(al & 3)) continue;
-                const int i = sd ? sinc_site[kk] : inc_site[kk];
-                if (spos[i] == fpos[x]) continue;
-                const unsigned long long key = ((unsigned long long)ord[x] << 20) | (unsigned)(sd ? sinc_sidx[kk] : inc_sidx[kk]);
-                if (key == bestkey[i]) {
-                    const uint8_t lab = label[x];
-                    const uint8_t fh = (lab & 2) ? 2 : 1;       // level 0: the "alt" visit comes first
-                    best_info[i] = (uint8_t)((fh << 2) | (al & 3));
-                }
             }
             __syncthreads();
             // b. earliest claiming key per unlabelled pair
@@ -630,8 +711,7 @@ chain_kernel(ChainArgs A) {
                     }
                     const unsigned b = __ballot_sync(0xffffffffu, claim);
                     if (claim) {
-                        const uint8_t info = best_info[i];
-                        const uint8_t fh = info >> 2, fa = info & 3, ta = inc_al[k] >> 2;
+                        const uint8_t fh = (uint8_t)((bk >> 2) & 3), fa = (uint8_t)(bk & 3), ta = inc_al[k] >> 2;
                         const uint8_t nh_ = (ta == fa) ? fh : (uint8_t)(3 - fh);
                         tmp[x] = (i << 8) | (nh_ << 4) | 1;
                         ord[x] = (uint32_t)(cnt + __popc(b & ((1u << lane) - 1u)));   // rank inside the site
@@ -816,7 +896,7 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
             b_hi = lb_start(reads, b_lo, blk_hi, maxB);
             if (b_lo <= a_hi) { a_hi = max(a_hi, b_hi); a_lo = min(a_lo, b_lo); b_lo = b_hi = 0; }
         }
-        nd[0] = (a_hi - a_lo) + (b_hi - b_lo);
+        nd[0] = ((a_hi - a_lo) + (b_hi - b_lo) + 3) & ~(int64_t)3;   // word-aligned label/evidence regions
         // seed entries and the het sites each entry registers (start <= pos <= end)
         int64_t seeds = 0, sincs = 0;
         for (int wdx = 0; wdx < (sv ? 2 : 1); ++wdx) {
@@ -943,6 +1023,7 @@ Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_
     S.sinc_sidx = (int32_t*)carve<int32_t>(p, sincs); S.sinc_al = (uint8_t*)carve<uint8_t>(p, sincs);
     S.spos = (int32_t*)carve<int32_t>(p, hets); S.sref = (uint8_t*)carve<uint8_t>(p, hets);
     S.salt = (uint8_t*)carve<uint8_t>(p, hets); S.site_off = (int32_t*)carve<int32_t>(p, hets + n_dnms + 1);
+    S.cand_off = (int32_t*)carve<int32_t>(p, hets + n_dnms + 1);
     S.bestkey = (unsigned long long*)carve<unsigned long long>(p, hets); S.best_info = (uint8_t*)carve<uint8_t>(p, hets);
     S.site_cnt = (int32_t*)carve<int32_t>(p, hets); S.site_base = (int32_t*)carve<int32_t>(p, hets);
     S.cpos = (int32_t*)carve<int32_t>(p, cands);

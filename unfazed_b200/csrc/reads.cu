@@ -58,13 +58,22 @@ struct ScanParams {
 };
 
 __device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, int beg, int end, uint32_t minq) {
-    // number of bytes b in s[beg,end) with (b & 0x7f) < minq; minq in [0,128]
+    // number of bytes b in s[beg,end) with (b & 0x7f) < minq; minq in [0,128].
+    // Per word: t = (x | 0x80..) - m4 never borrows across bytes (x, m <= 128), and bit 7 of a byte
+    // of t is clear exactly when x < m.  Byte-wise counters are summed with one multiply; POPC is
+    // avoided on purpose (it issues on the quarter-rate XU pipe and was the top pipe in ncu).
     int cnt = 0, i = beg;
     const uint32_t m4 = minq * 0x01010101u;
     while (i < end && (i & 3)) { cnt += (uint32_t)(s[i] & 0x7f) < minq; ++i; }
-    for (; i + 4 <= end; i += 4) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(s + i) & 0x7f7f7f7fu;
-        cnt += __popc(__vcmpltu4(w, m4)) >> 3;
+    while (i + 4 <= end) {
+        uint32_t acc = 0;
+        const int stop = min(end - 3, i + 4 * 63);          // <= 63 words: byte counters stay < 256
+        for (; i < stop; i += 4) {
+            const uint32_t x = *reinterpret_cast<const uint32_t*>(s + i) & 0x7f7f7f7fu;
+            const uint32_t t = (x | 0x80808080u) - m4;
+            acc += (~t & 0x80808080u) >> 7;
+        }
+        cnt += (int)((acc * 0x01010101u) >> 24);
     }
     for (; i < end; ++i) cnt += (uint32_t)(s[i] & 0x7f) < minq;
     return cnt;
@@ -229,6 +238,217 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K2, pipelined variant: used when a whole tile's quality span fits one stage
+// (tile_reads * max l_seq <= RS_STAGE - 32).
+//  * every CTA owns a CONTIGUOUS range of tiles, so the site-row window and the read block are
+//    carried from tile to tile instead of being re-searched (one binary search per CTA);
+//  * two quality stages per CTA: the TMA bulk copy of tile j+1 is issued at the top of iteration j;
+//  * headers are prefetched two tiles ahead, so the spans TMA needs are already in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_STAGE = 36 * 1024;
+
+__global__ void __launch_bounds__(RS_THREADS)
+read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
+                      int tile_reads, UnfzReadSum* __restrict__ out, int32_t* __restrict__ blk_maxspan) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stage[2] = {smem, smem + RS_STAGE};
+    int32_t* spos = reinterpret_cast<int32_t*>(smem + 2 * RS_STAGE);
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int64_t s_qa[3], s_qb[3];
+    __shared__ int64_t s_base, s_row_end;
+    __shared__ int32_t s_rb0, s_maxspan;
+
+    const int64_t n = reads.n_reads;
+    const int64_t n_tiles = (n + tile_reads - 1) / tile_reads;
+    const int64_t tpc = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * tpc;
+    const int64_t t1 = min(t0 + tpc, n_tiles);
+    if (t0 >= t1) return;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+    }
+    uint32_t phase[2] = {0, 0};
+    const bool lane_ok = (int)threadIdx.x < tile_reads;
+
+    auto hdr_of = [&](int64_t tile, bool& live) -> UnfzRead {
+        const int64_t r = tile * tile_reads + threadIdx.x;
+        live = lane_ok && tile < t1 && r < n;
+        UnfzRead h;
+        h.start = 0; h.l_seq = 0; h.n_cigar = 0; h.qoff_lo = 0; h.qoff_hi = 0;
+        if (live) h = load_read(reads.hdr + r);
+        return h;
+    };
+    auto publish_span = [&](int64_t tile, const UnfzRead& h, bool live) {     // slot tile % 3
+        if (tile >= t1) return;
+        const int64_t r0 = tile * tile_reads;
+        const int64_t last = min(r0 + tile_reads, n) - 1;
+        const int64_t r = r0 + threadIdx.x;
+        const int slot = (int)((tile - t0) % 3);
+        if (threadIdx.x == 0) s_qa[slot] = read_qoff(h);
+        if (live && r == last) s_qb[slot] = read_qoff(h) + h.l_seq;
+    };
+    auto issue = [&](int64_t tile) {                                          // thread 0 only
+        const int slot = (int)((tile - t0) % 3), st = (int)((tile - t0) & 1);
+        const int64_t qa = s_qa[slot], qb = s_qb[slot];
+        if (qb > qa) {
+            const int64_t ga = qa & ~(int64_t)15;
+            const uint32_t bytes = (uint32_t)(((qb - ga) + 15) & ~(int64_t)15);
+            fence_proxy_async();
+            mbar_expect_tx(&bar[st], bytes);
+            tma_bulk_g2s(stage[st], reads.qual + ga, bytes, &bar[st]);
+        }
+    };
+
+    bool live, live1, live2 = false;
+    UnfzRead h = hdr_of(t0, live);
+    UnfzRead h1 = hdr_of(t0 + 1, live1);
+    UnfzRead h2 = h1;
+    publish_span(t0, h, live);
+    publish_span(t0 + 1, h1, live1);
+    if (threadIdx.x == 0) {
+        const int64_t r0 = t0 * tile_reads;
+        const int rb = (int)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r0) - 1);
+        s_rb0 = rb;
+        const int sb0 = reads.blk_sblk[rb];
+        int64_t rowb = 0, rowe = 0;
+        if (sb0 >= 0) {
+            rowe = sites.blk_off[sb0 + 1];
+            rowb = lower_bound_dev(sites.pos, sites.blk_off[sb0], rowe, h.start);
+        }
+        s_base = rowb;
+        s_row_end = rowe;
+        s_maxspan = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) issue(t0);
+
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int st = (int)((tile - t0) & 1);
+        const int slot = (int)((tile - t0) % 3);
+        h2 = hdr_of(tile + 2, live2);                        // in flight during this iteration
+        if (threadIdx.x == 0 && tile + 1 < t1) issue(tile + 1);
+        const int64_t r0 = tile * tile_reads;
+        const int64_t r = r0 + threadIdx.x;
+        const int rb0 = s_rb0;
+        const int64_t row_base = s_base, row_end = s_row_end;
+        for (int i = threadIdx.x; i < RS_SPOS; i += RS_THREADS)
+            spos[i] = (row_base + i < row_end) ? __ldg(sites.pos + row_base + i) : 0x7fffffff;
+        int rb = rb0;
+        if (live && r >= reads.blk_off[rb + 1])
+            rb = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb, (int64_t)reads.n_blocks + 1, r) - 1);
+        const int sb = live ? reads.blk_sblk[rb] : -1;
+
+        int32_t end = 0;
+        uint32_t flags = 0;
+        if (live) {
+            int none_cnt = 0, non_m = 0;
+            end = h.start;
+            const uint32_t* cg = reads.cigar + h.cigar_off;
+            for (int k = 0; k < h.n_cigar; ++k) {
+                const uint32_t w = __ldg(cg + k);
+                const uint32_t op = w & 15u, ln = w >> 4;
+                if (op == 0 || op == 7 || op == 8 || op == 2 || op == 3) end += (int32_t)ln;
+                if (op == 1 || op == 4) none_cnt += (int)ln;
+                if (op != 0 && op != 7) ++non_m;
+            }
+            const uint32_t f = h.flag;
+            const bool base_ok = !(f & (0x200u | 0x4u | 0x400u | 0x100u | 0x800u | 0x8u)) &&
+                                 (int)h.mapq >= P.min_mapq && (h.aux & 1u);
+            if (base_ok) flags |= UNFZ_RS_GOOD_DISC;
+            if (none_cnt <= 5) flags |= UNFZ_RS_NONE_OK;
+            if (non_m <= 5) flags |= UNFZ_RS_EXT_OK;
+            long long ins = (long long)h.tlen - 2ll * P.readlen;
+            if (ins < 0) ins = -ins;
+            if ((double)ins <= reads.blk_cul[rb]) flags |= UNFZ_RS_INS_OK;
+            if ((f & 1u) && !(f & 8u) && h.mate >= 0) flags |= UNFZ_RS_HAS_MATE;
+            atomicMax(&s_maxspan, end - h.start);
+        }
+        __syncthreads();   // spos visible
+
+        int32_t fmark = 0, cnt = 0;
+        if (live && sb >= 0) {
+            int64_t lbs, lbe;
+            if (rb == rb0) {
+                int lo = 0, hi = RS_SPOS;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h.start) lo = mid + 1; else hi = mid; }
+                int lo2 = lo; hi = RS_SPOS;
+                while (lo2 < hi) { int mid = (lo2 + hi) >> 1; if (spos[mid] < end) lo2 = mid + 1; else hi = mid; }
+                lbs = row_base + lo;
+                lbe = row_base + lo2;
+                if (lo2 == RS_SPOS) {
+                    if (lo == RS_SPOS) lbs = lower_bound_dev(sites.pos, row_base + RS_SPOS - 1, row_end, h.start);
+                    lbe = lower_bound_dev(sites.pos, lbs, row_end, end);
+                }
+            } else {
+                const int64_t a = sites.blk_off[sb], b = sites.blk_off[sb + 1];
+                lbs = lower_bound_dev(sites.pos, a, b, h.start);
+                lbe = lower_bound_dev(sites.pos, lbs, b, end);
+            }
+            fmark = __ldg(mark_prefix + lbs);
+            const int32_t c = __ldg(mark_prefix + lbe) - fmark;
+            cnt = c > 0xffff ? 0xffff : c;
+        }
+
+        int low = 0;
+        const int64_t qa = s_qa[slot], qb = s_qb[slot];
+        if (qb > qa) {
+            mbar_wait(&bar[st], phase[st]);
+            phase[st] ^= 1u;
+            if (live && h.l_seq > 0) {
+                const int off = (int)(read_qoff(h) - (qa & ~(int64_t)15));
+                low = count_low_quals(stage[st], off, off + h.l_seq, (uint32_t)P.min_bq);
+            }
+        }
+        if (live) {
+            if ((flags & UNFZ_RS_GOOD_DISC) && low <= 10 && h.n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
+            UnfzReadSum o;
+            o.end = end; o.fmark = fmark; o.flags = (uint16_t)flags; o.cnt = (uint16_t)cnt; o.hoff = 0;
+            *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
+        }
+        // ---- hand-over to the next tile ---------------------------------------------------------
+        publish_span(tile + 2, h2, live2);                   // slot (tile+2)%3 is not in use
+        if (threadIdx.x == 0) {
+            const int64_t rn = (tile + 1) * tile_reads;
+            // flush the span of this tile to every block it touches, then carry the window forward
+            const int64_t last = min(r0 + tile_reads, n) - 1;
+            int rb_last = rb0;
+            if (last >= reads.blk_off[rb0 + 1])
+                rb_last = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb0, (int64_t)reads.n_blocks + 1, last) - 1);
+            if (s_maxspan > 0)
+                for (int b = rb0; b <= rb_last; ++b) atomicMax(blk_maxspan + b, s_maxspan);
+            s_maxspan = 0;
+            if (tile + 1 < t1 && rn < n) {
+                if (rn >= reads.blk_off[rb0 + 1]) {           // next tile starts in another read block
+                    const int rbn = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb0, (int64_t)reads.n_blocks + 1, rn) - 1);
+                    s_rb0 = rbn;
+                    const int sbn = reads.blk_sblk[rbn];
+                    int64_t rowb = 0, rowe = 0;
+                    if (sbn >= 0) {
+                        rowe = sites.blk_off[sbn + 1];
+                        rowb = lower_bound_dev(sites.pos, sites.blk_off[sbn], rowe, h1.start);
+                    }
+                    s_base = rowb;
+                    s_row_end = rowe;
+                } else {
+                    int lo = 0, hi = RS_SPOS;                 // first staged row with pos >= next tile's first start
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h1.start) lo = mid + 1; else hi = mid; }
+                    int64_t nb = row_base + lo;
+                    if (lo == RS_SPOS) nb = lower_bound_dev(sites.pos, row_base + RS_SPOS - 1, row_end, h1.start);
+                    s_base = nb;
+                }
+            }
+        }
+        h = h1; live = live1;
+        h1 = h2; live1 = live2;
+        __syncthreads();   // stage st, spos and the carried state are consistent for the next tile
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: read x marked-site allele lookup
 // ------------------------------------------------------------------------------------------------
@@ -291,7 +511,7 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
 }  // namespace
 
 extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
-                              const int32_t* mark_prefix, const UnfzParams* hp, UnfzReadSum* out,
+                              const int32_t* mark_prefix, const UnfzParams* hp, int32_t max_l_seq, UnfzReadSum* out,
                               int32_t* blk_maxspan, void* stream) {
     if (reads->n_reads <= 0) return 0;
     ScanParams P;
@@ -299,6 +519,22 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     double bq = hp->min_gt_qual;
     P.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));
     P.readlen = hp->readlen;
+    if (max_l_seq > 0 && (int64_t)max_l_seq + 32 <= RS_STAGE) {
+        int tile_reads = (RS_STAGE - 32) / max_l_seq;
+        if (tile_reads > RS_THREADS) tile_reads = RS_THREADS;
+        const size_t smem2 = 2 * RS_STAGE + RS_SPOS * sizeof(int32_t);
+        static bool attr2 = false;
+        if (!attr2) {
+            UNFZ_CHECK(ctx, cudaFuncSetAttribute(read_scan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            attr2 = true;
+        }
+        const int64_t tiles = (reads->n_reads + tile_reads - 1) / tile_reads;
+        int64_t g = (int64_t)ctx->sm_count * 3;     // 3 CTAs x 72 KB of staging per SM
+        if (g > tiles) g = tiles;
+        read_scan_pipe_kernel<<<(unsigned)g, RS_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, tile_reads, out, blk_maxspan);
+        UNFZ_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     const size_t smem = RS_QBUF + 16 + RS_SPOS * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {

@@ -71,6 +71,7 @@ class DeviceReads:
     def __init__(self, table: ReadTable, device: torch.device, pin: bool = False):
         self.table = table
         self.n_reads = table.n_reads
+        self.max_l_seq = int(table.hdr["l_seq"].max()) if table.n_reads else 0
         up = lambda a, pad=0: _to_device(np.ascontiguousarray(a), device, pin, pad)
         self.blk_off = up(table.blk_off.astype(np.int64))
         self.hdr = up(table.hdr.view(np.uint8).reshape(-1))
@@ -291,7 +292,7 @@ class Engine:
             blk_maxspan = self._zeros(dreads.table.n_blocks, torch.int32)
             total_hits = self._zeros(1, torch.int64)
             mark("alloc2")
-            self._check(lib.unfz_read_scan(ctx, rc_, sc, mark_prefix.data_ptr(), C.byref(params), rsum.data_ptr(),
+            self._check(lib.unfz_read_scan(ctx, rc_, sc, mark_prefix.data_ptr(), C.byref(params), dreads.max_l_seq, rsum.data_ptr(),
                                            blk_maxspan.data_ptr(), s), "read_scan")
             launches += 1
             mark("read_scan")

@@ -65,51 +65,58 @@ def make_ds(args, rank, n_dnms=None):
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a
+    thread (the timed region of this benchmark is tens of milliseconds, too short for nvidia-smi -lms)."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _poll(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)): "sw_power_cap",
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -303,6 +310,13 @@ def run_b200(args):
             if v["bytes"] and v["ms"] > 0:
                 v["gbps"] = v["bytes"] / (v["ms"] * 1e6)
                 v["frac"] = v["gbps"] / peak
+        try:
+            sat = saturating_classify(eng, max(args.steps, 3))
+            sat["gbps"] = sat["bytes"] / (sat["classify_ms"] * 1e6)
+            sat["frac"] = sat["gbps"] / peak
+            sat["pairs_per_s"] = sat["pairs"] / (sat["classify_ms"] / 1000.0)
+        except Exception as e:  # keep the headline line even if the extra measurement cannot run
+            sat = {"error": repr(e)}
         dom = max(kern, key=lambda k: kern[k]["ms"])
         domk = kern[dom]
         lookup_ms = kern["read_scan"]["ms"] + kern["read_site_alleles"]["ms"]
@@ -311,6 +325,7 @@ def run_b200(args):
             "achieved": domk.get("gbps"), "frac": domk.get("frac"), "traffic": None,
             "ms_per_launch": domk["ms"],
             "kernels": kern,
+            "classify_sites_saturating": sat,
             "read_allele_lookup_survey_bytes": {
                 "bytes": survey_read_bytes, "ms": lookup_ms,
                 "gbps": survey_read_bytes / (lookup_ms * 1e6) if lookup_ms > 0 else None,
@@ -343,6 +358,72 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def saturating_classify(eng, steps, n_rows=1 << 25, rows_per_window=336):
+    """Bandwidth measurement of the site classifier alone (SURVEY 8(d) "saturating variant"): the
+    named configs move only 15-150 MB through it, i.e. they are launch-bound.  2^25 rows (1.5 GB of
+    site columns, generated on the device) are covered once by non-overlapping DNM windows."""
+    import ctypes as C
+    import torch
+    from unfazed_b200 import _lib as L
+    from unfazed_b200.engine import make_params
+    from unfazed_b200.plan import Plan
+    dev = eng.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    V = n_rows
+    pos = (torch.arange(V, device=dev, dtype=torch.int32) * 3)
+    flag = (torch.rand(V, device=dev, generator=g) < 0.98).to(torch.uint8)
+    gt_codes = torch.tensor([0, 1, 3, 2], device=dev, dtype=torch.uint8)
+    gt = gt_codes[torch.multinomial(torch.tensor([0.45, 0.35, 0.19, 0.01], device=dev), 3 * V, replacement=True, generator=g)].reshape(3, V).contiguous()
+    gq = torch.where(torch.rand(3, V, device=dev, generator=g) < 0.05, torch.rand(3, V, device=dev, generator=g) * 40, torch.full((3, V), 99.0, device=dev)).to(torch.float32).contiguous()
+    depth = torch.poisson(torch.full((3, V), 30.0, device=dev), generator=g).to(torch.int32)
+    frac = torch.where(gt == 1, 0.5, torch.where(gt == 3, 0.99, 0.01))
+    ad = torch.round(depth * frac + torch.randn(3, V, device=dev, generator=g) * 2).clamp(min=0).to(torch.int32)
+    ad = torch.minimum(ad, depth).contiguous()
+    rd = (depth - ad).contiguous()
+    ref = torch.full((V,), 65, device=dev, dtype=torch.uint8)
+    alt = torch.full((V,), 67, device=dev, dtype=torch.uint8)
+    blk_off = torch.tensor([0, V], device=dev, dtype=torch.int64)
+
+    from unfazed_b200.engine import make_site_cols, pack_site_rows
+
+    class Raw:
+        pass
+    ds = Raw()
+    ds.n_rows = V
+    meta, rec, dep = pack_site_rows(pos, flag, gt, gq, rd, ad)
+    del flag, gt, gq, rd, ad, depth, frac
+    ds.keep = (pos, ref, alt, blk_off, meta, rec, dep)
+    ds.cols = make_site_cols(V, 1, blk_off, pos, ref, alt, meta, rec, dep)
+    n_win = V // rows_per_window
+    seg = np.zeros(n_win, dtype=L.SEG_DTYPE)
+    seg["sblk"] = 0
+    seg["lo_pos"] = np.arange(n_win, dtype=np.int64) * rows_per_window * 3
+    seg["hi_pos"] = seg["lo_pos"] + rows_per_window * 3 - 1
+    seg["mult"] = 1
+    seg["dnm"] = np.arange(n_win)
+    seg["mode"] = L.MODE_READ
+    dnm = np.zeros(n_win, dtype=L.DNM_DTYPE)
+    dnm["seg_lo"] = np.arange(n_win)
+    dnm["seg_hi"] = dnm["seg_lo"] + 1
+    dnm["rblk"], dnm["cnv_entry"] = -1, -1
+    dnm["pos"] = seg["lo_pos"] + 1
+    dnm["end"] = dnm["pos"] + 1
+    plan = Plan(dnm=dnm, seg=seg, alleles=np.zeros(0, np.uint8), entries=[{}] * n_win, trio=np.zeros(n_win, np.int32),
+                found=np.ones(n_win, bool))
+    params = make_params()
+    for _ in range(3):
+        eng.run(ds, None, plan, params, keep_device=False)
+    ms = {}
+    for _ in range(steps):
+        r = eng.run(ds, None, plan, params, time_stages=True, keep_device=False)
+        for k, v in r.timings_ms.items():
+            ms[k] = ms.get(k, 0.0) + v / steps
+    return {"pairs": int(r.n_pairs), "rows": V, "windows": n_win, "classify_ms": ms.get("classify_sites"),
+            "compact_ms": ms.get("compact_sites"), "window_search_ms": ms.get("window_search"),
+            "bytes": 45.0 * r.n_pairs}
 
 
 def _pin_table(t):

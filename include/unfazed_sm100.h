@@ -65,20 +65,24 @@ extern "C" {
 #define UNFZ_EV_AMBIG_BOTH        0x10
 #define UNFZ_EV_SEX_CHROM         0x20
 
-/* Trio-major site columns (schema.SiteTable).  44 B per row: pos 4 + flag 1 + 3*(gt 1+gq 4+rd 4+ad 4). */
+/* Trio-major site rows on the DEVICE.  The host table (schema.SiteTable) is plain SoA; at upload the
+ * genotype fields are packed so that the classifier reads one row with five naturally aligned loads
+ * (44 B per row, the "canonical" byte count of SURVEY 8(a)-3):
+ *   meta u32      flag | gt_kid<<8 | gt_dad<<16 | gt_mom<<24   (cyvcf2 gt_types 0/1/2/3)        4 B
+ *   rec  4 x f32  { pos (int32 bits), gq_kid, gq_dad, gq_mom }                                  16 B
+ *   dep  6 x i32  { rd_kid, ad_kid, rd_dad, ad_dad, rd_mom, ad_mom }                            24 B
+ * pos / ref / alt are kept as separate columns for the read path and the host. */
 typedef struct {
-    int64_t        n_rows;
-    int32_t        n_blocks;
-    int32_t        _pad;
-    const int64_t* blk_off;      /* [n_blocks+1] */
-    const int32_t* pos;
-    const uint8_t* flag;         /* bit0: simple biallelic SNV record */
-    const uint8_t* ref;          /* ASCII */
-    const uint8_t* alt;          /* ASCII */
-    const uint8_t* gt[3];        /* kid, dad, mom: cyvcf2 gt_types 0/1/2/3 */
-    const float*   gq[3];
-    const int32_t* rd[3];
-    const int32_t* ad[3];
+    int64_t         n_rows;
+    int32_t         n_blocks;
+    int32_t         _pad;
+    const int64_t*  blk_off;     /* [n_blocks+1] */
+    const int32_t*  pos;
+    const uint8_t*  ref;         /* ASCII */
+    const uint8_t*  alt;         /* ASCII */
+    const uint32_t* meta;        /* bit0 of the low byte: simple biallelic SNV record */
+    const float*    rec;         /* [n_rows][4], 16-byte aligned */
+    const int32_t*  dep;         /* [n_rows][6],  8-byte aligned */
 } UnfzSiteCols;
 
 /* 32-byte read header (schema.READ_HDR) */
@@ -192,6 +196,8 @@ int unfz_exclusive_scan_i64(UnfzCtx*, const int64_t* in, int64_t* out, int64_t n
 int unfz_exclusive_scan_u16_u32(UnfzCtx*, const uint16_t* in, int64_t in_stride_bytes, uint32_t* out,
                                 int64_t out_stride_bytes, int64_t n, int64_t* total_out, void* work, void* stream);
 int unfz_exclusive_scan_u8_i32(UnfzCtx*, const uint8_t* in, int32_t* out, int64_t n, void* work, void* stream);
+/* n_rows independent rows in one launch: in[n_rows][n] -> out[n_rows][n+1] (last entry = row total) */
+int unfz_exclusive_scan_rows_i64(UnfzCtx*, const int64_t* in, int64_t* out, int32_t n_rows, int64_t n, void* stream);
 
 /* Window membership: informative_site_finder.py get_position :10-43 / get_close_vars :399-420.
  * For every segment: seg_row_lo = first row of the block with pos >= lo_pos, seg_count =

@@ -20,8 +20,8 @@ c_void_p, c_int32, c_int64, c_double = C.c_void_p, C.c_int32, C.c_int64, C.c_dou
 class SiteCols(C.Structure):
     _fields_ = [
         ("n_rows", c_int64), ("n_blocks", c_int32), ("_pad", c_int32),
-        ("blk_off", c_void_p), ("pos", c_void_p), ("flag", c_void_p), ("ref", c_void_p), ("alt", c_void_p),
-        ("gt", c_void_p * 3), ("gq", c_void_p * 3), ("rd", c_void_p * 3), ("ad", c_void_p * 3),
+        ("blk_off", c_void_p), ("pos", c_void_p), ("ref", c_void_p), ("alt", c_void_p),
+        ("meta", c_void_p), ("rec", c_void_p), ("dep", c_void_p),
     ]
 
 
@@ -80,6 +80,7 @@ SYMBOLS = {
     "unfz_exclusive_scan_i64": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
     "unfz_exclusive_scan_u16_u32": (C.c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, _P, _P]),
     "unfz_exclusive_scan_u8_i32": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
+    "unfz_exclusive_scan_rows_i64": (C.c_int, [_P, _P, _P, c_int32, c_int64, _P]),
     "unfz_window_search": (C.c_int, [_P, C.POINTER(SiteCols), _P, c_int32, _P, _P, _P]),
     "unfz_classify_sites": (C.c_int, [_P, C.POINTER(SiteCols), _P, _P, _P, c_int32, c_int64, C.POINTER(Params), _P, _P]),
     "unfz_compact_sites": (C.c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -114,7 +114,41 @@ int scan_impl(UnfzCtx* ctx, const TIn* in, int64_t in_stride, TOut* out, int64_t
     return 0;
 }
 
+// several independent rows in ONE launch: one CTA per row, sequential tiles with a running carry
+__global__ void __launch_bounds__(SCAN_THREADS)
+rows_scan_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+    const int64_t* src = in + (int64_t)blockIdx.x * n;
+    int64_t* dst = out + (int64_t)blockIdx.x * (n + 1);
+    int64_t carry = 0;
+    for (int64_t t0 = 0; t0 < n; t0 += SCAN_TILE) {
+        const int64_t base = t0 + (int64_t)threadIdx.x * SCAN_ITEMS;
+        int64_t v[SCAN_ITEMS];
+        int64_t s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = (base + k < n) ? src[base + k] : 0;
+            s += v[k];
+        }
+        int64_t total;
+        int64_t run = carry + block_exclusive_scan(s, &total);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (base + k < n) dst[base + k] = run;
+            run += v[k];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) dst[n] = carry;
+}
+
 }  // namespace
+
+extern "C" int unfz_exclusive_scan_rows_i64(UnfzCtx* ctx, const int64_t* in, int64_t* out, int32_t n_rows, int64_t n, void* stream) {
+    if (n_rows <= 0) return 0;
+    rows_scan_kernel<<<n_rows, SCAN_THREADS, 0, (cudaStream_t)stream>>>(in, out, n);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
 
 extern "C" int64_t unfz_scan_work_bytes(int64_t n) {
     // tile sums + scanned tile sums at every recursion level (geometric), generous bound

@@ -5,6 +5,8 @@
 // consecutive pairs, which map to consecutive rows of the SoA site columns inside one DNM window
 // -> every column load of a warp is one contiguous 32..128 B span.  Allele balance is IEEE double
 // division exactly like the reference's np.int32 / float (informative_site_finder.py:69).
+#include <math.h>
+
 #include "common.cuh"
 
 namespace {
@@ -31,138 +33,232 @@ __global__ void window_search_kernel(UnfzSiteCols sites, const UnfzSegIn* __rest
 // ------------------------------------------------------------------------------------------------
 // K1: classification
 // ------------------------------------------------------------------------------------------------
+// per-genotype thresholds, indexed by the cyvcf2 gt code (2 = unknown -> never high quality).
+// fp32 pre-filter of the allele-balance test: q ~ ad/tot in fp32 (a few ulp), so q inside
+// [in_lo, in_hi] proves the fp64 test true and q outside [out_lo, out_hi] proves it false; only
+// ratios within ~1e-6 of a threshold take the exact IEEE fp64 division.  ad == 0 / ad == tot give
+// exactly 0.0 / 1.0 and are decided on the host in fp64 (flags).
+struct GtThr {
+    float4 f;             // in_lo, in_hi, out_lo, out_hi
+    double lo, hi;        // the fp64 thresholds for the exact path
+    int32_t flags;        // bit0 valid genotype, bit1 0.0 in range, bit2 1.0 in range
+    int32_t _pad;
+};
+
 struct ClsParams {
-    double ab[3][2];      // indexed by range id: 0 homref, 1 het, 2 homalt
-    double min_gq;
+    GtThr thr[4];
+    float min_gq_f;       // smallest float >= min_gq: for a float gq, (double)gq < min_gq <=> gq < min_gq_f
     int32_t min_depth;
 };
 
-// is_high_quality_site, informative_site_finder.py:46-73
-__device__ __forceinline__ bool high_quality(const ClsParams& P, int gt, float gq, int32_t rd, int32_t ad) {
-    int r;
-    if (gt == 0) r = 0; else if (gt == 3) r = 2; else if (gt == 1) r = 1; else return false;
-    if ((double)gq < P.min_gq) return false;
-    const int32_t tot = (int32_t)((uint32_t)rd + (uint32_t)ad);    // numpy int32 add wraps
-    if (tot < P.min_depth) return false;
+// exact: min_ab <= float(ad / float(rd+ad)) <= max_ab, informative_site_finder.py:69-71
+__device__ __noinline__ bool ab_exact(double lo, double hi, int32_t ad, int32_t tot) {
     const double ab = (double)ad / (double)tot;                     // IEEE division, NaN/inf as numpy
-    return P.ab[r][0] <= ab && ab <= P.ab[r][1];
+    return lo <= ab && ab <= hi;
 }
 
-// get_kid_allele, informative_site_finder.py:76-134.  returns 0 none, 1 ref_parent, 2 alt_parent
-__device__ __forceinline__ int kid_allele(const ClsParams& P, int mode, int gk, const int32_t rd[3], const int32_t ad[3]) {
-    const int32_t tk = (int32_t)((uint32_t)rd[0] + (uint32_t)ad[0]);
-    if (mode == UNFZ_MODE_CNV_DEL && tk > 4) {
-        if (gk == 3) return 1;
-        if (gk == 0) return 2;
-        return 0;
-    }
-    if (mode == UNFZ_MODE_CNV_DUP && rd[0] > 2 && ad[0] > 2 && tk > P.min_depth) {
-        if (gk != 1) return 0;
-        const double k = (double)ad[0] / (double)tk;
-        const double d = (double)ad[1] / (double)(int32_t)((uint32_t)rd[1] + (uint32_t)ad[1]);
-        const double m = (double)ad[2] / (double)(int32_t)((uint32_t)rd[2] + (uint32_t)ad[2]);
-        const double dm = d + m;
-        if ((dm < 1.0 && k > 0.5) || (dm > 1.0 && k < 0.5)) return 0;
-        if (k >= 0.67) return 2;
-        if (k <= 0.33) return 1;
-        return 0;
-    }
+// DUP branch of get_kid_allele :89-130 (exact fp64); returns 0 none, 1 ref_parent, 2 alt_parent
+__device__ __noinline__ int kid_allele_dup(int32_t rd0, int32_t ad0, int32_t rd1, int32_t ad1, int32_t rd2, int32_t ad2) {
+    const double k = (double)ad0 / (double)(int32_t)((uint32_t)rd0 + (uint32_t)ad0);
+    const double d = (double)ad1 / (double)(int32_t)((uint32_t)rd1 + (uint32_t)ad1);
+    const double m = (double)ad2 / (double)(int32_t)((uint32_t)rd2 + (uint32_t)ad2);
+    const double dm = d + m;
+    if ((dm < 1.0 && k > 0.5) || (dm > 1.0 && k < 0.5)) return 0;
+    if (k >= 0.67) return 2;
+    if (k <= 0.33) return 1;
     return 0;
 }
 
-// find :252-339 == add_good_candidate_variant :457-542 for one (DNM, row)
-__device__ __forceinline__ uint8_t classify_pair(const ClsParams& P, int mode, int32_t pos, int32_t excl_lo,
-                                                 int32_t excl_hi, uint8_t flag, const uint8_t gt[3],
+// One (DNM, row) pair: is_high_quality_site :46-73, get_kid_allele :76-134 and the classifier
+// find :252-339 == add_good_candidate_variant :457-542.
+// Written branch-free (a warp covers 32 different rows, so every early exit of the reference would
+// be taken by some lane anyway); all predicates are pure, so the evaluation order is irrelevant.
+// Only two rare events branch: an allele balance within 1e-6 of a threshold (exact fp64 division)
+// and the DUP allele-balance rule.
+__device__ __forceinline__ uint8_t classify_pair(const GtThr* __restrict__ thr, const uint8_t* __restrict__ gt_lut,
+                                                 float min_gq_f, int32_t min_depth, int mode,
+                                                 int32_t pos, int32_t excl_lo, int32_t excl_hi, uint32_t meta,
                                                  const float gq[3], const int32_t rd[3], const int32_t ad[3]) {
-    if (!(flag & 1)) return 0;                                   // prefilter :239-244
-    if (pos >= excl_lo && pos < excl_hi) return 0;                // small-event rule :253-256
-    const int gk = gt[0], gd = gt[1], gm = gt[2];
-    const bool parents = high_quality(P, gd, gq[1], rd[1], ad[1]) && high_quality(P, gm, gq[2], rd[2], ad[2]);
+    const bool base = (meta & 1u) && !(pos >= excl_lo && pos < excl_hi);  // prefilter :239-244, small event :253-256
+    const int gk = (meta >> 8) & 0xff, gd = (meta >> 16) & 0xff, gm = meta >> 24;
+    const bool read_mode = mode == UNFZ_MODE_READ;
+    bool hq[3], need[3];
+    int32_t tot[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const int g = m == 0 ? gk : (m == 1 ? gd : gm);
+        const GtThr t = thr[g & 3];
+        const bool valid = (g <= 3) & (t.flags & 1);
+        tot[m] = (int32_t)((uint32_t)rd[m] + (uint32_t)ad[m]);             // numpy int32 add wraps
+        const bool pre = valid & !(gq[m] < min_gq_f) & (tot[m] >= min_depth);
+        const bool fv = (ad[m] >= 0) & (ad[m] <= tot[m]) & (tot[m] > 0) & (tot[m] < (1 << 24));
+        const float q = __fdividef((float)ad[m], (float)tot[m]);           // <= 2 ulp; the margin is 1e-6
+        const bool is0 = ad[m] == 0, is1 = ad[m] == tot[m];               // exactly 0.0 / 1.0 (very common)
+        const bool in = is0 ? ((t.flags & 2) != 0) : (is1 ? ((t.flags & 4) != 0) : ((q >= t.f.x) & (q <= t.f.y)));
+        const bool out = (q < t.f.z) | (q > t.f.w);
+        hq[m] = pre & fv & in;
+        need[m] = pre & !(fv & (is0 | is1 | in | out));
+    }
+    if (base && (need[0] | need[1] | need[2])) {                           // rare
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+            if (need[m]) {
+                const int g = m == 0 ? gk : (m == 1 ? gd : gm);
+                hq[m] = ab_exact(thr[g & 3].lo, thr[g & 3].hi, ad[m], tot[m]);
+            }
+    }
+    const bool parents = hq[1] & hq[2];
+    int ka = 0;                                                            // get_kid_allele
+    if (!read_mode) {
+        if (mode == UNFZ_MODE_CNV_DEL && tot[0] > 4) ka = gk == 3 ? 1 : (gk == 0 ? 2 : 0);
+        else if (mode == UNFZ_MODE_CNV_DUP && base && parents && rd[0] > 2 && ad[0] > 2 && tot[0] > min_depth && gk == 1)
+            ka = kid_allele_dup(rd[0], ad[0], rd[1], ad[1], rd[2], ad[2]);
+    }
+    const bool het = base & (gk == 1) & parents;
+    // parental pattern :307-320 and hemizygous-kid uniqueness :322-337 depend on the three genotype
+    // codes only: 64-entry table (bit0 informative pattern, bit1 alt_parent is dad, bit2 kid shares the
+    // homozygous parent's allele -> reject)
+    const uint32_t lut = gt_lut[((gk & 3) << 4) | ((gd & 3) << 2) | (gm & 3)];
+    const bool alt_is_dad = (lut & 2u) != 0;
+    const bool kid_ok = read_mode ? ((gk == 1) & hq[0]) : (ka != 0);
+    const bool cand = base & parents & kid_ok & ((lut & 1u) != 0) & !(lut & 4u);
     uint8_t code = 0;
-    if (gk == 1 && parents) code |= UNFZ_CLS_HET;
-    int ka = 0;
-    if (mode != UNFZ_MODE_READ) {
-        ka = kid_allele(P, mode, gk, rd, ad);
-        if (!ka) return code;
-    } else if (gk != 1 || !high_quality(P, gk, gq[0], rd[0], ad[0])) {
-        return code;
-    }
-    if (!parents) return code;
-    bool alt_is_dad;
-    if ((gd == 1 || gd == 3) && gm == 0) alt_is_dad = true;
-    else if ((gm == 1 || gm == 3) && gd == 0) alt_is_dad = false;
-    else if (gm == 1 && gd == 3) alt_is_dad = true;
-    else if (gd == 1 && gm == 3) alt_is_dad = false;
-    else return code;
-    if (gk == 3 || gk == 0) {                                     // hemizygous-kid uniqueness :322-337
-        const bool any_het = (gd == 1) || (gm == 1);
-        const bool any_hom = (gd == 3) || (gm == 3) || (gd == 0) || (gm == 0);
-        if (any_het && any_hom) {
-            if (((gd == 3 || gd == 0) && gk == gd) || ((gm == 3 || gm == 0) && gk == gm)) return code;
-        }
-    }
-    code |= UNFZ_CLS_CAND;
-    if (alt_is_dad) code |= UNFZ_CLS_ALT_IS_DAD;
-    if (ka == 2) code |= UNFZ_CLS_KID_ALT;
+    if (het) code |= UNFZ_CLS_HET;
+    if (cand) code |= UNFZ_CLS_CAND;
+    if (cand & alt_is_dad) code |= UNFZ_CLS_ALT_IS_DAD;
+    if (cand & (ka == 2)) code |= UNFZ_CLS_KID_ALT;
     return code;
 }
 
 constexpr int CLS_THREADS = 256;
 constexpr int CLS_PER_THREAD = 4;
 constexpr int CLS_TILE = CLS_THREADS * CLS_PER_THREAD;
-constexpr int CLS_SMEM_SEGS = 1024;
+constexpr int CLS_SMEM_SEGS = 512;
 
+// Flat stream over pairs.  Every CTA owns a contiguous range of 1024-pair tiles, so the first
+// segment of a tile is carried over from the previous tile (one global binary search per CTA);
+// the descriptors of the segments a tile touches are staged in shared memory and a pair -> segment
+// map is built with one block scan per tile (segment starts are counted per pair slot, the
+// inclusive prefix is the index of the last segment starting at or before the pair).
 __global__ void __launch_bounds__(CLS_THREADS)
 classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const int32_t* __restrict__ seg_row_lo,
                 const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs, ClsParams P,
                 uint8_t* __restrict__ out) {
-    __shared__ int64_t s_off[CLS_SMEM_SEGS + 1];
-    __shared__ int32_t s_seg0, s_nseg;
+    __shared__ int32_t s_off[CLS_SMEM_SEGS + 1];     // pair offset of the segment relative to the tile
+    __shared__ int32_t s_row[CLS_SMEM_SEGS], s_mult[CLS_SMEM_SEGS], s_exlo[CLS_SMEM_SEGS], s_exhi[CLS_SMEM_SEGS];
+    __shared__ uint8_t s_mode[CLS_SMEM_SEGS];
+    __shared__ int32_t s_map[CLS_TILE];
+    __shared__ int32_t s_warp[CLS_THREADS / 32];
+    __shared__ GtThr s_thr[4];
+    __shared__ uint8_t s_lut[64];
+    __shared__ int32_t s_seg0;
     const int64_t n_tiles = (n_pairs + CLS_TILE - 1) / CLS_TILE;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t tpc = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * tpc, t1 = min(t0 + tpc, n_tiles);
+    if (t0 >= t1) return;
+    if (threadIdx.x == 0) { s_thr[0] = P.thr[0]; s_thr[1] = P.thr[1]; s_thr[2] = P.thr[2]; s_thr[3] = P.thr[3]; }
+    if (threadIdx.x < 64) {
+        const int gk = threadIdx.x >> 4, gd = (threadIdx.x >> 2) & 3, gm = threadIdx.x & 3;
+        const bool p1 = ((gd == 1) | (gd == 3)) & (gm == 0);
+        const bool p2 = ((gm == 1) | (gm == 3)) & (gd == 0);
+        const bool p3 = (gm == 1) & (gd == 3);
+        const bool p4 = (gd == 1) & (gm == 3);
+        const bool kid_hom = (gk == 3) | (gk == 0);
+        const bool any_het = (gd == 1) | (gm == 1);
+        const bool any_hom = (gd == 3) | (gm == 3) | (gd == 0) | (gm == 0);
+        const bool shared = (((gd == 3) | (gd == 0)) & (gk == gd)) | (((gm == 3) | (gm == 0)) & (gk == gm));
+        s_lut[threadIdx.x] = (uint8_t)(((p1 | p2 | p3 | p4) ? 1 : 0) | ((p1 | p3) ? 2 : 0) | ((kid_hom & any_het & any_hom & shared) ? 4 : 0));
+    }
+    if (threadIdx.x == 0)
+        s_seg0 = (int32_t)(upper_bound_dev(seg_pair_off, 0, (int64_t)n_segs + 1, t0 * CLS_TILE) - 1);
+    __syncthreads();
+    int seg0 = s_seg0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(sites.rec);
+    const int2* __restrict__ dep2 = reinterpret_cast<const int2*>(sites.dep);
+    for (int64_t tile = t0; tile < t1; ++tile) {
         const int64_t p0 = tile * CLS_TILE;
-        const int64_t p1 = min(p0 + (int64_t)CLS_TILE, n_pairs);
-        if (threadIdx.x == 0) {
-            // segment holding pair p0: last s with off[s] <= p0; segment holding pair p1-1
-            const int64_t a = upper_bound_dev(seg_pair_off, 0, (int64_t)n_segs + 1, p0) - 1;
-            const int64_t b = upper_bound_dev(seg_pair_off, a, (int64_t)n_segs + 1, p1 - 1) - 1;
-            s_seg0 = (int32_t)a;
-            s_nseg = (int32_t)(b - a + 1);
+        const int npair = (int)min((int64_t)CLS_TILE, n_pairs - p0);
+#pragma unroll
+        for (int j = 0; j < CLS_PER_THREAD; ++j) s_map[j * CLS_THREADS + threadIdx.x] = 0;
+        // stage the descriptors of the segments this tile touches, starting at the carried one, in
+        // rounds of 128 (typically one round)
+        int staged_n = 0;
+        for (int round = 0; round < CLS_SMEM_SEGS / 128; ++round) {
+            const int i = round * 128 + threadIdx.x;
+            if (threadIdx.x < 128) {
+                const int sidx = seg0 + i;
+                int64_t rel = (int64_t)1 << 30;
+                if (sidx <= n_segs) rel = min(max(seg_pair_off[sidx] - p0, -((int64_t)1 << 30)), (int64_t)1 << 30);
+                s_off[i] = (int32_t)rel;
+                if (sidx < n_segs && rel < npair) {
+                    const UnfzSegIn sg = segs[sidx];
+                    s_row[i] = seg_row_lo[sidx];
+                    s_mult[i] = sg.mult;
+                    s_exlo[i] = sg.excl_lo;
+                    s_exhi[i] = sg.excl_hi;
+                    s_mode[i] = (uint8_t)sg.mode;
+                }
+            }
+            if (threadIdx.x == 0 && round == CLS_SMEM_SEGS / 128 - 1) s_off[CLS_SMEM_SEGS] = 1 << 30;
+            __syncthreads();
+            staged_n = round * 128 + 128;
+            if (s_off[staged_n - 1] >= npair) break;              // the next segment starts beyond the tile
         }
-        __syncthreads();
-        const int seg0 = s_seg0, nseg = s_nseg;
-        const bool staged = nseg <= CLS_SMEM_SEGS;
-        if (staged)
-            for (int i = threadIdx.x; i <= nseg; i += CLS_THREADS) s_off[i] = seg_pair_off[seg0 + i];
-        __syncthreads();
+        const bool staged = !(s_off[staged_n - 1] < npair);       // false: more than 512 segments in this tile
+        int last_started = 0;                                     // largest staged i with s_off[i] < npair
+        if (staged) {
+            // count segment starts per pair slot (segments i >= 1 that start inside the tile)
+            for (int i = 1 + threadIdx.x; i < staged_n; i += CLS_THREADS) {
+                const int q = s_off[i];
+                if (q < npair) atomicAdd(&s_map[max(q, 0)], 1);
+            }
+            __syncthreads();
+            // inclusive scan over the 1024 slots: thread t owns slots 4t..4t+3
+            int c[CLS_PER_THREAD];
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < CLS_PER_THREAD; ++j) { sum += s_map[threadIdx.x * CLS_PER_THREAD + j]; c[j] = sum; }
+            int x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_warp[warp] = x;
+            __syncthreads();
+            int basew = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < CLS_THREADS / 32; ++w) { if (w < warp) basew += s_warp[w]; total += s_warp[w]; }
+            const int excl = basew + x - sum;
+#pragma unroll
+            for (int j = 0; j < CLS_PER_THREAD; ++j) s_map[threadIdx.x * CLS_PER_THREAD + j] = excl + c[j];
+            last_started = total;
+            __syncthreads();
+        }
 #pragma unroll
         for (int j = 0; j < CLS_PER_THREAD; ++j) {
-            const int64_t p = p0 + (int64_t)j * CLS_THREADS + threadIdx.x;
-            if (p >= p1) continue;
-            int s;
+            const int q = j * CLS_THREADS + threadIdx.x;          // pair index inside the tile
+            if (q >= npair) continue;
+            int32_t row_lo, mult, exlo, exhi, mode, within;
             if (staged) {
-                int lo = 0, hi = nseg;                   // last i with s_off[i] <= p
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_off[mid] <= p) lo = mid; else hi = mid; }
-                s = seg0 + lo;
+                const int lo = s_map[q];
+                row_lo = s_row[lo]; mult = s_mult[lo]; exlo = s_exlo[lo]; exhi = s_exhi[lo]; mode = s_mode[lo];
+                within = q - s_off[lo];
             } else {
-                s = (int)(upper_bound_dev(seg_pair_off, (int64_t)seg0, (int64_t)n_segs + 1, p) - 1);
+                const int sidx = (int)(upper_bound_dev(seg_pair_off, (int64_t)seg0, (int64_t)n_segs + 1, p0 + q) - 1);
+                const UnfzSegIn sg = segs[sidx];
+                row_lo = seg_row_lo[sidx]; mult = sg.mult; exlo = sg.excl_lo; exhi = sg.excl_hi; mode = sg.mode;
+                within = (int32_t)(p0 + q - seg_pair_off[sidx]);
             }
-            const UnfzSegIn sg = segs[s];
-            const int64_t within = p - (staged ? s_off[s - seg0] : seg_pair_off[s]);
-            const int64_t row = (int64_t)seg_row_lo[s] + (sg.mult == 1 ? within : within / sg.mult);
-            uint8_t gt[3]; float gq[3]; int32_t rd[3], ad[3];
-            const int32_t pos = __ldg(sites.pos + row);
-            const uint8_t flag = __ldg(sites.flag + row);
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                gt[m] = __ldg(sites.gt[m] + row);
-                gq[m] = __ldg(sites.gq[m] + row);
-                rd[m] = __ldg(sites.rd[m] + row);
-                ad[m] = __ldg(sites.ad[m] + row);
-            }
-            out[p] = classify_pair(P, sg.mode, pos, sg.excl_lo, sg.excl_hi, flag, gt, gq, rd, ad);
+            const int64_t row = (int64_t)row_lo + (mult == 1 ? within : within / mult);
+            const uint32_t meta = __ldg(sites.meta + row);
+            const float4 rc = __ldg(rec4 + row);
+            const int2 d0 = __ldg(dep2 + row * 3), d1 = __ldg(dep2 + row * 3 + 1), d2 = __ldg(dep2 + row * 3 + 2);
+            const float gq[3] = {rc.y, rc.z, rc.w};
+            const int32_t rd[3] = {d0.x, d1.x, d2.x}, ad[3] = {d0.y, d1.y, d2.y};
+            out[p0 + q] = classify_pair(s_thr, s_lut, P.min_gq_f, P.min_depth, mode, __float_as_int(rc.x), exlo, exhi, meta, gq, rd, ad);
         }
         __syncthreads();
+        if (staged) seg0 += last_started;                         // the last segment may continue into the next tile
+        else seg0 = (int)(upper_bound_dev(seg_pair_off, (int64_t)seg0, (int64_t)n_segs + 1, p0 + npair - 1) - 1);
     }
 }
 
@@ -240,10 +336,22 @@ extern "C" int unfz_classify_sites(UnfzCtx* ctx, const UnfzSiteCols* sites, cons
                                    int64_t n_pairs, const UnfzParams* hp, uint8_t* out_class, void* stream) {
     if (n_pairs <= 0) return 0;
     ClsParams P;
-    P.ab[0][0] = hp->ab_homref[0]; P.ab[0][1] = hp->ab_homref[1];
-    P.ab[1][0] = hp->ab_het[0];    P.ab[1][1] = hp->ab_het[1];
-    P.ab[2][0] = hp->ab_homalt[0]; P.ab[2][1] = hp->ab_homalt[1];
-    P.min_gq = hp->min_gt_qual;
+    const double ab[3][2] = {{hp->ab_homref[0], hp->ab_homref[1]}, {hp->ab_het[0], hp->ab_het[1]}, {hp->ab_homalt[0], hp->ab_homalt[1]}};
+    for (int g = 0; g < 4; ++g) {
+        const int r = g == 0 ? 0 : (g == 3 ? 2 : 1);
+        GtThr t;
+        t.f.x = nextafterf((float)(ab[r][0] + 1e-6), INFINITY);
+        t.f.y = nextafterf((float)(ab[r][1] - 1e-6), -INFINITY);
+        t.f.z = nextafterf((float)(ab[r][0] - 1e-6), -INFINITY);
+        t.f.w = nextafterf((float)(ab[r][1] + 1e-6), INFINITY);
+        t.lo = ab[r][0];
+        t.hi = ab[r][1];
+        t.flags = g == 2 ? 0 : (1 | ((ab[r][0] <= 0.0 && 0.0 <= ab[r][1]) ? 2 : 0) | ((ab[r][0] <= 1.0 && 1.0 <= ab[r][1]) ? 4 : 0));
+        t._pad = 0;
+        P.thr[g] = t;
+    }
+    P.min_gq_f = (float)hp->min_gt_qual;
+    if ((double)P.min_gq_f < hp->min_gt_qual) P.min_gq_f = nextafterf(P.min_gq_f, INFINITY);
     P.min_depth = hp->min_depth;
     const int64_t n_tiles = (n_pairs + CLS_TILE - 1) / CLS_TILE;
     // persistent grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM

@@ -42,29 +42,40 @@ def make_params(ab_homref=(0.0, 0.2), ab_homalt=(0.8, 1.0), ab_het=(0.2, 0.8), m
     return p
 
 
+def pack_site_rows(pos, flag, gt, gq, rd, ad):
+    """Device-side repack of the SoA genotype columns into the classifier's row layout
+    (meta u32, rec 4xf32, dep 6xi32 -- see include/unfazed_sm100.h).  All torch ops on the device."""
+    g = gt.to(torch.int32)
+    meta = (flag.to(torch.int32) | (g[0] << 8) | (g[1] << 16) | (g[2] << 24)).contiguous()
+    rec = torch.stack([pos.view(torch.float32), gq[0], gq[1], gq[2]], dim=1).contiguous()
+    dep = torch.stack([rd[0], ad[0], rd[1], ad[1], rd[2], ad[2]], dim=1).contiguous()
+    return meta, rec, dep
+
+
 class DeviceSites:
     def __init__(self, table: SiteTable, device: torch.device, pin: bool = False):
         self.table = table
         self.n_rows = table.n_rows
         up = lambda a: _to_device(np.ascontiguousarray(a), device, pin)
         self.blk_off = up(table.blk_off.astype(np.int64))
-        self.pos, self.flag, self.ref, self.alt = up(table.pos), up(table.flag), up(table.ref), up(table.alt)
-        self.gt, self.gq, self.rd, self.ad = up(table.gt), up(table.gq), up(table.rd), up(table.ad)
-        c = L.SiteCols()
-        c.n_rows, c.n_blocks = table.n_rows, table.n_blocks
-        c.blk_off, c.pos, c.flag = self.blk_off.data_ptr(), self.pos.data_ptr(), self.flag.data_ptr()
-        c.ref, c.alt = self.ref.data_ptr(), self.alt.data_ptr()
-        V = max(table.n_rows, 0)
-        for m in range(3):
-            c.gt[m] = self.gt.data_ptr() + m * V
-            c.gq[m] = self.gq.data_ptr() + m * V * 4
-            c.rd[m] = self.rd.data_ptr() + m * V * 4
-            c.ad[m] = self.ad.data_ptr() + m * V * 4
-        self.cols = c
+        self.pos, self.ref, self.alt = up(table.pos), up(table.ref), up(table.alt)
+        flag, gt, gq, rd, ad = up(table.flag), up(table.gt), up(table.gq), up(table.rd), up(table.ad)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.pos, self.ref, self.alt, flag, gt, gq, rd, ad))
+        self.meta, self.rec, self.dep = pack_site_rows(self.pos, flag, gt, gq, rd, ad)
+        self.cols = make_site_cols(table.n_rows, table.n_blocks, self.blk_off, self.pos, self.ref, self.alt,
+                                   self.meta, self.rec, self.dep)
 
     @property
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.pos, self.flag, self.ref, self.alt, self.gt, self.gq, self.rd, self.ad))
+        return self.h2d_bytes
+
+
+def make_site_cols(n_rows, n_blocks, blk_off, pos, ref, alt, meta, rec, dep) -> L.SiteCols:
+    c = L.SiteCols()
+    c.n_rows, c.n_blocks = n_rows, n_blocks
+    c.blk_off, c.pos, c.ref, c.alt = blk_off.data_ptr(), pos.data_ptr(), ref.data_ptr(), alt.data_ptr()
+    c.meta, c.rec, c.dep = meta.data_ptr(), rec.data_ptr(), dep.data_ptr()
+    return c
 
 
 class DeviceReads:
@@ -317,10 +328,8 @@ class Engine:
                                             rsum.data_ptr(), blk_maxspan.data_ptr(), het_list.data_ptr(), n_het.data_ptr(),
                                             cand_list.data_ptr(), n_cand.data_ptr(), win.data_ptr(),
                                             need.data_ptr(), s), "chain_size")
-            for k in range(6):
-                self._check(lib.unfz_exclusive_scan_i64(ctx, need.data_ptr() + 8 * k * n_dnms, off.data_ptr() + 8 * k * (n_dnms + 1),
-                                                        n_dnms, work.data_ptr(), s), "scan(need)")
-            launches += 1 + 6 * 3
+            self._check(lib.unfz_exclusive_scan_rows_i64(ctx, need.data_ptr(), off.data_ptr(), 6, n_dnms, s), "scan(need)")
+            launches += 2
             h_off = off.cpu().numpy().reshape(6, n_dnms + 1)
             totals = np.ascontiguousarray(h_off[:, n_dnms]).astype(np.int64)
             mark("chain_size")

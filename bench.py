@@ -202,7 +202,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from unfazed_b200.engine import Engine, make_params
     from unfazed_b200.phaser import BatchPhaser
-    from unfazed_b200.plan import plan_find
+    from unfazed_b200.plan import plan_find_fast as plan_find
 
     t_gen = time.perf_counter()
     ds = make_ds(args, rank)
@@ -262,9 +262,10 @@ def run_b200(args):
     host_read_t = _pin_table(ds.reads)
 
     def step_e2e():
-        pl = plan_find(ds.dnms, ds.pedigrees, bp.sidx, ds.reads, **plan_kw)
+        # the H2D copies are asynchronous (pinned source): the host plans the windows while they fly
         dsites = eng.upload_sites(host_site_t, pin=False)
         dreads = eng.upload_reads(host_read_t, pin=False)
+        pl = plan_find(ds.dnms, ds.pedigrees, bp.sidx, ds.reads, **plan_kw)
         return eng.run(dsites, dreads, pl, params, blk_cul=cul, download=True, keep_device=False)
 
     for _ in range(2):

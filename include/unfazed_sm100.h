@@ -228,6 +228,7 @@ int unfz_compact_sites(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const Unfz
 int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                    const int32_t* mark_prefix, const UnfzParams* h_params,
                    int32_t max_l_seq /* longest read, 0 = unknown: picks the staging strategy */, UnfzReadSum* out,
+                   int32_t* row_lb /* [n_reads] first site row with pos >= start (input of unfz_read_site_alleles) */,
                    int32_t* blk_maxspan /* [n_blocks], zeroed by the caller: max(end-start) */,
                    void* stream);
 
@@ -237,7 +238,7 @@ int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* site
  * bits16-23 raw quality byte, bits24-25 base code, bit26: index+1 < l_seq. */
 int unfz_read_site_alleles(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                            const uint8_t* row_mark, const int32_t* mark_prefix,
-                           const UnfzReadSum* rsum, uint32_t* hits, void* stream);
+                           const UnfzReadSum* rsum, const int32_t* row_lb, uint32_t* hits, void* stream);
 
 /* Sizing pass of unfz_chain_tally: per DNM read window and scratch needs (need[6][n_dnms] int64:
  * window slots, het incidences, seed entries, seed incidences, het sites, candidate sites). */

@@ -666,9 +666,9 @@ chain_kernel(ChainArgs A) {
         __syncthreads();
 
         // ------------------------------------------------------------ phase 4: level-synchronous BFS
+        for (int x = tid; x < W; x += CH_THREADS) minkey[x] = KEY_NONE;
         for (int level = 0;; ++level) {
             for (int i = tid; i < nh; i += CH_THREADS) { bestkey[i] = KEY_NONE; site_cnt[i] = 0; }
-            for (int x = tid; x < W; x += CH_THREADS) minkey[x] = KEY_NONE;
             __syncthreads();
             // a. best finder per site; the finder's haplotype and allele ride in the low key bits
             for (int k = tid; k < n_inc + n_sinc; k += CH_THREADS) {
@@ -739,7 +739,8 @@ chain_kernel(ChainArgs A) {
                 const int x = inc_x[k];
                 if (label[x] != 0) continue;
                 const int t = tmp[x];
-                if (!(t & 1) || (t >> 8) != inc_site[k] || minkey[x] != bestkey[inc_site[k]] || !(inc_al[k] >> 2)) continue;
+                if (!(t & 1)) { minkey[x] = KEY_NONE; continue; }        // still unlabelled: re-arm for the next level
+                if ((t >> 8) != inc_site[k] || minkey[x] != bestkey[inc_site[k]] || !(inc_al[k] >> 2)) continue;
                 const int i = t >> 8;
                 const uint8_t nhap = (t >> 4) & 3;
                 const uint32_t seq = (uint32_t)site_base[i] + ord[x];

@@ -81,7 +81,7 @@ __device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, in
 
 __global__ void __launch_bounds__(RS_THREADS)
 read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
-                 UnfzReadSum* __restrict__ out, int32_t* __restrict__ blk_maxspan) {
+                 UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb, int32_t* __restrict__ blk_maxspan) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* qbuf = smem;                                             // RS_QBUF + 16
     int32_t* spos = reinterpret_cast<int32_t*>(smem + RS_QBUF + 16);  // RS_SPOS
@@ -175,8 +175,8 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
 
         // ---- marked-site overlap count -------------------------------------------------------
         int32_t fmark = 0, cnt = 0;
+        int64_t lbs = 0, lbe = 0;
         if (live && sb >= 0) {
-            int64_t lbs, lbe;
             if (rb == s_rb0) {
                 int lo = 0, hi = RS_SPOS;
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h.start) lo = mid + 1; else hi = mid; }
@@ -227,6 +227,7 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
             o.cnt = (uint16_t)cnt;
             o.hoff = 0;
             *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
+            row_lb[r] = (int32_t)lbs;
         }
         __syncthreads();
         if (threadIdx.x == 0 && s_maxspan > 0) {
@@ -251,7 +252,8 @@ constexpr int RS_STAGE = 36 * 1024;
 
 __global__ void __launch_bounds__(RS_THREADS)
 read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
-                      int tile_reads, UnfzReadSum* __restrict__ out, int32_t* __restrict__ blk_maxspan) {
+                      int tile_reads, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
+                      int32_t* __restrict__ blk_maxspan) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage[2] = {smem, smem + RS_STAGE};
     int32_t* spos = reinterpret_cast<int32_t*>(smem + 2 * RS_STAGE);
@@ -371,8 +373,8 @@ read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
         __syncthreads();   // spos visible
 
         int32_t fmark = 0, cnt = 0;
+        int64_t lbs = 0, lbe = 0;
         if (live && sb >= 0) {
-            int64_t lbs, lbe;
             if (rb == rb0) {
                 int lo = 0, hi = RS_SPOS;
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h.start) lo = mid + 1; else hi = mid; }
@@ -409,6 +411,7 @@ read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
             UnfzReadSum o;
             o.end = end; o.fmark = fmark; o.flags = (uint16_t)flags; o.cnt = (uint16_t)cnt; o.hoff = 0;
             *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
+            row_lb[r] = (int32_t)lbs;
         }
         // ---- hand-over to the next tile ---------------------------------------------------------
         publish_span(tile + 2, h2, live2);                   // slot (tile+2)%3 is not in use
@@ -476,7 +479,7 @@ __device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n
 __global__ void __launch_bounds__(256)
 read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
                          const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
-                         uint32_t* __restrict__ hits) {
+                         const int32_t* __restrict__ row_lb, uint32_t* __restrict__ hits) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= reads.n_reads) return;
     const UnfzReadSum s = load_rsum(rsum + r);
@@ -486,7 +489,7 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
     const int sb = reads.blk_sblk[rb];
     if (sb < 0) return;
     const int64_t b = sites.blk_off[sb + 1];
-    int64_t row = lower_bound_dev(sites.pos, sites.blk_off[sb], b, h.start);
+    int64_t row = __ldg(row_lb + r);                       // first site row with pos >= start (from read_scan)
     const uint32_t* cg = reads.cigar + h.cigar_off;
     const int64_t q0 = read_qoff(h);
     int written = 0;
@@ -512,7 +515,7 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
 
 extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                               const int32_t* mark_prefix, const UnfzParams* hp, int32_t max_l_seq, UnfzReadSum* out,
-                              int32_t* blk_maxspan, void* stream) {
+                              int32_t* row_lb, int32_t* blk_maxspan, void* stream) {
     if (reads->n_reads <= 0) return 0;
     ScanParams P;
     P.min_mapq = hp->min_map_qual;
@@ -531,7 +534,7 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
         const int64_t tiles = (reads->n_reads + tile_reads - 1) / tile_reads;
         int64_t g = (int64_t)ctx->sm_count * 3;     // 3 CTAs x 72 KB of staging per SM
         if (g > tiles) g = tiles;
-        read_scan_pipe_kernel<<<(unsigned)g, RS_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, tile_reads, out, blk_maxspan);
+        read_scan_pipe_kernel<<<(unsigned)g, RS_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, tile_reads, out, row_lb, blk_maxspan);
         UNFZ_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -544,17 +547,17 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     const int64_t n_tiles = (reads->n_reads + RS_THREADS - 1) / RS_THREADS;
     int64_t grid = (int64_t)ctx->sm_count * 4;     // 4 x ~49 KB of staging per SM
     if (grid > n_tiles) grid = n_tiles;
-    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, blk_maxspan);
+    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 extern "C" int unfz_read_site_alleles(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                                       const uint8_t* row_mark, const int32_t* mark_prefix,
-                                      const UnfzReadSum* rsum, uint32_t* hits, void* stream) {
+                                      const UnfzReadSum* rsum, const int32_t* row_lb, uint32_t* hits, void* stream) {
     if (reads->n_reads <= 0) return 0;
     const int64_t blocks = (reads->n_reads + 255) / 256;
-    read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, hits);
+    read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, row_lb, hits);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

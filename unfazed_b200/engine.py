@@ -227,69 +227,110 @@ class Engine:
     def run(self, dsites: DeviceSites, dreads: Optional[DeviceReads], plan: Plan, params: L.Params,
             blk_cul: Optional[np.ndarray] = None, time_stages: bool = False, download: bool = True,
             keep_device: bool = True) -> BatchResult:
+        """One batch through the pipeline.  Two host syncs size the variable outputs (pairs; hits +
+        chain scratch), everything else is asynchronous; all per-DNM results come back in ONE D2H
+        copy.  Device memory comes from three arenas (one torch allocation each)."""
         lib, ctx, dev = self.lib, self.ctx, self.device
         st = torch.cuda.current_stream(dev)
         s = C.c_void_p(st.cuda_stream)
-        n_dnms, n_segs = int(plan.dnm.shape[0]), int(plan.seg.shape[0])
+        n, S = int(plan.dnm.shape[0]), int(plan.seg.shape[0])
+        V = int(dsites.n_rows)
+        N = int(dreads.n_reads) if dreads is not None else 0
         ev: List = []
         launches = 0
 
         def mark(name):
             if time_stages:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(st)
-                ev.append((name, e))
+                e_ = torch.cuda.Event(enable_timing=True)
+                e_.record(st)
+                ev.append((name, e_))
 
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev) if a.size else self._empty(1, torch.uint8)
-        d_dnm, d_seg, d_all = up(plan.dnm), up(plan.seg), up(plan.alleles)
+        class Arena:
+            def __init__(self, zero: bool):
+                self.items, self.size, self.zero, self.buf = [], 0, zero, None
+
+            def add(self, name, nbytes):
+                self.items.append((name, self.size, int(nbytes)))
+                self.size += (int(nbytes) + 255) & ~255
+
+            def alloc(self_):
+                fn = torch.zeros if self_.zero else torch.empty
+                self_.buf = fn((max(self_.size, 256),), dtype=torch.uint8, device=dev)
+                base = self_.buf.data_ptr()
+                self_.ptr = {nm: base + off for nm, off, _ in self_.items}
+                self_.view = {nm: self_.buf[off: off + nb] for nm, off, nb in self_.items}
+
+        # ---- plan upload: one H2D ----------------------------------------------------------------
+        hp = np.concatenate([plan.dnm.view(np.uint8).reshape(-1), plan.seg.view(np.uint8).reshape(-1), plan.alleles,
+                             np.zeros(16, np.uint8)])
+        d_plan = torch.from_numpy(hp).to(dev)
+        p_dnm = d_plan.data_ptr()
+        p_seg = p_dnm + plan.dnm.nbytes
+        p_all = p_seg + plan.seg.nbytes
         sc = C.byref(dsites.cols)
+        has_reads = dreads is not None and N > 0 and bool((plan.dnm["rblk"] >= 0).any())
+
+        # ---- arena 1: everything whose size is known up front -------------------------------------
+        z1, e1 = Arena(True), Arena(False)
+        # int32 result block, downloaded with one copy at the end
+        r_fields = [("n_het", n), ("n_cand", n), ("cnv_dad", n), ("cnv_mom", n), ("tally", 8 * n), ("calls_s", 4 * n),
+                    ("calls_a", 4 * n), ("win", 4 * n), ("seg_row_lo", S)]
+        r_off, acc = {}, 0
+        for nm, cnt in r_fields:
+            r_off[nm] = acc
+            acc += cnt
+        z1.add("result", 4 * acc)
+        z1.add("seg_pair_off", 8 * (S + 1))
+        z1.add("row_mark", V)
+        z1.add("mark_prefix", 4 * (V + 1))
+        e1.add("seg_count", 8 * S)
+        e1.add("scan_work", lib.unfz_scan_work_bytes(max(S, V, N, n) + 1))
+        if has_reads:
+            z1.add("blk_maxspan", 4 * max(dreads.table.n_blocks, 1))
+            z1.add("need", 8 * 6 * n)
+            z1.add("off", 8 * (6 * (n + 1) + 1))
+            e1.add("rsum", 16 * N)
+            e1.add("row_lb", 4 * N)
+        z1.alloc()
+        e1.alloc()
+        R = z1.ptr["result"]
+        rp = {nm: R + 4 * o for nm, o in r_off.items()}
         mark("start")
 
         # ---- K0 + scan ---------------------------------------------------------------------
-        seg_row_lo = self._empty(n_segs, torch.int32)
-        seg_count = self._empty(n_segs, torch.int64)
-        seg_pair_off = self._zeros(n_segs + 1, torch.int64)
-        self._check(lib.unfz_window_search(ctx, sc, d_seg.data_ptr(), n_segs, seg_row_lo.data_ptr(), seg_count.data_ptr(), s), "window_search")
-        work = self._scan_work(max(n_segs, dsites.n_rows, dreads.n_reads if dreads else 0, n_dnms) + 1)
-        self._check(lib.unfz_exclusive_scan_i64(ctx, seg_count.data_ptr(), seg_pair_off.data_ptr(), n_segs, work.data_ptr(), s), "scan(pairs)")
+        self._check(lib.unfz_window_search(ctx, sc, p_seg, S, rp["seg_row_lo"], e1.ptr["seg_count"], s), "window_search")
+        self._check(lib.unfz_exclusive_scan_i64(ctx, e1.ptr["seg_count"], z1.ptr["seg_pair_off"], S, e1.ptr["scan_work"], s), "scan(pairs)")
         launches += 4
         mark("window_search")
-        h_pair_off = seg_pair_off.cpu().numpy()[: n_segs + 1]
-        n_pairs = int(h_pair_off[n_segs]) if n_segs > 0 else 0
+        h_pair_off = z1.view["seg_pair_off"].cpu().numpy().view(np.int64)[: S + 1]      # host sync 1
+        n_pairs = int(h_pair_off[S]) if S > 0 else 0
 
-        # ---- K1 + compaction + marks ---------------------------------------------------------
-        cls = self._empty(n_pairs, torch.uint8)
-        het_list = self._empty(n_pairs, torch.int32)
-        cand_list = self._empty(n_pairs, torch.int32)
-        n_het = self._zeros(n_dnms, torch.int32)
-        n_cand = self._zeros(n_dnms, torch.int32)
-        cnv_dad = self._zeros(n_dnms, torch.int32)
-        cnv_mom = self._zeros(n_dnms, torch.int32)
-        row_mark = self._zeros(dsites.n_rows, torch.uint8)
-        mark_prefix = self._zeros(dsites.n_rows + 1, torch.int32)
+        # ---- arena 2: per-pair outputs ---------------------------------------------------------------
+        z2, e2 = Arena(True), Arena(False)
+        e2.add("cls", n_pairs)
+        e2.add("het_list", 4 * n_pairs)
+        e2.add("cand_list", 4 * n_pairs)
+        z2.add("cand_evid", n_pairs + 8)
+        z2.alloc()
+        e2.alloc()
         mark("alloc1")
-        self._check(lib.unfz_classify_sites(ctx, sc, d_seg.data_ptr(), seg_row_lo.data_ptr(), seg_pair_off.data_ptr(),
-                                            n_segs, n_pairs, C.byref(params), cls.data_ptr(), s), "classify_sites")
+        self._check(lib.unfz_classify_sites(ctx, sc, p_seg, rp["seg_row_lo"], z1.ptr["seg_pair_off"], S, n_pairs,
+                                            C.byref(params), e2.ptr["cls"], s), "classify_sites")
         launches += 1 if n_pairs else 0
         mark("classify_sites")
-        self._check(lib.unfz_compact_sites(ctx, d_dnm.data_ptr(), n_dnms, d_seg.data_ptr(), seg_row_lo.data_ptr(),
-                                           seg_pair_off.data_ptr(), cls.data_ptr(), het_list.data_ptr(), n_het.data_ptr(),
-                                           cand_list.data_ptr(), n_cand.data_ptr(), cnv_dad.data_ptr(), cnv_mom.data_ptr(),
-                                           row_mark.data_ptr(), s), "compact_sites")
-        self._check(lib.unfz_exclusive_scan_u8_i32(ctx, row_mark.data_ptr(), mark_prefix.data_ptr(), dsites.n_rows,
-                                                   work.data_ptr(), s), "scan(marks)")
+        self._check(lib.unfz_compact_sites(ctx, p_dnm, n, p_seg, rp["seg_row_lo"], z1.ptr["seg_pair_off"], e2.ptr["cls"],
+                                           e2.ptr["het_list"], rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], rp["cnv_dad"],
+                                           rp["cnv_mom"], z1.ptr["row_mark"], s), "compact_sites")
+        self._check(lib.unfz_exclusive_scan_u8_i32(ctx, z1.ptr["row_mark"], z1.ptr["mark_prefix"], V, e1.ptr["scan_work"], s), "scan(marks)")
         launches += 4
         mark("compact_sites")
 
         res = BatchResult(plan=plan, n_pairs=n_pairs, n_hits=0, seg_row_lo=None, seg_pair_off=h_pair_off,
                           n_het=None, n_cand=None, cnv_dad=None, cnv_mom=None)
         dv = res._dev
-        dv.update(cls=cls, het_list=het_list, cand_list=cand_list)
-        tally = self._zeros(n_dnms * 8, torch.int32)
-        calls_s = self._zeros(n_dnms * 4, torch.int32)
-        calls_a = self._zeros(n_dnms * 4, torch.int32)
+        dv.update(cls=e2.view["cls"], het_list=e2.view["het_list"].view(torch.int32), cand_list=e2.view["cand_list"].view(torch.int32),
+                  cand_evid=z2.view["cand_evid"], _keep=(z1, e1, z2, e2, d_plan))
 
-        has_reads = dreads is not None and dreads.n_reads > 0 and bool((plan.dnm["rblk"] >= 0).any())
         if has_reads:
             rc_ = C.byref(dreads.cols)
             sb = np.full(max(dreads.table.n_blocks, 1), -1, dtype=np.int32)
@@ -298,81 +339,77 @@ class Engine:
             dreads.blk_sblk.copy_(torch.from_numpy(sb))
             if blk_cul is not None:
                 dreads.blk_cul[: blk_cul.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(blk_cul, dtype=np.float64)))
-            # ---- K2 + scan + K3 ----------------------------------------------------------------
-            rsum = self._empty(dreads.n_reads * 16, torch.uint8)
-            blk_maxspan = self._zeros(dreads.table.n_blocks, torch.int32)
-            total_hits = self._zeros(1, torch.int64)
-            mark("alloc2")
-            self._check(lib.unfz_read_scan(ctx, rc_, sc, mark_prefix.data_ptr(), C.byref(params), dreads.max_l_seq, rsum.data_ptr(),
-                                           blk_maxspan.data_ptr(), s), "read_scan")
+            # ---- K2 + scan(hit counts) + chain sizing; ONE host sync for all the sizes ---------------
+            off_ptr = z1.ptr["off"]
+            total_hits_ptr = off_ptr + 8 * 6 * (n + 1)
+            self._check(lib.unfz_read_scan(ctx, rc_, sc, z1.ptr["mark_prefix"], C.byref(params), dreads.max_l_seq, e1.ptr["rsum"],
+                                           e1.ptr["row_lb"], z1.ptr["blk_maxspan"], s), "read_scan")
             launches += 1
             mark("read_scan")
-            self._check(lib.unfz_exclusive_scan_u16_u32(ctx, rsum.data_ptr() + 10, 16, rsum.data_ptr() + 12, 16,
-                                                        dreads.n_reads, total_hits.data_ptr(), work.data_ptr(), s), "scan(hits)")
+            self._check(lib.unfz_exclusive_scan_u16_u32(ctx, e1.ptr["rsum"] + 10, 16, e1.ptr["rsum"] + 12, 16, N, total_hits_ptr,
+                                                        e1.ptr["scan_work"], s), "scan(hits)")
             launches += 3
-            n_hits = int(total_hits.item())
+            mark("scan_hits")
+            self._check(lib.unfz_chain_size(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
+                                            z1.ptr["blk_maxspan"], e2.ptr["het_list"], rp["n_het"], e2.ptr["cand_list"],
+                                            rp["n_cand"], rp["win"], z1.ptr["need"], s), "chain_size")
+            self._check(lib.unfz_exclusive_scan_rows_i64(ctx, z1.ptr["need"], off_ptr, 6, n, s), "scan(need)")
+            launches += 2
+            h_all = z1.view["off"].cpu().numpy().view(np.int64)                          # host sync 2
+            h_off = h_all[: 6 * (n + 1)].reshape(6, n + 1)
+            n_hits = int(h_all[6 * (n + 1)])
+            totals = np.ascontiguousarray(h_off[:, n]).astype(np.int64)
+            mark("chain_size")
             if n_hits >= 2**32:
                 raise RuntimeError("more than 2^32 read x site hits in one batch")
-            hits = self._empty(n_hits, torch.int32)
-            mark("scan_hits")
-            self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, row_mark.data_ptr(), mark_prefix.data_ptr(),
-                                                   rsum.data_ptr(), hits.data_ptr(), s), "read_site_alleles")
+            res.n_hits = n_hits
+            # ---- arena 3: hits + chain scratch + labels -------------------------------------------------
+            z3, e3 = Arena(True), Arena(False)
+            nbytes = lib.unfz_chain_scratch_bytes(*(int(x) for x in totals), n)
+            e3.add("hits", 4 * max(n_hits, 1))
+            e3.add("scratch", nbytes)
+            z3.add("slot_label", int(totals[0]) + 4)
+            z3.add("slot_evid", int(totals[0]) + 4)
+            z3.alloc()
+            e3.alloc()
+            mark("alloc3")
+            self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, z1.ptr["row_mark"], z1.ptr["mark_prefix"], e1.ptr["rsum"],
+                                                   e1.ptr["row_lb"], e3.ptr["hits"], s), "read_site_alleles")
             launches += 1
             mark("read_site_alleles")
-            res.n_hits = n_hits
-            # ---- chain sizing + scans ------------------------------------------------------------
-            win = self._zeros(4 * n_dnms, torch.int32)
-            need = self._zeros(6 * n_dnms, torch.int64)
-            off = self._zeros(6 * (n_dnms + 1), torch.int64)
-            self._check(lib.unfz_chain_size(ctx, d_dnm.data_ptr(), n_dnms, d_seg.data_ptr(), seg_pair_off.data_ptr(), sc, rc_,
-                                            rsum.data_ptr(), blk_maxspan.data_ptr(), het_list.data_ptr(), n_het.data_ptr(),
-                                            cand_list.data_ptr(), n_cand.data_ptr(), win.data_ptr(),
-                                            need.data_ptr(), s), "chain_size")
-            self._check(lib.unfz_exclusive_scan_rows_i64(ctx, need.data_ptr(), off.data_ptr(), 6, n_dnms, s), "scan(need)")
-            launches += 2
-            h_off = off.cpu().numpy().reshape(6, n_dnms + 1)
-            totals = np.ascontiguousarray(h_off[:, n_dnms]).astype(np.int64)
-            mark("chain_size")
-            nbytes = lib.unfz_chain_scratch_bytes(*(int(x) for x in totals), n_dnms)
-            scratch = self._empty(nbytes, torch.uint8)
-            slot_label = self._zeros(int(totals[0]) + 4, torch.uint8)
-            slot_evid = self._zeros(int(totals[0]) + 4, torch.uint8)
-            cand_evid = self._zeros(n_pairs + 8, torch.uint8)
-            mark("alloc3")
-            self._check(lib.unfz_chain_tally(ctx, d_dnm.data_ptr(), n_dnms, d_seg.data_ptr(), seg_pair_off.data_ptr(), sc, rc_,
-                                             rsum.data_ptr(), blk_maxspan.data_ptr(), hits.data_ptr(), mark_prefix.data_ptr(),
-                                             het_list.data_ptr(), n_het.data_ptr(), cand_list.data_ptr(), n_cand.data_ptr(),
-                                             d_all.data_ptr(), win.data_ptr(), off.data_ptr(),
-                                             totals.ctypes.data, C.byref(params), scratch.data_ptr(), nbytes,
-                                             slot_label.data_ptr(), slot_evid.data_ptr(), cand_evid.data_ptr(),
-                                             tally.data_ptr(), s), "chain_tally")
+            self._check(lib.unfz_chain_tally(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
+                                             z1.ptr["blk_maxspan"], e3.ptr["hits"], z1.ptr["mark_prefix"], e2.ptr["het_list"],
+                                             rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], p_all, rp["win"], off_ptr,
+                                             totals.ctypes.data, C.byref(params), e3.ptr["scratch"], nbytes,
+                                             z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"], s),
+                        "chain_tally")
             launches += 1
             mark("chain_tally")
-            dv.update(rsum=rsum, hits=hits, slot_label=slot_label, slot_evid=slot_evid, cand_evid=cand_evid,
-                      blk_maxspan=blk_maxspan, row_mark=row_mark, mark_prefix=mark_prefix)
+            dv.update(rsum=e1.view["rsum"], hits=e3.view["hits"].view(torch.int32), slot_label=z3.view["slot_label"],
+                      slot_evid=z3.view["slot_evid"], row_mark=z1.view["row_mark"],
+                      mark_prefix=z1.view["mark_prefix"].view(torch.int32), _keep3=(z3, e3))
             res.slot_off = h_off[0].copy()
-            if download:
-                res.win = win.cpu().numpy()[: 4 * n_dnms].reshape(4, n_dnms)
-        self._check(lib.unfz_summarize(ctx, d_dnm.data_ptr(), n_dnms, tally.data_ptr(), cnv_dad.data_ptr(), cnv_mom.data_ptr(),
-                                       n_cand.data_ptr(), C.byref(params), calls_s.data_ptr(), calls_a.data_ptr(), s), "summarize")
+        self._check(lib.unfz_summarize(ctx, p_dnm, n, rp["tally"], rp["cnv_dad"], rp["cnv_mom"], rp["n_cand"], C.byref(params),
+                                       rp["calls_s"], rp["calls_a"], s), "summarize")
         launches += 1
         mark("summarize")
-        # ---- results (a few bytes per DNM) ---------------------------------------------------
+        # ---- results: ONE device-to-host copy of the int32 result block ----------------------------
         if download:
-            res.seg_row_lo = seg_row_lo.cpu().numpy()[:n_segs]
-            res.n_het, res.n_cand = n_het.cpu().numpy()[:n_dnms], n_cand.cpu().numpy()[:n_dnms]
-            res.cnv_dad, res.cnv_mom = cnv_dad.cpu().numpy()[:n_dnms], cnv_mom.cpu().numpy()[:n_dnms]
-            res.tally = tally.cpu().numpy()[: n_dnms * 8].view(L.TALLY_DTYPE)
-            res.calls_strict = calls_s.cpu().numpy()[: n_dnms * 4].view(L.CALL_DTYPE)
-            res.calls_ambiguous = calls_a.cpu().numpy()[: n_dnms * 4].view(L.CALL_DTYPE)
-        else:
-            dv.update(n_het=n_het, n_cand=n_cand, tally=tally, calls_s=calls_s, calls_a=calls_a)
+            hr = z1.view["result"].cpu().numpy().view(np.int32)
+            g = lambda nm, cnt: hr[r_off[nm]: r_off[nm] + cnt]
+            res.seg_row_lo = g("seg_row_lo", S)
+            res.n_het, res.n_cand = g("n_het", n), g("n_cand", n)
+            res.cnv_dad, res.cnv_mom = g("cnv_dad", n), g("cnv_mom", n)
+            res.tally = g("tally", 8 * n).view(L.TALLY_DTYPE)
+            res.calls_strict = g("calls_s", 4 * n).view(L.CALL_DTYPE)
+            res.calls_ambiguous = g("calls_a", 4 * n).view(L.CALL_DTYPE)
+            res.win = g("win", 4 * n).reshape(4, n)
         mark("download")
         res.launches = launches
         if time_stages:
             torch.cuda.synchronize(dev)
-            for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
-                res.timings_ms[n1] = res.timings_ms.get(n1, 0.0) + e0.elapsed_time(e1)
+            for (n0, e0), (n1, e1_) in zip(ev[:-1], ev[1:]):
+                res.timings_ms[n1] = res.timings_ms.get(n1, 0.0) + e0.elapsed_time(e1_)
         if not keep_device:
             dv.clear()
         return res

@@ -12,7 +12,7 @@ import sys
 from typing import List
 
 from . import datasource
-from .plan import FindManyKeyError, SiteIndex, is_autophaseable, plan_find
+from .plan import FindManyKeyError, SiteIndex, is_autophaseable, plan_find_fast as plan_find
 
 _engine = None
 

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib as L
 from .engine import BatchResult, DeviceReads, DeviceSites, Engine, make_params
 from .plan import (SNV_TYPES, SV_TYPES, Plan, SiteIndex, concat_plans, concordant_upper_lens,
-                   plan_find)
+                   plan_find_fast)
 from .schema import ReadTable, SiteTable
 
 
@@ -76,7 +76,7 @@ class BatchPhaser:
 
         def add(dnms, **kw):
             nonlocal n0, a0
-            p = plan_find(dnms, self.ped, self.sidx, self.reads, first_entry=n0, alleles_base=a0, **common, **kw)
+            p = plan_find_fast(dnms, self.ped, self.sidx, self.reads, first_entry=n0, alleles_base=a0, **common, **kw)
             plans.append(p)
             n0 += len(dnms)
             a0 += int(p.alleles.shape[0])

@@ -155,7 +155,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(cores * 6, 48)
+    per_step = max(cores * 60, 240)      # a few seconds of all-core CPU work per step
     n_gen = min(args.dnms, per_step)
     ds = make_ds(args, 0, n_dnms=n_gen)
     shards = [ds.dnms[i::cores] for i in range(cores)]

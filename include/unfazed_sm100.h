@@ -122,7 +122,7 @@ typedef struct {
     int32_t  fmark;       /* number of marked site rows before the first row with pos >= start */
     uint16_t flags;       /* UNFZ_RS_* */
     uint16_t cnt;         /* marked site rows with start <= pos < end */
-    uint32_t hoff;        /* first hit word of this read (filled by the exclusive scan of cnt) */
+    uint32_t hoff;        /* first hit word of this read, relative to its scan tile (see unfz_read_scan) */
 } UnfzReadSum;
 
 typedef struct {
@@ -196,6 +196,8 @@ int unfz_exclusive_scan_i64(UnfzCtx*, const int64_t* in, int64_t* out, int64_t n
 int unfz_exclusive_scan_u16_u32(UnfzCtx*, const uint16_t* in, int64_t in_stride_bytes, uint32_t* out,
                                 int64_t out_stride_bytes, int64_t n, int64_t* total_out, void* work, void* stream);
 int unfz_exclusive_scan_u8_i32(UnfzCtx*, const uint8_t* in, int32_t* out, int64_t n, void* work, void* stream);
+int unfz_exclusive_scan_u32(UnfzCtx*, const uint32_t* in, uint32_t* out /* n+1 entries */, int64_t n, int64_t* total_out,
+                            void* work, void* stream);
 /* n_rows independent rows in one launch: in[n_rows][n] -> out[n_rows][n+1] (last entry = row total) */
 int unfz_exclusive_scan_rows_i64(UnfzCtx*, const int64_t* in, int64_t* out, int32_t n_rows, int64_t n, void* stream);
 
@@ -223,14 +225,19 @@ int unfz_compact_sites(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const Unfz
                        int32_t* cnv_dad, int32_t* cnv_mom, uint8_t* row_mark, void* stream);
 
 /* Read scan: goodread :28-53, insert-size / None-count / CIGAR-op filters :181-203 :395-408,
- * reference_end, and the number of marked site rows each read overlaps.
- * mark_prefix = exclusive scan of row_mark (n_rows+1 entries). */
+ * reference_end and the number of marked site rows each read overlaps.
+ * mark_prefix = exclusive scan of row_mark (n_rows+1 entries).
+ * Hit slots: reads are processed in tiles of unfz_read_scan_tile_reads(max_l_seq) consecutive
+ * reads; UnfzReadSum.hoff is the read's offset INSIDE its tile and tile_tot[tile] the tile's number
+ * of hit words.  With tile_base = exclusive scan of tile_tot (unfz_exclusive_scan_u32), the hits of
+ * read r live at hits[tile_base[r / tile_reads] + hoff, ... + cnt). */
+int32_t unfz_read_scan_tile_reads(int32_t max_l_seq);
 int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                    const int32_t* mark_prefix, const UnfzParams* h_params,
                    int32_t max_l_seq /* longest read, 0 = unknown: picks the staging strategy */, UnfzReadSum* out,
                    int32_t* row_lb /* [n_reads] first site row with pos >= start (input of unfz_read_site_alleles) */,
                    int32_t* blk_maxspan /* [n_blocks], zeroed by the caller: max(end-start) */,
-                   void* stream);
+                   uint32_t* tile_tot /* [ceil(n_reads / tile_reads)] */, void* stream);
 
 /* Read-by-site allele lookup: get_reference_positions(full_length=True).index(pos) + base +
  * quality for every (read x marked site) overlap (get_allele_at :56-73, phase_by_reads
@@ -238,7 +245,8 @@ int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* site
  * bits16-23 raw quality byte, bits24-25 base code, bit26: index+1 < l_seq. */
 int unfz_read_site_alleles(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                            const uint8_t* row_mark, const int32_t* mark_prefix,
-                           const UnfzReadSum* rsum, const int32_t* row_lb, uint32_t* hits, void* stream);
+                           const UnfzReadSum* rsum, const int32_t* row_lb, const uint32_t* tile_base,
+                           int32_t tile_reads, uint32_t* hits, void* stream);
 
 /* Sizing pass of unfz_chain_tally: per DNM read window and scratch needs (need[6][n_dnms] int64:
  * window slots, het incidences, seed entries, seed incidences, het sites, candidate sites). */
@@ -257,7 +265,8 @@ int unfz_chain_size(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSeg
 int unfz_chain_tally(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
                      const int64_t* seg_pair_off, const UnfzSiteCols* sites,
                      const UnfzReadCols* reads, const UnfzReadSum* rsum, const int32_t* blk_maxspan,
-                     const uint32_t* hits, const int32_t* mark_prefix,
+                     const uint32_t* hits, const uint32_t* hit_tile_base, int32_t hit_tile_reads,
+                     const int32_t* mark_prefix,
                      const int32_t* het_list, const int32_t* n_het, const uint32_t* cand_list,
                      const int32_t* n_cand, const uint8_t* alleles, const int32_t* win,
                      const int64_t* off, const int64_t* h_totals /* off[k][n_dnms], k<6 */,

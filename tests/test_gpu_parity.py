@@ -123,3 +123,45 @@ def test_device_calls_match_summarize_record(engine):
                 bits = {"READBACKED": 1, "ALLELE-BALANCE": 2, "AMBIGUOUS_READBACKED": 4, "AMBIGUOUS_ALLELE-BALANCE": 8,
                         "AMBIGUOUS_BOTH": 16, "SEX-CHROM": 32}
                 assert int(c["evidence_types"]) == sum(bits[t] for t in types), (key, amb)
+
+
+def test_hit_words_match_the_oracle_lookup(engine):
+    """Hit words written by unfz_read_site_alleles == get_reference_positions().index(pos) + base +
+    quality computed by the oracle's decoder, for a sample of (read, marked site) overlaps."""
+    from unfazed_b200.phaser import BatchPhaser
+    ds = make_dataset(SynthConfig(dnms_per_trio=40, seed=51, indel_frac=0.2))
+    bp = BatchPhaser(engine, ds.sites, ds.reads, ds.pedigrees)
+    res, _ = bp.run(ds.dnms, [])
+    rs = res.read_summaries()
+    hits = res._np("hits").view(np.uint32)
+    tile_base = res._np("tile_base").view(np.uint32)
+    tile_reads = res._dev["tile_reads"]
+    mark = res._np("row_mark")
+    pos = ds.sites.pos
+    bam = port.Bam(ds.reads, 0)
+    idx = np.nonzero(rs["cnt"])[0]
+    assert idx.size > 500
+    checked = 0
+    for r in idx[:: max(1, idx.size // 400)]:
+        cig, rp, seq, quals = bam.decoded(int(r))
+        st, en = int(ds.reads.hdr["start"][r]), int(rs["end"][r])
+        rb = int(np.searchsorted(ds.reads.blk_off, r, side="right")) - 1
+        sb = ds.sites.block_of(0, ds.reads.contigs[int(ds.reads.blk_contig[rb])])
+        a, b = int(ds.sites.blk_off[sb]), int(ds.sites.blk_off[sb + 1])
+        rows = [j for j in range(a + int(np.searchsorted(pos[a:b], st)), a + int(np.searchsorted(pos[a:b], en))) if mark[j]]
+        assert len(rows) == rs["cnt"][r]
+        base = int(tile_base[r // tile_reads]) + int(rs["hoff"][r])
+        for k, j in enumerate(rows):
+            w = int(hits[base + k])
+            p = int(pos[j])
+            if p in rp:
+                q = rp.index(p)
+                assert (w & 0xFFFF) == q + 1
+                assert ((w >> 16) & 0x7F) == quals[q]
+                ch = "N" if (w >> 16) & 0x80 and ((w >> 24) & 3) == 0 else ("?" if (w >> 16) & 0x80 else "ACGT"[(w >> 24) & 3])
+                assert ch == seq[q]
+                assert bool(w & (1 << 26)) == (q + 1 < len(seq))
+            else:
+                assert (w & 0xFFFF) == 0
+            checked += 1
+    assert checked > 300

@@ -44,6 +44,7 @@ struct ChainArgs {
     const int32_t* het_list; const int32_t* n_het; const uint32_t* cand_list; const int32_t* n_cand;
     const uint8_t* alleles; const int32_t* win; const int64_t* off;  // win[4][n], off[6][n+1]
     int32_t split_margin;
+    const uint32_t* hit_tile_base; int32_t hit_tile_reads;
     int32_t readlen, min_bq, ext_goal, no_extended;
     uint8_t* slot_label; uint8_t* slot_evid; uint8_t* cand_evid; UnfzTally* tally;
     Scratch S;
@@ -98,7 +99,8 @@ __device__ __forceinline__ uint32_t hit_lookup(const ChainArgs& A, int64_t e, in
     const UnfzReadSum s = load_rsum(A.rsum + e);
     const int k = __ldg(A.mp + row) - s.fmark;
     if (k < 0 || k >= (int)s.cnt) return 0;
-    return __ldg(A.hits + (int64_t)s.hoff + k);
+    const int64_t base = (int64_t)__ldg(A.hit_tile_base + (uint32_t)e / (uint32_t)A.hit_tile_reads) + s.hoff;
+    return __ldg(A.hits + base + k);
 }
 
 // goodread + insert + mate + None-count + mate-overlap (read_collector.py:181-214, :395-418)
@@ -1057,7 +1059,7 @@ extern "C" int unfz_chain_size(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms
 extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
                                 const int64_t* seg_pair_off, const UnfzSiteCols* sites, const UnfzReadCols* reads,
                                 const UnfzReadSum* rsum, const int32_t* blk_maxspan, const uint32_t* hits,
-                                const int32_t* mark_prefix, const int32_t* het_list, const int32_t* n_het,
+                                const uint32_t* hit_tile_base, int32_t hit_tile_reads, const int32_t* mark_prefix, const int32_t* het_list, const int32_t* n_het,
                                 const uint32_t* cand_list, const int32_t* n_cand, const uint8_t* alleles,
                                 const int32_t* win, const int64_t* off,
                                 const int64_t* h_totals, const UnfzParams* hp, void* scratch, int64_t scratch_bytes,
@@ -1069,6 +1071,7 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     A.sites = *sites; A.reads = *reads; A.rsum = rsum; A.blk_maxspan = blk_maxspan; A.hits = hits; A.mp = mark_prefix;
     A.het_list = het_list; A.n_het = n_het; A.cand_list = cand_list; A.n_cand = n_cand; A.alleles = alleles;
     A.win = win; A.off = off; A.split_margin = hp->split_error_margin;
+    A.hit_tile_base = hit_tile_base; A.hit_tile_reads = hit_tile_reads;
     A.readlen = hp->readlen;
     const double bq = hp->min_gt_qual;
     A.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));

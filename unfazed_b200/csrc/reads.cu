@@ -81,7 +81,8 @@ __device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, in
 
 __global__ void __launch_bounds__(RS_THREADS)
 read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
-                 UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb, int32_t* __restrict__ blk_maxspan) {
+                 UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb, int32_t* __restrict__ blk_maxspan,
+                 uint32_t* __restrict__ tile_tot) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* qbuf = smem;                                             // RS_QBUF + 16
     int32_t* spos = reinterpret_cast<int32_t*>(smem + RS_QBUF + 16);  // RS_SPOS
@@ -89,6 +90,7 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
     __shared__ int64_t s_qa, s_qb, s_row_base, s_row_end;
     __shared__ int32_t s_rb0;
     __shared__ int32_t s_maxspan;
+    __shared__ int32_t s_wsum[RS_THREADS / 32];
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -198,6 +200,20 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
             cnt = c > 0xffff ? 0xffff : c;
         }
 
+        uint32_t hoff = 0;                       // offset inside the tile; see the pipelined kernel
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            int x = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_wsum[warp] = x;
+            __syncthreads();
+            int basew = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < RS_THREADS / 32; ++w) { if (w < warp) basew += s_wsum[w]; total += s_wsum[w]; }
+            hoff = (uint32_t)(basew + x - cnt);
+            if (threadIdx.x == 0) tile_tot[tile] = (uint32_t)total;
+        }
         // ---- low-quality bases out of the staged span ---------------------------------------
         int low = 0;
         while (chunk_lo < qb) {
@@ -225,7 +241,7 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
             o.fmark = fmark;
             o.flags = (uint16_t)flags;
             o.cnt = (uint16_t)cnt;
-            o.hoff = 0;
+            o.hoff = hoff;
             *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
             row_lb[r] = (int32_t)lbs;
         }
@@ -250,15 +266,39 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_STAGE = 36 * 1024;
 
+// query index of reference position p, or -1 (pysam get_reference_positions(full_length=True).index)
+__device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n_cigar, int32_t start, int32_t p) {
+    int32_t cur = start;
+    int q = 0;
+    for (int k = 0; k < n_cigar; ++k) {
+        const uint32_t w = __ldg(cg + k);
+        const uint32_t op = w & 15u;
+        const int32_t ln = (int32_t)(w >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            if (p < cur + ln) return p >= cur ? q + (p - cur) : -1;
+            cur += ln; q += ln;
+        } else if (op == 1 || op == 4) {
+            q += ln;
+        } else if (op == 2 || op == 3) {
+            if (p < cur + ln) return -1;
+            cur += ln;
+        }
+    }
+    return -1;
+}
+
+
+
 __global__ void __launch_bounds__(RS_THREADS)
 read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
                       int tile_reads, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
-                      int32_t* __restrict__ blk_maxspan) {
+                      int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage[2] = {smem, smem + RS_STAGE};
     int32_t* spos = reinterpret_cast<int32_t*>(smem + 2 * RS_STAGE);
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int64_t s_qa[3], s_qb[3];
+    __shared__ int32_t s_wsum[RS_THREADS / 32];
     __shared__ int64_t s_base, s_row_end;
     __shared__ int32_t s_rb0, s_maxspan;
 
@@ -329,9 +369,25 @@ read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
     __syncthreads();
     if (threadIdx.x == 0) issue(t0);
 
+    struct Pending { bool live; int64_t r; int64_t tile; UnfzReadSum o; int32_t lbs; } pend;
+    pend.live = false; pend.tile = -1;
+    auto flush = [&]() {                                       // after a barrier that follows the s_wsum writes
+        if (pend.tile < 0) return;
+        const int warp = threadIdx.x >> 5;
+        int basew = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) { const int v = s_wsum[w]; if (w < warp) basew += v; total += v; }
+        if (threadIdx.x == 0) tile_tot[pend.tile] = (uint32_t)total;
+        if (pend.live) {
+            pend.o.hoff += (uint32_t)basew;
+            *reinterpret_cast<int4*>(out + pend.r) = *reinterpret_cast<const int4*>(&pend.o);
+            if (row_lb) row_lb[pend.r] = pend.lbs;
+        }
+    };
     for (int64_t tile = t0; tile < t1; ++tile) {
         const int st = (int)((tile - t0) & 1);
         const int slot = (int)((tile - t0) % 3);
+        flush();                                               // results of the previous tile
         h2 = hdr_of(tile + 2, live2);                        // in flight during this iteration
         if (threadIdx.x == 0 && tile + 1 < t1) issue(tile + 1);
         const int64_t r0 = tile * tile_reads;
@@ -396,6 +452,17 @@ read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
             cnt = c > 0xffff ? 0xffff : c;
         }
 
+        // ---- hit slots: offset of the read inside its tile (block scan of cnt) + the tile's total; the
+        // pipeline scans the tile totals, so hoff(read) = tile_base[tile] + local offset.  Only the warp
+        // part of the scan runs here; it is finished after the tile's closing barrier (see `pending`),
+        // so the scan costs no barrier of its own.
+        int warp_incl = cnt;
+        {
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, warp_incl, o); if (lane >= o) warp_incl += y; }
+        }
+
         int low = 0;
         const int64_t qa = s_qa[slot], qb = s_qb[slot];
         if (qb > qa) {
@@ -406,13 +473,13 @@ read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
                 low = count_low_quals(stage[st], off, off + h.l_seq, (uint32_t)P.min_bq);
             }
         }
-        if (live) {
-            if ((flags & UNFZ_RS_GOOD_DISC) && low <= 10 && h.n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
-            UnfzReadSum o;
-            o.end = end; o.fmark = fmark; o.flags = (uint16_t)flags; o.cnt = (uint16_t)cnt; o.hoff = 0;
-            *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
-            row_lb[r] = (int32_t)lbs;
-        }
+        if (live && (flags & UNFZ_RS_GOOD_DISC) && low <= 10 && h.n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
+        // stash this tile's results; they are written once the block scan is complete
+        pend.live = live; pend.r = r; pend.tile = tile;
+        pend.o.end = end; pend.o.fmark = fmark; pend.o.flags = (uint16_t)flags; pend.o.cnt = (uint16_t)cnt;
+        pend.o.hoff = (uint32_t)(warp_incl - cnt);
+        pend.lbs = (int32_t)lbs;
+        if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = warp_incl;
         // ---- hand-over to the next tile ---------------------------------------------------------
         publish_span(tile + 2, h2, live2);                   // slot (tile+2)%3 is not in use
         if (threadIdx.x == 0) {
@@ -448,38 +515,19 @@ read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
         }
         h = h1; live = live1;
         h1 = h2; live1 = live2;
-        __syncthreads();   // stage st, spos and the carried state are consistent for the next tile
+        __syncthreads();   // stage st, spos, s_wsum and the carried state are consistent for the next tile
     }
+    flush();
 }
 
 // ------------------------------------------------------------------------------------------------
 // K3: read x marked-site allele lookup
 // ------------------------------------------------------------------------------------------------
-// query index of reference position p, or -1 (pysam get_reference_positions(full_length=True).index)
-__device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n_cigar, int32_t start, int32_t p) {
-    int32_t cur = start;
-    int q = 0;
-    for (int k = 0; k < n_cigar; ++k) {
-        const uint32_t w = __ldg(cg + k);
-        const uint32_t op = w & 15u;
-        const int32_t ln = (int32_t)(w >> 4);
-        if (op == 0 || op == 7 || op == 8) {
-            if (p < cur + ln) return p >= cur ? q + (p - cur) : -1;
-            cur += ln; q += ln;
-        } else if (op == 1 || op == 4) {
-            q += ln;
-        } else if (op == 2 || op == 3) {
-            if (p < cur + ln) return -1;
-            cur += ln;
-        }
-    }
-    return -1;
-}
-
 __global__ void __launch_bounds__(256)
 read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
                          const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
-                         const int32_t* __restrict__ row_lb, uint32_t* __restrict__ hits) {
+                         const int32_t* __restrict__ row_lb, const uint32_t* __restrict__ tile_base, int32_t tile_reads,
+                         uint32_t* __restrict__ hits) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= reads.n_reads) return;
     const UnfzReadSum s = load_rsum(rsum + r);
@@ -492,6 +540,7 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
     int64_t row = __ldg(row_lb + r);                       // first site row with pos >= start (from read_scan)
     const uint32_t* cg = reads.cigar + h.cigar_off;
     const int64_t q0 = read_qoff(h);
+    const int64_t hbase = (int64_t)__ldg(tile_base + (uint32_t)r / (uint32_t)tile_reads) + s.hoff;
     int written = 0;
     for (; row < b && written < s.cnt; ++row) {
         const int32_t p = __ldg(sites.pos + row);
@@ -506,16 +555,26 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
             const uint32_t code = (__ldg(reads.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
             word = (uint32_t)(q + 1) | (qb << 16) | (code << 24) | ((q + 1 < h.l_seq) ? (1u << 26) : 0u);
         }
-        if (k >= 0 && k < s.cnt) hits[(int64_t)s.hoff + k] = word;
+        if (k >= 0 && k < s.cnt) hits[hbase + k] = word;
         ++written;
     }
 }
 
 }  // namespace
 
+static int scan_tile_reads(int32_t max_l_seq) {
+    if (max_l_seq > 0 && (int64_t)max_l_seq + 32 <= RS_STAGE) {
+        int t = (RS_STAGE - 32) / max_l_seq;
+        return t > RS_THREADS ? RS_THREADS : t;
+    }
+    return RS_THREADS;
+}
+
+extern "C" int32_t unfz_read_scan_tile_reads(int32_t max_l_seq) { return scan_tile_reads(max_l_seq); }
+
 extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                               const int32_t* mark_prefix, const UnfzParams* hp, int32_t max_l_seq, UnfzReadSum* out,
-                              int32_t* row_lb, int32_t* blk_maxspan, void* stream) {
+                              int32_t* row_lb, int32_t* blk_maxspan, uint32_t* tile_tot, void* stream) {
     if (reads->n_reads <= 0) return 0;
     ScanParams P;
     P.min_mapq = hp->min_map_qual;
@@ -523,8 +582,7 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     P.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));
     P.readlen = hp->readlen;
     if (max_l_seq > 0 && (int64_t)max_l_seq + 32 <= RS_STAGE) {
-        int tile_reads = (RS_STAGE - 32) / max_l_seq;
-        if (tile_reads > RS_THREADS) tile_reads = RS_THREADS;
+        const int tile_reads = scan_tile_reads(max_l_seq);
         const size_t smem2 = 2 * RS_STAGE + RS_SPOS * sizeof(int32_t);
         static bool attr2 = false;
         if (!attr2) {
@@ -534,7 +592,8 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
         const int64_t tiles = (reads->n_reads + tile_reads - 1) / tile_reads;
         int64_t g = (int64_t)ctx->sm_count * 3;     // 3 CTAs x 72 KB of staging per SM
         if (g > tiles) g = tiles;
-        read_scan_pipe_kernel<<<(unsigned)g, RS_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, tile_reads, out, row_lb, blk_maxspan);
+        read_scan_pipe_kernel<<<(unsigned)g, RS_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, tile_reads,
+                                                                                     out, row_lb, blk_maxspan, tile_tot);
         UNFZ_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -547,17 +606,19 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     const int64_t n_tiles = (reads->n_reads + RS_THREADS - 1) / RS_THREADS;
     int64_t grid = (int64_t)ctx->sm_count * 4;     // 4 x ~49 KB of staging per SM
     if (grid > n_tiles) grid = n_tiles;
-    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan);
+    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan, tile_tot);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
 
 extern "C" int unfz_read_site_alleles(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                                       const uint8_t* row_mark, const int32_t* mark_prefix,
-                                      const UnfzReadSum* rsum, const int32_t* row_lb, uint32_t* hits, void* stream) {
+                                      const UnfzReadSum* rsum, const int32_t* row_lb, const uint32_t* tile_base,
+                                      int32_t tile_reads, uint32_t* hits, void* stream) {
     if (reads->n_reads <= 0) return 0;
     const int64_t blocks = (reads->n_reads + 255) / 256;
-    read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, row_lb, hits);
+    read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, row_lb,
+                                                                                 tile_base, tile_reads, hits);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -170,6 +170,11 @@ extern "C" int unfz_exclusive_scan_u16_u32(UnfzCtx* ctx, const uint16_t* in, int
     return scan_impl<uint16_t, uint32_t>(ctx, in, in_stride, out, out_stride, n, work, (cudaStream_t)stream, 0, total_out);
 }
 
+extern "C" int unfz_exclusive_scan_u32(UnfzCtx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int64_t* total_out,
+                                       void* work, void* stream) {
+    return scan_impl<uint32_t, uint32_t>(ctx, in, 4, out, 4, n, work, (cudaStream_t)stream, 1, total_out);
+}
+
 extern "C" int unfz_exclusive_scan_u8_i32(UnfzCtx* ctx, const uint8_t* in, int32_t* out, int64_t n, void* work, void* stream) {
     return scan_impl<uint8_t, int32_t>(ctx, in, 1, out, 4, n, work, (cudaStream_t)stream, 1, nullptr);
 }

@@ -291,6 +291,10 @@ class Engine:
             z1.add("off", 8 * (6 * (n + 1) + 1))
             e1.add("rsum", 16 * N)
             e1.add("row_lb", 4 * N)
+            tile_reads = int(lib.unfz_read_scan_tile_reads(dreads.max_l_seq))
+            n_tiles = (N + tile_reads - 1) // tile_reads
+            e1.add("tile_tot", 4 * n_tiles)
+            e1.add("tile_base", 4 * (n_tiles + 1))
         z1.alloc()
         e1.alloc()
         R = z1.ptr["result"]
@@ -339,15 +343,16 @@ class Engine:
             dreads.blk_sblk.copy_(torch.from_numpy(sb))
             if blk_cul is not None:
                 dreads.blk_cul[: blk_cul.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(blk_cul, dtype=np.float64)))
-            # ---- K2 + scan(hit counts) + chain sizing; ONE host sync for all the sizes ---------------
+            # ---- K2 + scan(tile hit totals) + chain sizing; ONE host sync for all the sizes ------------
             off_ptr = z1.ptr["off"]
             total_hits_ptr = off_ptr + 8 * 6 * (n + 1)
+            mark("alloc2")
             self._check(lib.unfz_read_scan(ctx, rc_, sc, z1.ptr["mark_prefix"], C.byref(params), dreads.max_l_seq, e1.ptr["rsum"],
-                                           e1.ptr["row_lb"], z1.ptr["blk_maxspan"], s), "read_scan")
+                                           e1.ptr["row_lb"], z1.ptr["blk_maxspan"], e1.ptr["tile_tot"], s), "read_scan")
             launches += 1
             mark("read_scan")
-            self._check(lib.unfz_exclusive_scan_u16_u32(ctx, e1.ptr["rsum"] + 10, 16, e1.ptr["rsum"] + 12, 16, N, total_hits_ptr,
-                                                        e1.ptr["scan_work"], s), "scan(hits)")
+            self._check(lib.unfz_exclusive_scan_u32(ctx, e1.ptr["tile_tot"], e1.ptr["tile_base"], n_tiles, total_hits_ptr,
+                                                    e1.ptr["scan_work"], s), "scan(hits)")
             launches += 3
             mark("scan_hits")
             self._check(lib.unfz_chain_size(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
@@ -374,18 +379,21 @@ class Engine:
             e3.alloc()
             mark("alloc3")
             self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, z1.ptr["row_mark"], z1.ptr["mark_prefix"], e1.ptr["rsum"],
-                                                   e1.ptr["row_lb"], e3.ptr["hits"], s), "read_site_alleles")
+                                                   e1.ptr["row_lb"], e1.ptr["tile_base"], tile_reads, e3.ptr["hits"], s),
+                        "read_site_alleles")
             launches += 1
             mark("read_site_alleles")
             self._check(lib.unfz_chain_tally(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
-                                             z1.ptr["blk_maxspan"], e3.ptr["hits"], z1.ptr["mark_prefix"], e2.ptr["het_list"],
+                                             z1.ptr["blk_maxspan"], e3.ptr["hits"], e1.ptr["tile_base"], tile_reads, z1.ptr["mark_prefix"],
+                                             e2.ptr["het_list"],
                                              rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], p_all, rp["win"], off_ptr,
                                              totals.ctypes.data, C.byref(params), e3.ptr["scratch"], nbytes,
                                              z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"], s),
                         "chain_tally")
             launches += 1
             mark("chain_tally")
-            dv.update(rsum=e1.view["rsum"], hits=e3.view["hits"].view(torch.int32), slot_label=z3.view["slot_label"],
+            dv.update(rsum=e1.view["rsum"], hits=e3.view["hits"].view(torch.int32),
+                      tile_base=e1.view["tile_base"].view(torch.int32), tile_reads=tile_reads, slot_label=z3.view["slot_label"],
                       slot_evid=z3.view["slot_evid"], row_mark=z1.view["row_mark"],
                       mark_prefix=z1.view["mark_prefix"].view(torch.int32), _keep3=(z3, e3))
             res.slot_off = h_off[0].copy()

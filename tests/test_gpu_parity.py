@@ -165,3 +165,42 @@ def test_hit_words_match_the_oracle_lookup(engine):
                 assert (w & 0xFFFF) == 0
             checked += 1
     assert checked > 300
+
+
+@pytest.mark.parametrize("no_extended", [False, True])
+def test_collect_reads_drop_in_matches_oracle(engine, no_extended):
+    """read_collector.collect_reads_snv / collect_reads_sv (reference signatures, GPU inside) return the
+    same haplotype-grouped reads as the oracle's per-variant functions."""
+    from unfazed_b200 import datasource, read_collector
+    ds = make_dataset(SynthConfig(dnms_per_trio=24, seed=61, indel_frac=0.2, sv_frac=0.3, sv_max_len=20000))
+    p = port.Params(no_extended=no_extended)
+    bam_name = ds.bam_name("kid0")
+    datasource._registry.clear()
+    datasource.register_tables(bam_name, reads=ds.reads)
+    ann = port.find(copy.deepcopy(ds.dnms), ds.pedigrees, ds.sites, p, p.search_dist, whole_region=False)
+    bam = port.Bam(ds.reads, 0)
+    n_checked = 0
+    for dn in ann:
+        if "het_sites" not in dn:
+            continue
+        region = {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]}
+        if dn["vartype"] in port.SV_TYPES:
+            want, cul, _ = port.collect_reads_sv(bam, region, dn["het_sites"], None, p)
+            got, cul2 = read_collector.collect_reads_sv(bam_name, region, dn["het_sites"], None, no_extended, None,
+                                                        p.insert_size_max_sample, p.stdevs, p.min_map_qual, p.min_gt_qual,
+                                                        p.readlen, p.split_error_margin)
+        else:
+            ref, alts = port.get_refalt(ds.sites, 0, dn["chrom"], dn["start"], "")
+            if len(alts) != 1:
+                continue
+            want, cul, _ = port.collect_reads_snv(bam, region, dn["het_sites"], ref, alts[0], None, p)
+            got, cul2 = read_collector.collect_reads_snv(bam_name, region, dn["het_sites"], ref, alts[0], None, no_extended,
+                                                         None, p.insert_size_max_sample, p.stdevs, p.min_map_qual,
+                                                         p.min_gt_qual, p.readlen, p.split_error_margin)
+        assert float(cul) == float(cul2)
+        for hap in ("ref", "alt"):
+            w = sorted({(bam.name(r), int(ds.reads.hdr["start"][r])) for r in want[hap]})
+            g = sorted({(r.query_name, r.reference_start) for r in got[hap]})
+            assert g == w, (port._key(dn), hap)
+        n_checked += 1
+    assert n_checked >= 12

@@ -18,6 +18,7 @@ namespace {
 constexpr int CH_THREADS = 128;
 constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr unsigned long long KEY_NONE = ~0ull;
+constexpr int CH_SMEM_SITES = 256;         // per-site state lives in shared memory up to this many het sites
 
 struct Scratch {
     // per window slot
@@ -334,7 +335,7 @@ __device__ uint8_t allele_info(const ChainArgs& A, const Scratch& S, int64_t e0,
     return out;
 }
 
-__global__ void __launch_bounds__(CH_THREADS)
+__global__ void __launch_bounds__(CH_THREADS, 8)
 chain_kernel(ChainArgs A) {
     const int d = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -371,11 +372,19 @@ chain_kernel(ChainArgs A) {
     int32_t* seed_e = S0.seed_e + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed;
     int32_t* sinc_x = S0.sinc_x + o_sinc; int32_t* sinc_site = S0.sinc_site + o_sinc;
     int32_t* sinc_sidx = S0.sinc_sidx + o_sinc; uint8_t* sinc_al = S0.sinc_al + o_sinc;
-    int32_t* spos = S0.spos + o_het; uint8_t* sref = S0.sref + o_het; uint8_t* salt = S0.salt + o_het;
-    int32_t* site_off = S0.site_off + o_het + d;
-    int32_t* cand_off = S0.cand_off + o_het + d;
-    unsigned long long* bestkey = S0.bestkey + o_het;
-    int32_t* site_cnt = S0.site_cnt + o_het; int32_t* site_base = S0.site_base + o_het;
+    __shared__ int32_t sh_spos[CH_SMEM_SITES], sh_site_off[CH_SMEM_SITES + 1], sh_cand_off[CH_SMEM_SITES + 1];
+    __shared__ int32_t sh_site_cnt[CH_SMEM_SITES], sh_site_base[CH_SMEM_SITES];
+    __shared__ unsigned long long sh_bestkey[CH_SMEM_SITES];
+    __shared__ uint8_t sh_sref[CH_SMEM_SITES], sh_salt[CH_SMEM_SITES];
+    const bool small_sites = nh <= CH_SMEM_SITES;
+    int32_t* spos = small_sites ? sh_spos : S0.spos + o_het;
+    uint8_t* sref = small_sites ? sh_sref : S0.sref + o_het;
+    uint8_t* salt = small_sites ? sh_salt : S0.salt + o_het;
+    int32_t* site_off = small_sites ? sh_site_off : S0.site_off + o_het + d;
+    int32_t* cand_off = small_sites ? sh_cand_off : S0.cand_off + o_het + d;
+    unsigned long long* bestkey = small_sites ? sh_bestkey : S0.bestkey + o_het;
+    int32_t* site_cnt = small_sites ? sh_site_cnt : S0.site_cnt + o_het;
+    int32_t* site_base = small_sites ? sh_site_base : S0.site_base + o_het;
     int32_t* cpos = S0.cpos + o_cand;
     uint8_t* cev = A.cand_evid + lbase;
 
@@ -401,7 +410,9 @@ chain_kernel(ChainArgs A) {
     };
     const double cul = R.blk_cul[dn.rblk];
 
-    for (int x = tid; x < W; x += CH_THREADS) { label[x] = 0; evid[x] = 0; prim[x] = -1; lvl[x] = -1; fpos[x] = -1; ord[x] = 0xffffffffu; tmp[x] = 0; minkey[x] = 0ull; }
+    // per-slot state is initialised lazily, only for the pairs that get touched (seeds + registered
+    // reads); slot_label / slot_evid are zero-filled by the caller
+    auto init_slot = [&](int x) { prim[x] = -1; lvl[x] = -1; fpos[x] = -1; ord[x] = 0xffffffffu; tmp[x] = 0; minkey[x] = 0ull; };
     for (int i = tid; i < nh; i += CH_THREADS) {
         const int64_t row = H[i];
         spos[i] = __ldg(A.sites.pos + row);
@@ -492,6 +503,8 @@ chain_kernel(ChainArgs A) {
     }
     __syncthreads();
 
+    for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) init_slot(x); }
+    __syncthreads();
     int n_inc = 0, n_sinc = 0;
     const int nh_reg = A.no_extended ? 0 : nh;     // --no-extended: seeds are the haplotype lists
     if (!A.no_extended) {
@@ -550,19 +563,21 @@ chain_kernel(ChainArgs A) {
                 inc_x[k] = x;
                 inc_site[k] = i;
                 inc_sidx[k] = i;      // order key inside read_sites[x]: registered sites come in site order
-                // fetched_reads[name] = [read, mate]: the last writer (highest site) wins (Q18)
-                atomicMax(minkey + x, ((unsigned long long)(uint32_t)(i + 1) << 32) | (uint32_t)r);
             }
             n_inc += tot;
         }
         if (n_inc > cap_inc) { n_inc = (int)cap_inc; T.status |= 2; }
         __syncthreads();
-        for (int k = tid; k < n_inc; k += CH_THREADS)
+        for (int k = tid; k < n_inc; k += CH_THREADS) {
             if (k == 0 || inc_site[k - 1] != inc_site[k]) site_off[inc_site[k]] = k;
-        for (int x = tid; x < W; x += CH_THREADS) {
-            const unsigned long long pk = minkey[x];
-            if (pk != 0ull) prim[x] = (int32_t)(uint32_t)pk;
+            init_slot(inc_x[k]);                                    // idempotent
         }
+        __syncthreads();
+        // fetched_reads[name] = [read, mate]: the last writer (highest site) wins (Q18)
+        for (int k = tid; k < n_inc; k += CH_THREADS)
+            atomicMax(minkey + inc_x[k], ((unsigned long long)(uint32_t)(inc_site[k] + 1) << 32) | (uint32_t)inc_r[k]);
+        __syncthreads();
+        for (int k = tid; k < n_inc; k += CH_THREADS) prim[inc_x[k]] = (int32_t)(uint32_t)minkey[inc_x[k]];
         __syncthreads();
         if (tid == 0) {                                             // empty sites inherit the next offset
             int nxt = n_inc;
@@ -585,7 +600,8 @@ chain_kernel(ChainArgs A) {
             block_prefix(k < n_seed && seed_hap[k] == 1, &tot);
             n_ref_entries += tot;
         }
-        for (int x = tid; x < W; x += CH_THREADS) minkey[x] = 0ull;
+        for (int k = tid; k < n_inc; k += CH_THREADS) minkey[inc_x[k]] = 0ull;
+        for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) minkey[x] = 0ull; }
         __syncthreads();
         int ref_seen = 0, alt_seen = 0;
         int ns_total = 0;
@@ -647,9 +663,9 @@ chain_kernel(ChainArgs A) {
             ns_total += tm;
         }
         __syncthreads();
-        for (int x = tid; x < W; x += CH_THREADS) {
-            const unsigned long long pk = minkey[x];
-            if (pk != 0ull) prim[x] = (int32_t)(uint32_t)pk;
+        for (int k = tid; k < n_seed; k += CH_THREADS) {
+            const int x = canon(seed_e[k]);
+            if (x >= 0 && minkey[x] != 0ull) prim[x] = (int32_t)(uint32_t)minkey[x];
         }
         n_sinc = ns_total;
         if (n_sinc > cap_sinc) { n_sinc = (int)cap_sinc; T.status |= 4; }
@@ -668,7 +684,8 @@ chain_kernel(ChainArgs A) {
         __syncthreads();
 
         // ------------------------------------------------------------ phase 4: level-synchronous BFS
-        for (int x = tid; x < W; x += CH_THREADS) minkey[x] = KEY_NONE;
+        for (int k = tid; k < n_inc; k += CH_THREADS) minkey[inc_x[k]] = KEY_NONE;
+        __syncthreads();
         for (int level = 0;; ++level) {
             for (int i = tid; i < nh; i += CH_THREADS) { bestkey[i] = KEY_NONE; site_cnt[i] = 0; }
             __syncthreads();

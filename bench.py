@@ -295,7 +295,7 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         hd = ds.reads.hdr
-        rs_bytes = float(32 * n_reads + 4 * int(hd["n_cigar"].sum()) + int(hd["l_seq"].sum()) + 16 * n_reads)
+        rs_bytes = float(32 * n_reads + 4 * int(hd["n_cigar"].sum()) + int(hd["l_seq"].sum()) + 20 * n_reads)
         survey_read_bytes = float(24 * n_reads + 4 * int(hd["n_cigar"].sum()) + int(np.ceil(hd["l_seq"] / 4).sum())
                                   + int(hd["l_seq"].sum()) + 4 * n_hits)
         kern = {
@@ -321,9 +321,17 @@ def run_b200(args):
         dom = max(kern, key=lambda k: kern[k]["ms"])
         domk = kern[dom]
         lookup_ms = kern["read_scan"]["ms"] + kern["read_site_alleles"]["ms"]
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get(dom)
+            if ent and ent.get("dnms") == args.dnms:
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {
             "kernel": dom, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
-            "achieved": domk.get("gbps"), "frac": domk.get("frac"), "traffic": None,
+            "achieved": domk.get("gbps"), "frac": domk.get("frac"), "traffic": traffic,
             "ms_per_launch": domk["ms"],
             "kernels": kern,
             "classify_sites_saturating": sat,

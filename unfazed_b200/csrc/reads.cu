@@ -59,24 +59,34 @@ struct ScanParams {
 
 __device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, int beg, int end, uint32_t minq) {
     // number of bytes b in s[beg,end) with (b & 0x7f) < minq; minq in [0,128].
-    // Per word: t = (x | 0x80..) - m4 never borrows across bytes (x, m <= 128), and bit 7 of a byte
-    // of t is clear exactly when x < m.  Byte-wise counters are summed with one multiply; POPC is
-    // avoided on purpose (it issues on the quarter-rate XU pipe and was the top pipe in ncu).
-    int cnt = 0, i = beg;
+    // Per aligned 32-bit word: t = (x | 0x80808080) - m4 never borrows across bytes (the OR also drops
+    // the escape bit), and bit 7 of a byte of t is clear exactly when (x & 0x7f) < m.  The four flag
+    // bytes (0x80 or 0) are summed with one DP4A; the first and last word are masked to the range.
+    // No POPC (quarter-rate XU pipe, it was the top pipe in the first ncu capture) and no byte loops.
+    if (end <= beg) return 0;
     const uint32_t m4 = minq * 0x01010101u;
-    while (i < end && (i & 3)) { cnt += (uint32_t)(s[i] & 0x7f) < minq; ++i; }
-    while (i + 4 <= end) {
-        uint32_t acc = 0;
-        const int stop = min(end - 3, i + 4 * 63);          // <= 63 words: byte counters stay < 256
-        for (; i < stop; i += 4) {
-            const uint32_t x = *reinterpret_cast<const uint32_t*>(s + i) & 0x7f7f7f7fu;
-            const uint32_t t = (x | 0x80808080u) - m4;
-            acc += (~t & 0x80808080u) >> 7;
-        }
-        cnt += (int)((acc * 0x01010101u) >> 24);
+    const int w0 = beg & ~3, w1 = (end + 3) & ~3;
+    const uint32_t head = 0x80808080u << (8 * (beg & 3));                 // bytes >= beg inside the first word
+    const uint32_t tail = 0x80808080u >> (8 * ((4 - (end & 3)) & 3));     // bytes <  end inside the last word
+    unsigned acc = 0;
+    // first word (masked), unmasked middle words, last word (masked): the masks stay out of the loop
+    {
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(s + w0);
+        uint32_t f = ~((x | 0x80808080u) - m4) & 0x80808080u & head;
+        if (w1 - w0 == 4) f &= tail;
+        acc = __dp4a(f, 0x01010101u, acc);
     }
-    for (; i < end; ++i) cnt += (uint32_t)(s[i] & 0x7f) < minq;
-    return cnt;
+    const int wl = w1 - 4;
+#pragma unroll 8
+    for (int i = w0 + 4; i < wl; i += 4) {
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(s + i);
+        acc = __dp4a(~((x | 0x80808080u) - m4) & 0x80808080u, 0x01010101u, acc);
+    }
+    if (wl > w0) {
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(s + wl);
+        acc = __dp4a(~((x | 0x80808080u) - m4) & 0x80808080u & tail, 0x01010101u, acc);
+    }
+    return (int)(acc >> 7);
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -432,9 +442,12 @@ read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
         int64_t lbs = 0, lbe = 0;
         if (live && sb >= 0) {
             if (rb == rb0) {
-                int lo = 0, hi = RS_SPOS;
+                // a tile spans a few site rows only: gallop from the front of the staged window
+                int lo = 0, hi = 8;
+                while (hi < RS_SPOS && spos[hi - 1] < h.start) { lo = hi; hi = min(hi * 2, RS_SPOS); }
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h.start) lo = mid + 1; else hi = mid; }
-                int lo2 = lo; hi = RS_SPOS;
+                int lo2 = lo; hi = min(lo + 4, RS_SPOS);
+                while (hi < RS_SPOS && spos[hi - 1] < end) { lo2 = hi; hi = min(hi + 8, RS_SPOS); }
                 while (lo2 < hi) { int mid = (lo2 + hi) >> 1; if (spos[mid] < end) lo2 = mid + 1; else hi = mid; }
                 lbs = row_base + lo;
                 lbe = row_base + lo2;

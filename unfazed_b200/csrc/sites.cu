@@ -131,7 +131,7 @@ __device__ __forceinline__ uint8_t classify_pair(const GtThr* __restrict__ thr, 
 }
 
 constexpr int CLS_THREADS = 256;
-constexpr int CLS_PER_THREAD = 4;
+constexpr int CLS_PER_THREAD = 8;
 constexpr int CLS_TILE = CLS_THREADS * CLS_PER_THREAD;
 constexpr int CLS_SMEM_SEGS = 512;
 

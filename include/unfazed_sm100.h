@@ -193,8 +193,6 @@ const char* unfz_last_error(UnfzCtx* ctx);
 /* Exclusive prefix sums (device-wide).  `work` needs unfz_scan_work_bytes(n) bytes. */
 int64_t unfz_scan_work_bytes(int64_t n);
 int unfz_exclusive_scan_i64(UnfzCtx*, const int64_t* in, int64_t* out, int64_t n, void* work, void* stream);
-int unfz_exclusive_scan_u16_u32(UnfzCtx*, const uint16_t* in, int64_t in_stride_bytes, uint32_t* out,
-                                int64_t out_stride_bytes, int64_t n, int64_t* total_out, void* work, void* stream);
 int unfz_exclusive_scan_u8_i32(UnfzCtx*, const uint8_t* in, int32_t* out, int64_t n, void* work, void* stream);
 int unfz_exclusive_scan_u32(UnfzCtx*, const uint32_t* in, uint32_t* out /* n+1 entries */, int64_t n, int64_t* total_out,
                             void* work, void* stream);
@@ -275,6 +273,18 @@ int unfz_chain_tally(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSe
                      UnfzTally* tally, void* stream);
 int64_t unfz_chain_scratch_bytes(int64_t slots, int64_t incs, int64_t seeds, int64_t seed_incs,
                                  int64_t het_sites, int64_t cand_sites, int64_t n_dnms);
+
+/* estimate_concordant_insert_len (read_collector.py:11-25): four order statistics (0-based ranks
+ * h_ranks[4], HOST array) of |tlen - 2*readlen| over the reads of n_ranges index ranges
+ * [first, first+count) (HOST arrays), selected exactly with a two-level radix histogram.  numpy's
+ * percentile interpolates between two adjacent order statistics; the caller asks for the
+ * neighbourhood of the 99.5th percentile's virtual index and lets numpy itself interpolate, so the
+ * estimate is bit-identical to the reference's.  work: unfz_insert_size_work_bytes() bytes, zeroed
+ * by the caller.  out[0..3] (device uint32) receive the values. */
+int64_t unfz_insert_size_work_bytes(void);
+int unfz_insert_size_order_stats(UnfzCtx*, const UnfzReadCols* reads, const int64_t* h_first, const int64_t* h_count,
+                                 int32_t n_ranges, int32_t readlen, const uint64_t* h_ranks, void* work,
+                                 uint32_t* out, void* stream);
 
 /* Final call per DNM: unfazed.py summarize_record :190-334 on the tallies (+ autophase :162-187). */
 int unfz_summarize(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzTally* tally,

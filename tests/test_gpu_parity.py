@@ -204,3 +204,17 @@ def test_collect_reads_drop_in_matches_oracle(engine, no_extended):
             assert g == w, (port._key(dn), hap)
         n_checked += 1
     assert n_checked >= 12
+
+
+def test_device_insert_size_estimate_is_bit_identical(engine):
+    """estimate_concordant_insert_len via unfz_insert_size_order_stats == the host numpy percentile the
+    reference computes, for several sample caps (incl. caps that cut inside a read block)."""
+    from unfazed_b200.plan import concordant_upper_lens
+    ds = make_dataset(SynthConfig(n_trios=2, dnms_per_trio=12, seed=71, coverage=12.0))
+    dreads = engine.upload_reads(ds.reads)
+    for cap in (1000000, 5000, 777, 10, 0):
+        want = concordant_upper_lens(ds.reads, 151, cap, 3)
+        got = engine.concordant_upper_lens(dreads, 151, cap, 3)
+        assert np.array_equal(want, got), cap
+    bam = port.Bam(ds.reads, 1)
+    assert float(port.estimate_concordant_insert_len(bam, port.Params())) == float(engine.concordant_upper_lens(dreads, 151, 1000000, 3)[-1])

@@ -78,7 +78,6 @@ SYMBOLS = {
     "unfz_last_error": (C.c_char_p, [_P]),
     "unfz_scan_work_bytes": (c_int64, [c_int64]),
     "unfz_exclusive_scan_i64": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
-    "unfz_exclusive_scan_u16_u32": (C.c_int, [_P, _P, c_int64, _P, c_int64, c_int64, _P, _P, _P]),
     "unfz_exclusive_scan_u8_i32": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
     "unfz_exclusive_scan_u32": (C.c_int, [_P, _P, _P, c_int64, _P, _P, _P]),
     "unfz_exclusive_scan_rows_i64": (C.c_int, [_P, _P, _P, c_int32, c_int64, _P]),
@@ -94,6 +93,8 @@ SYMBOLS = {
     "unfz_chain_tally": (C.c_int, [_P, _P, c_int32, _P, _P, C.POINTER(SiteCols), C.POINTER(ReadCols), _P, _P, _P, _P, c_int32, _P,
                                    _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(Params), _P, c_int64,
                                    _P, _P, _P, _P, _P]),
+    "unfz_insert_size_work_bytes": (c_int64, []),
+    "unfz_insert_size_order_stats": (C.c_int, [_P, C.POINTER(ReadCols), _P, _P, c_int32, c_int32, _P, _P, _P, _P]),
     "unfz_summarize": (C.c_int, [_P, _P, c_int32, _P, _P, _P, _P, C.POINTER(Params), _P, _P, _P]),
 }
 

@@ -22,7 +22,7 @@ constexpr int CH_SMEM_SITES = 256;         // per-site state lives in shared mem
 
 struct Scratch {
     // per window slot
-    int32_t* prim; uint32_t* ord; int32_t* lvl; int32_t* fpos; int32_t* icnt;
+    int32_t* prim; uint32_t* ord; int32_t* lvl; int32_t* fpos;
     unsigned long long* minkey; int32_t* tmp;
     // per het-site incidence
     int32_t* inc_r; int32_t* inc_x; int32_t* inc_site; int32_t* inc_sidx; uint8_t* inc_al;
@@ -32,7 +32,7 @@ struct Scratch {
     int32_t* sinc_x; int32_t* sinc_site; int32_t* sinc_sidx; uint8_t* sinc_al;
     // per het site (site_off has one extra entry per DNM)
     int32_t* spos; uint8_t* sref; uint8_t* salt; int32_t* site_off; int32_t* cand_off;
-    unsigned long long* bestkey; uint8_t* best_info; int32_t* site_cnt; int32_t* site_base;
+    unsigned long long* bestkey; int32_t* site_cnt; int32_t* site_base;
     // per candidate site
     int32_t* cpos;
 };
@@ -1033,7 +1033,7 @@ Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_
     char* p = base;
     S.prim = (int32_t*)carve<int32_t>(p, slots); S.ord = (uint32_t*)carve<uint32_t>(p, slots);
     S.lvl = (int32_t*)carve<int32_t>(p, slots); S.fpos = (int32_t*)carve<int32_t>(p, slots);
-    S.icnt = (int32_t*)carve<int32_t>(p, slots); S.minkey = (unsigned long long*)carve<unsigned long long>(p, slots);
+    S.minkey = (unsigned long long*)carve<unsigned long long>(p, slots);
     S.tmp = (int32_t*)carve<int32_t>(p, slots);
     S.inc_r = (int32_t*)carve<int32_t>(p, incs); S.inc_x = (int32_t*)carve<int32_t>(p, incs);
     S.inc_site = (int32_t*)carve<int32_t>(p, incs); S.inc_sidx = (int32_t*)carve<int32_t>(p, incs);
@@ -1044,7 +1044,7 @@ Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_
     S.spos = (int32_t*)carve<int32_t>(p, hets); S.sref = (uint8_t*)carve<uint8_t>(p, hets);
     S.salt = (uint8_t*)carve<uint8_t>(p, hets); S.site_off = (int32_t*)carve<int32_t>(p, hets + n_dnms + 1);
     S.cand_off = (int32_t*)carve<int32_t>(p, hets + n_dnms + 1);
-    S.bestkey = (unsigned long long*)carve<unsigned long long>(p, hets); S.best_info = (uint8_t*)carve<uint8_t>(p, hets);
+    S.bestkey = (unsigned long long*)carve<unsigned long long>(p, hets);
     S.site_cnt = (int32_t*)carve<int32_t>(p, hets); S.site_base = (int32_t*)carve<int32_t>(p, hets);
     S.cpos = (int32_t*)carve<int32_t>(p, cands);
     *total = (int64_t)(p - base);

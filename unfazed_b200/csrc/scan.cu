@@ -165,11 +165,6 @@ extern "C" int unfz_exclusive_scan_i64(UnfzCtx* ctx, const int64_t* in, int64_t*
     return scan_impl<int64_t, int64_t>(ctx, in, 8, out, 8, n, work, (cudaStream_t)stream, 1, nullptr);
 }
 
-extern "C" int unfz_exclusive_scan_u16_u32(UnfzCtx* ctx, const uint16_t* in, int64_t in_stride, uint32_t* out,
-                                           int64_t out_stride, int64_t n, int64_t* total_out, void* work, void* stream) {
-    return scan_impl<uint16_t, uint32_t>(ctx, in, in_stride, out, out_stride, n, work, (cudaStream_t)stream, 0, total_out);
-}
-
 extern "C" int unfz_exclusive_scan_u32(UnfzCtx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int64_t* total_out,
                                        void* work, void* stream) {
     return scan_impl<uint32_t, uint32_t>(ctx, in, 4, out, 4, n, work, (cudaStream_t)stream, 1, total_out);

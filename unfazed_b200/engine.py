@@ -204,6 +204,56 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------------------------
+    def concordant_upper_lens(self, dreads: "DeviceReads", readlen: int, insert_size_max_sample: int, stdevs: int) -> np.ndarray:
+        """Per read block: the reference's estimate_concordant_insert_len of the block's kid
+        (read_collector.py:11-25), with the order statistics selected on the GPU
+        (unfz_insert_size_order_stats) and numpy's own interpolation applied to them."""
+        t = dreads.table
+        lib, dev = self.lib, self.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        out = np.zeros(max(t.n_blocks, 1), dtype=np.float64)
+        nwork = int(lib.unfz_insert_size_work_bytes())
+        head = getattr(t, "head_tlen", None) or {}
+        for k, kid in enumerate(t.kids):
+            blocks = [b for b in range(t.n_blocks) if int(t.blk_kid[b]) == k]
+            if kid in head:                       # packed from a real file: the head of the BAM is host data
+                from .plan import concordant_upper_lens as host_cul
+                return host_cul(t, readlen, insert_size_max_sample, stdevs)
+            first, count, left = [], [], insert_size_max_sample + 1
+            for b in blocks:
+                if left <= 0:
+                    break
+                lo, hi = int(t.blk_off[b]), int(t.blk_off[b + 1])
+                take = min(left, hi - lo)
+                first.append(lo)
+                count.append(take)
+                left -= take
+            n = int(sum(count))
+            if n == 0:
+                continue
+            # neighbourhood of numpy's virtual index (n-1)*0.995 (linear method)
+            k0 = int(np.floor((n - 1) * 0.995))
+            ranks = np.clip(np.array([k0 - 1, k0, k0 + 1, k0 + 2], dtype=np.int64), 0, n - 1).astype(np.uint64)
+            work = torch.zeros(nwork, dtype=torch.uint8, device=dev)
+            vals = torch.zeros(4, dtype=torch.int32, device=dev)
+            hf, hc = np.array(first, dtype=np.int64), np.array(count, dtype=np.int64)
+            self._check(lib.unfz_insert_size_order_stats(self.ctx, C.byref(dreads.cols), hf.ctypes.data, hc.ctypes.data, len(first),
+                                                         int(readlen), ranks.ctypes.data, work.data_ptr(), vals.data_ptr(), st),
+                        "insert_size_order_stats")
+            v = vals.cpu().numpy().view(np.uint32).astype(np.int64)
+            # an array with the same order statistics around the virtual index; numpy does the rest
+            surrogate = np.empty(n, dtype=np.int64)
+            r = ranks.astype(np.int64)
+            surrogate[: r[1]] = v[0]
+            surrogate[r[1]] = v[1]
+            surrogate[r[2]:] = v[3]
+            surrogate[r[2]] = v[2]
+            pct = np.percentile(surrogate, 99.5)
+            cul = float(int(np.mean(pct)) + (np.std(pct) * stdevs))
+            for b in blocks:
+                out[b] = cul
+        return out
+
     def upload_sites(self, table: SiteTable, pin: bool = False) -> DeviceSites:
         return DeviceSites(table, self.device, pin)
 

@@ -39,7 +39,7 @@ class BatchPhaser:
             return None
         key = (readlen, insert_size_max_sample, stdevs)
         if key not in self._cul_cache:
-            self._cul_cache[key] = concordant_upper_lens(self.reads, readlen, insert_size_max_sample, stdevs)
+            self._cul_cache[key] = self.engine.concordant_upper_lens(self.dreads, readlen, insert_size_max_sample, stdevs)
         return self._cul_cache[key]
 
     def site_dicts(self, res: BatchResult, d: int, trio: int, with_kid_allele: bool):

@@ -253,7 +253,9 @@ int unfz_chain_size(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSeg
                     const UnfzReadCols* reads, const UnfzReadSum* rsum, const int32_t* blk_maxspan,
                     const int32_t* het_list, const int32_t* n_het, const uint32_t* cand_list,
                     const int32_t* n_cand, int32_t* win /* [4][n_dnms]: a_lo, a_hi, b_lo, b_hi */,
-                    int64_t* need, void* stream);
+                    int64_t* need,
+                    int32_t* site_lo, int32_t* site_n /* per het-list entry: candidate read range of fetch(pos, pos+1) */,
+                    int32_t* seed_win /* [n_dnms][4]: candidate read ranges of the seed fetches */, void* stream);
 
 /* Seed reads (collect_reads_snv :339-432), extended chaining (group_reads_by_haplotype :155-263,
  * connect_reads :76-152), site matching (site_searcher.py:6-78), phase_by_reads and the per-parent
@@ -267,7 +269,7 @@ int unfz_chain_tally(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSe
                      const int32_t* mark_prefix,
                      const int32_t* het_list, const int32_t* n_het, const uint32_t* cand_list,
                      const int32_t* n_cand, const uint8_t* alleles, const int32_t* win,
-                     const int64_t* off, const int64_t* h_totals /* off[k][n_dnms], k<6 */,
+                     const int32_t* site_lo, const int32_t* site_n, const int32_t* seed_win, const int64_t* off, const int64_t* h_totals /* off[k][n_dnms], k<6 */,
                      const UnfzParams* h_params, void* scratch, int64_t scratch_bytes,
                      uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid,
                      UnfzTally* tally, void* stream);

@@ -88,10 +88,10 @@ SYMBOLS = {
     "unfz_read_scan": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, C.POINTER(Params), c_int32, _P, _P, _P, _P, _P]),
     "unfz_read_site_alleles": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, _P, _P, _P, _P, c_int32, _P, _P]),
     "unfz_chain_size": (C.c_int, [_P, _P, c_int32, _P, _P, C.POINTER(SiteCols), C.POINTER(ReadCols), _P, _P,
-                                  _P, _P, _P, _P, _P, _P, _P]),
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "unfz_chain_scratch_bytes": (c_int64, [c_int64] * 7),
     "unfz_chain_tally": (C.c_int, [_P, _P, c_int32, _P, _P, C.POINTER(SiteCols), C.POINTER(ReadCols), _P, _P, _P, _P, c_int32, _P,
-                                   _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(Params), _P, c_int64,
+                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(Params), _P, c_int64,
                                    _P, _P, _P, _P, _P]),
     "unfz_insert_size_work_bytes": (c_int64, []),
     "unfz_insert_size_order_stats": (C.c_int, [_P, C.POINTER(ReadCols), _P, _P, c_int32, c_int32, _P, _P, _P, _P]),

@@ -46,6 +46,7 @@ struct ChainArgs {
     const uint8_t* alleles; const int32_t* win; const int64_t* off;  // win[4][n], off[6][n+1]
     int32_t split_margin;
     const uint32_t* hit_tile_base; int32_t hit_tile_reads;
+    const int32_t* site_lo; const int32_t* site_n; const int32_t* seed_win;   // fetch ranges found by chain_size
     int32_t readlen, min_bq, ext_goal, no_extended;
     uint8_t* slot_label; uint8_t* slot_evid; uint8_t* cand_evid; UnfzTally* tally;
     Scratch S;
@@ -389,8 +390,7 @@ chain_kernel(ChainArgs A) {
     uint8_t* cev = A.cand_evid + lbase;
 
     const UnfzReadCols& R = A.reads;
-    const int64_t blk_lo = R.blk_off[dn.rblk], blk_hi = R.blk_off[dn.rblk + 1];
-    const int64_t maxspan = A.blk_maxspan[dn.rblk];
+    const int64_t blk_lo = R.blk_off[dn.rblk];
     // the read window is the union of two index ranges (second one only for far-apart SV breakpoints)
     const int64_t nd_ = A.n_dnms;
     const int64_t a_lo = A.win[d], a_hi = A.win[nd_ + d], b_lo = A.win[2 * nd_ + d], b_hi = A.win[3 * nd_ + d];
@@ -430,8 +430,7 @@ chain_kernel(ChainArgs A) {
     if (dn.kind == UNFZ_KIND_SNV || dn.kind == UNFZ_KIND_INDEL) {
         // fetch(chrom, pos-1, pos+1); after a failed fetch the reference retries with (pos, pos+1) (Q24)
         const int64_t flo = (dn.flags & 8) ? (int64_t)dn.pos : (int64_t)dn.pos - 1;
-        const int64_t lo = lb_start(R, blk_lo, blk_hi, flo - maxspan + 1);
-        const int64_t hi = lb_start(R, lo, blk_hi, (int64_t)dn.pos + 1);
+        const int64_t lo = A.seed_win[4 * (int64_t)d], hi = A.seed_win[4 * (int64_t)d + 1];   // from chain_size
         for (int64_t base = lo; base < hi; base += CH_THREADS) {
             const int64_t r = base + tid;
             int hap = 0;
@@ -453,8 +452,7 @@ chain_kernel(ChainArgs A) {
             const double dlo = (double)position - cul;
             const int64_t flo = dlo > 0.0 ? (int64_t)dlo : 0;
             const int64_t fhi = (int64_t)((double)position + cul);
-            const int64_t lo = lb_start(R, blk_lo, blk_hi, flo - maxspan + 1);
-            const int64_t hi = lb_start(R, lo, blk_hi, fhi);
+            const int64_t lo = A.seed_win[4 * (int64_t)d + 2 * wdx], hi = A.seed_win[4 * (int64_t)d + 2 * wdx + 1];
             if (wdx == 1) { e_lo = lo; e_hi = hi; e_flo = flo; e_fhi = fhi; }
             for (int64_t base = lo; base < hi; base += CH_THREADS) {
                 const int64_t r = base + tid;
@@ -510,12 +508,9 @@ chain_kernel(ChainArgs A) {
     if (!A.no_extended) {
         // ------------------------------------------------------------ phase 2: het-site incidences
         // (a) candidate read range of every het site: fetch(chrom, pos, pos+1) as index range
-        for (int i = tid; i < nh; i += CH_THREADS) {
-            const int64_t p = spos[i];
-            const int64_t lo = lb_start(R, blk_lo, blk_hi, p - maxspan + 1);
-            const int64_t hi = lb_start(R, lo, blk_hi, p + 1);
-            site_base[i] = (int32_t)(lo - blk_lo);
-            site_cnt[i] = (int32_t)(hi - lo);
+        for (int i = tid; i < nh; i += CH_THREADS) {          // found by chain_size, no search here
+            site_base[i] = A.site_lo[lbase + i];
+            site_cnt[i] = A.site_n[lbase + i];
         }
         __syncthreads();
         // (b) exclusive scan of the range sizes (warp 0), candidates are flattened site-major
@@ -871,7 +866,8 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
                   UnfzSiteCols sites, UnfzReadCols reads, const UnfzReadSum* __restrict__ rsum,
                   const int32_t* __restrict__ blk_maxspan, const int32_t* __restrict__ het_list,
                   const int32_t* __restrict__ n_het, const uint32_t* __restrict__ cand_list,
-                  const int32_t* __restrict__ n_cand, int32_t* __restrict__ win, int64_t* __restrict__ need) {
+                  const int32_t* __restrict__ n_cand, int32_t* __restrict__ win, int64_t* __restrict__ need,
+                  int32_t* __restrict__ site_lo, int32_t* __restrict__ site_n, int32_t* __restrict__ seed_win) {
     const int lane = threadIdx.x & 31;
     const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_dnms) return;
@@ -905,6 +901,8 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
             else { minB = min(minB, p); maxB = max(maxB, p + 1); }
             const int64_t a = lb_start(reads, blk_lo, blk_hi, p - maxspan + 1);
             const int64_t b = lb_start(reads, a, blk_hi, p + 1);
+            site_lo[lbase + i] = (int32_t)(a - blk_lo);
+            site_n[lbase + i] = (int32_t)(b - a);
             incs += b - a;
         }
         minA = warp_min64(minA); maxA = warp_max64(maxA); minB = warp_min64(minB); maxB = warp_max64(maxB);
@@ -923,6 +921,7 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
             const int64_t flo = wdx ? sb_lo : sa_lo, fhi = wdx ? sb_hi : sa_hi;
             const int64_t a = lb_start(reads, blk_lo, blk_hi, flo - maxspan + 1);
             const int64_t b = lb_start(reads, a, blk_hi, fhi);
+            if (lane == 0) { seed_win[4 * (int64_t)d + 2 * wdx] = (int32_t)a; seed_win[4 * (int64_t)d + 2 * wdx + 1] = (int32_t)b; }
             seeds += 2 * (b - a);
             for (int64_t r = a + lane; r < b; r += 32) {
                 const int64_t ents[2] = {r, (int64_t)reads.hdr[r].mate};
@@ -1064,11 +1063,13 @@ extern "C" int unfz_chain_size(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms
                                const int64_t* seg_pair_off, const UnfzSiteCols* sites, const UnfzReadCols* reads,
                                const UnfzReadSum* rsum, const int32_t* blk_maxspan, const int32_t* het_list,
                                const int32_t* n_het, const uint32_t* cand_list, const int32_t* n_cand,
-                               int32_t* win, int64_t* need, void* stream) {
+                               int32_t* win, int64_t* need, int32_t* site_lo, int32_t* site_n, int32_t* seed_win,
+                               void* stream) {
     (void)segs;
     if (n_dnms <= 0) return 0;
     chain_size_kernel<<<(n_dnms + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-        dnms, n_dnms, seg_pair_off, *sites, *reads, rsum, blk_maxspan, het_list, n_het, cand_list, n_cand, win, need);
+        dnms, n_dnms, seg_pair_off, *sites, *reads, rsum, blk_maxspan, het_list, n_het, cand_list, n_cand, win, need,
+        site_lo, site_n, seed_win);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1078,8 +1079,8 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
                                 const UnfzReadSum* rsum, const int32_t* blk_maxspan, const uint32_t* hits,
                                 const uint32_t* hit_tile_base, int32_t hit_tile_reads, const int32_t* mark_prefix, const int32_t* het_list, const int32_t* n_het,
                                 const uint32_t* cand_list, const int32_t* n_cand, const uint8_t* alleles,
-                                const int32_t* win, const int64_t* off,
-                                const int64_t* h_totals, const UnfzParams* hp, void* scratch, int64_t scratch_bytes,
+                                const int32_t* win, const int32_t* site_lo, const int32_t* site_n, const int32_t* seed_win,
+                                const int64_t* off, const int64_t* h_totals, const UnfzParams* hp, void* scratch, int64_t scratch_bytes,
                                 uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid, UnfzTally* tally,
                                 void* stream) {
     if (n_dnms <= 0) return 0;
@@ -1089,6 +1090,7 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     A.het_list = het_list; A.n_het = n_het; A.cand_list = cand_list; A.n_cand = n_cand; A.alleles = alleles;
     A.win = win; A.off = off; A.split_margin = hp->split_error_margin;
     A.hit_tile_base = hit_tile_base; A.hit_tile_reads = hit_tile_reads;
+    A.site_lo = site_lo; A.site_n = site_n; A.seed_win = seed_win;
     A.readlen = hp->readlen;
     const double bq = hp->min_gt_qual;
     A.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));

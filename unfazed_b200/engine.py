@@ -364,6 +364,10 @@ class Engine:
         e2.add("cls", n_pairs)
         e2.add("het_list", 4 * n_pairs)
         e2.add("cand_list", 4 * n_pairs)
+        if has_reads:
+            e2.add("site_lo", 4 * n_pairs)
+            e2.add("site_n", 4 * n_pairs)
+            e2.add("seed_win", 16 * n)
         z2.add("cand_evid", n_pairs + 8)
         z2.alloc()
         e2.alloc()
@@ -407,7 +411,8 @@ class Engine:
             mark("scan_hits")
             self._check(lib.unfz_chain_size(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
                                             z1.ptr["blk_maxspan"], e2.ptr["het_list"], rp["n_het"], e2.ptr["cand_list"],
-                                            rp["n_cand"], rp["win"], z1.ptr["need"], s), "chain_size")
+                                            rp["n_cand"], rp["win"], z1.ptr["need"], e2.ptr["site_lo"], e2.ptr["site_n"],
+                                            e2.ptr["seed_win"], s), "chain_size")
             self._check(lib.unfz_exclusive_scan_rows_i64(ctx, z1.ptr["need"], off_ptr, 6, n, s), "scan(need)")
             launches += 2
             h_all = z1.view["off"].cpu().numpy().view(np.int64)                          # host sync 2
@@ -436,7 +441,8 @@ class Engine:
             self._check(lib.unfz_chain_tally(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
                                              z1.ptr["blk_maxspan"], e3.ptr["hits"], e1.ptr["tile_base"], tile_reads, z1.ptr["mark_prefix"],
                                              e2.ptr["het_list"],
-                                             rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], p_all, rp["win"], off_ptr,
+                                             rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], p_all, rp["win"], e2.ptr["site_lo"], e2.ptr["site_n"],
+                                             e2.ptr["seed_win"], off_ptr,
                                              totals.ctypes.data, C.byref(params), e3.ptr["scratch"], nbytes,
                                              z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"], s),
                         "chain_tally")

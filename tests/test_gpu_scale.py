@@ -121,3 +121,41 @@ def test_no_extended_labels_are_a_subset(big):
         for name, hap in seeds.items():
             assert full.get(name) == hap
         assert len(full) >= len(seeds)
+
+
+def test_more_het_sites_than_the_shared_memory_budget(engine):
+    """> 256 het sites per DNM: the chain kernel's per-site state falls back to global scratch."""
+    n = _compare(engine, SynthConfig(dnms_per_trio=3, seed=502, search_dist=30000, site_spacing=100, coverage=16.0),
+                 dict(search_dist=30000))
+    assert n >= 2
+
+
+def test_long_reads_take_the_chunked_scan_kernel(engine):
+    """40 kb reads do not fit a TMA stage: read_scan falls back to the chunked kernel; read summaries
+    (reference_end, goodread, filters) and records must still match the oracle."""
+    from unfazed_b200.phaser import BatchPhaser
+    cfg = SynthConfig(dnms_per_trio=4, seed=501, readlen=40000, frag_mean=90000.0, frag_sd=3000.0, search_dist=3000,
+                      coverage=40.0, read_margin=100000, noise=False)
+    ds = make_dataset(cfg)
+    # sprinkle low qualities / bad flags so that the filters have something to reject
+    rng = np.random.default_rng(5)
+    q = ds.reads.qual
+    for r in range(0, ds.reads.n_reads, 7):
+        q0 = ds.reads.qoff(r)
+        q[q0 + rng.integers(0, 40000, size=int(rng.integers(0, 25)))] = 5
+    ds.reads.hdr["mapq"][::11] = 0
+    params = dict(readlen=40001)
+    want, _ = run_port(ds, **params)
+    bp = BatchPhaser(engine, ds.sites, ds.reads, ds.pedigrees)
+    res, layout = bp.run(ds.dnms, [], **gpu_kwargs(**params))
+    got = bp.records(res, layout)
+    assert set(got) == set(want)
+    for k in want:
+        assert norm_record(got[k]) == norm_record(want[k]), k
+    rs = res.read_summaries()
+    bam = port.Bam(ds.reads, 0)
+    p = port.Params(readlen=40001)
+    assert np.array_equal(rs["end"], ds.reads.ref_ends().astype(np.int32))
+    for r in range(0, ds.reads.n_reads, 3):
+        assert bool(rs["flags"][r] & L.RS_GOOD_CONC) == port.goodread(bam, r, p), r
+        assert bool(rs["flags"][r] & L.RS_GOOD_DISC) == port.goodread(bam, r, p, True), r

@@ -68,6 +68,7 @@ KIND_SKIP, KIND_SNV, KIND_INDEL, KIND_SV = 0, 1, 2, 3
 ORIGIN_NONE, ORIGIN_DAD, ORIGIN_MOM, ORIGIN_BOTH = 0, 1, 2, 3
 EV_READBACKED, EV_ALLELE_BALANCE, EV_AMBIG_READBACKED, EV_AMBIG_ALLELE_BAL, EV_AMBIG_BOTH, EV_SEX_CHROM = 1, 2, 4, 8, 16, 32
 DNM_AUTOPHASE, DNM_AUTOPHASE_Y, DNM_SV_QUIRK, DNM_FALLBACK_FETCH = 1, 2, 4, 8
+RS_GOOD_CONC, RS_GOOD_DISC, RS_NONE_OK, RS_EXT_OK, RS_INS_OK, RS_HAS_MATE = 1, 2, 4, 8, 16, 32
 
 # every symbol the header declares: (name, restype, argtypes)
 _P = c_void_p

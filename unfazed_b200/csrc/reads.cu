@@ -558,8 +558,9 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
     for (; row < b && written < s.cnt; ++row) {
         const int32_t p = __ldg(sites.pos + row);
         if (p >= s.end) break;
-        if (!__ldg(row_mark + row)) continue;
-        const int k = __ldg(mark_prefix + row) - s.fmark;
+        const int mp0 = __ldg(mark_prefix + row);
+        if (__ldg(mark_prefix + row + 1) == mp0) continue;      // not a marked row (same sectors as mp0: no row_mark load)
+        const int k = mp0 - s.fmark;
         uint32_t word = 0;
         const int q = cigar_qpos(cg, h.n_cigar, h.start, p);
         if (q >= 0 && q < 0xffff) {

@@ -91,7 +91,8 @@ __device__ __forceinline__ uint8_t classify_pair(const GtThr* __restrict__ thr, 
         const bool valid = (g <= 3) & (t.flags & 1);
         tot[m] = (int32_t)((uint32_t)rd[m] + (uint32_t)ad[m]);             // numpy int32 add wraps
         const bool pre = valid & !(gq[m] < min_gq_f) & (tot[m] >= min_depth);
-        const bool fv = (ad[m] >= 0) & (ad[m] <= tot[m]) & (tot[m] > 0) & (tot[m] < (1 << 24));
+        // 0 <= ad <= tot, 0 < tot < 2^24 as two unsigned compares
+        const bool fv = ((uint32_t)ad[m] <= (uint32_t)tot[m]) & ((uint32_t)(tot[m] - 1) < (uint32_t)((1 << 24) - 1));
         const float q = __fdividef((float)ad[m], (float)tot[m]);           // <= 2 ulp; the margin is 1e-6
         const bool is0 = ad[m] == 0, is1 = ad[m] == tot[m];               // exactly 0.0 / 1.0 (very common)
         const bool in = is0 ? ((t.flags & 2) != 0) : (is1 ? ((t.flags & 4) != 0) : ((q >= t.f.x) & (q <= t.f.y)));
@@ -145,8 +146,7 @@ classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const in
                 const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs, ClsParams P,
                 uint8_t* __restrict__ out) {
     __shared__ int32_t s_off[CLS_SMEM_SEGS + 1];     // pair offset of the segment relative to the tile
-    __shared__ int32_t s_row[CLS_SMEM_SEGS], s_mult[CLS_SMEM_SEGS], s_exlo[CLS_SMEM_SEGS], s_exhi[CLS_SMEM_SEGS];
-    __shared__ uint8_t s_mode[CLS_SMEM_SEGS];
+    __shared__ int4 s_seg[CLS_SMEM_SEGS];            // row_lo, mult | mode << 24, excl_lo, excl_hi
     __shared__ int32_t s_map[CLS_TILE];
     __shared__ int32_t s_warp[CLS_THREADS / 32];
     __shared__ GtThr s_thr[4];
@@ -193,11 +193,7 @@ classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const in
                 s_off[i] = (int32_t)rel;
                 if (sidx < n_segs && rel < npair) {
                     const UnfzSegIn sg = segs[sidx];
-                    s_row[i] = seg_row_lo[sidx];
-                    s_mult[i] = sg.mult;
-                    s_exlo[i] = sg.excl_lo;
-                    s_exhi[i] = sg.excl_hi;
-                    s_mode[i] = (uint8_t)sg.mode;
+                    s_seg[i] = make_int4(seg_row_lo[sidx], (sg.mult & 0xffffff) | (sg.mode << 24), sg.excl_lo, sg.excl_hi);
                 }
             }
             if (threadIdx.x == 0 && round == CLS_SMEM_SEGS / 128 - 1) s_off[CLS_SMEM_SEGS] = 1 << 30;
@@ -240,7 +236,8 @@ classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const in
             int32_t row_lo, mult, exlo, exhi, mode, within;
             if (staged) {
                 const int lo = s_map[q];
-                row_lo = s_row[lo]; mult = s_mult[lo]; exlo = s_exlo[lo]; exhi = s_exhi[lo]; mode = s_mode[lo];
+                const int4 sg = s_seg[lo];
+                row_lo = sg.x; mult = sg.y & 0xffffff; mode = (uint32_t)sg.y >> 24; exlo = sg.z; exhi = sg.w;
                 within = q - s_off[lo];
             } else {
                 const int sidx = (int)(upper_bound_dev(seg_pair_off, (int64_t)seg0, (int64_t)n_segs + 1, p0 + q) - 1);

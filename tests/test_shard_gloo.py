@@ -32,7 +32,48 @@ def test_every_dnm_lands_on_its_kids_rank():
                 assert not kids & {d["kid"] for d in other}
 
 
-def _worker(rank, world, port_no, out_path):
+def test_single_heavy_family_is_cut_into_genomic_slices():
+    # one trio with 90 DNMs next to two light ones, 4 GPUs: the heavy family must spread out, in
+    # contiguous (chrom, start) slices; light kids stay whole
+    dnms = [{"kid": "big", "chrom": "chr%d" % (1 + i % 3), "start": 1000 * (90 - i)} for i in range(90)]
+    dnms += [{"kid": "s1", "chrom": "1", "start": i} for i in range(5)]
+    dnms += [{"kid": "s2", "chrom": "X", "start": i} for i in range(5)]
+    shards = shard_dnms(dnms, 4)
+    assert sorted(id(d) for s in shards for d in s) == sorted(id(d) for d in dnms)
+    sizes = [len(s) for s in shards]
+    assert max(sizes) <= 35 and min(sizes) >= 15
+    for kid in ("s1", "s2"):
+        assert sum(1 for s in shards if any(d["kid"] == kid for d in s)) == 1
+    spans = []
+    for s in shards:
+        big = sorted((int(d["chrom"][3:]), d["start"]) for d in s if d["kid"] == "big")
+        if big:
+            spans.append((big[0], big[-1]))
+    spans.sort()
+    assert len(spans) >= 3
+    for a, b in zip(spans, spans[1:]):
+        assert a[1] < b[0]                      # slices do not interleave
+    # opting out keeps the family on one GPU
+    whole = shard_dnms(dnms, 4, split_heavy=False)
+    assert sum(1 for s in whole if any(d["kid"] == "big" for d in s)) == 1
+    assert shard_dnms(dnms, 4) == shards        # deterministic
+
+
+def test_cross_kid_coupling_detector():
+    """Q12: in find_many CNV mode one kid's KeyError empties the chromosome for everybody; only a
+    kid that would not trip it alone makes a by-kid shard differ from the single-process run."""
+    from unfazed_b200.shard import cross_kid_coupling
+    ped = {k: {"dad": "d", "mom": "m", "sex": 2} for k in ("k1", "k2")}
+    sv = lambda k, c, s, e: {"kid": k, "chrom": c, "start": s, "end": e, "vartype": "DEL"}
+    assert not cross_kid_coupling([sv("k1", "1", 100, 500), sv("k2", "1", 900, 1500)], ped, "38", 2)
+    assert cross_kid_coupling([sv("k1", "1", 100, 500), sv("k2", "1", 900, 902)], ped, "38", 2)
+    assert not cross_kid_coupling([sv("k1", "1", 100, 500), sv("k2", "1", 900, 902)], ped, "38", 3)   # per-DNM find
+    assert not cross_kid_coupling([sv("k1", "1", 100, 500), sv("k2", "2", 900, 902)], ped, "38", 2)
+    # a DNM of the same kid starting at the end location defuses the KeyError
+    assert not cross_kid_coupling([sv("k1", "1", 100, 500), sv("k1", "1", 500, 502), sv("k2", "1", 900, 902)], ped, "38", 2)
+
+
+def _worker(rank, world, port_no, out_path, n_trios, per_trio):
     import pickle
     import torch.distributed as dist
     from oracle import port
@@ -40,12 +81,15 @@ def _worker(rank, world, port_no, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    ds = make_dataset(SynthConfig(n_trios=3, dnms_per_trio=4, seed=77, coverage=16.0))
+    ds = make_dataset(SynthConfig(n_trios=n_trios, dnms_per_trio=per_trio, seed=77, coverage=16.0))
 
     def phase_fn(dnms):
         ph = port.Phaser(ds.sites, ds.reads, ds.pedigrees, port.Params())
         return ph.phase(copy.deepcopy(dnms))
 
+    if n_trios == 1:                            # the family is split: both ranks must get work
+        from unfazed_b200.shard import shard_dnms as _sd
+        assert all(len(x) > 0 for x in _sd(ds.dnms, world))
     recs = phase_sharded(phase_fn, ds.dnms)
     if rank == 0:
         with open(out_path, "wb") as f:
@@ -56,7 +100,8 @@ def _worker(rank, world, port_no, out_path):
     dist.destroy_process_group()
 
 
-def test_sharded_equals_single_process(tmp_path):
+@pytest.mark.parametrize("n_trios,per_trio", [(3, 4), (1, 10)])
+def test_sharded_equals_single_process(tmp_path, n_trios, per_trio):
     import pickle
     from oracle import port
     s = socket.socket()
@@ -64,9 +109,9 @@ def test_sharded_equals_single_process(tmp_path):
     port_no = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "recs.pkl")
-    mp.spawn(_worker, args=(2, port_no, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port_no, out, n_trios, per_trio), nprocs=2, join=True)
     got = pickle.load(open(out, "rb"))
-    ds = make_dataset(SynthConfig(n_trios=3, dnms_per_trio=4, seed=77, coverage=16.0))
+    ds = make_dataset(SynthConfig(n_trios=n_trios, dnms_per_trio=per_trio, seed=77, coverage=16.0))
     want = port.Phaser(ds.sites, ds.reads, ds.pedigrees, port.Params()).phase(copy.deepcopy(ds.dnms))
     assert set(got) == set(want) and len(want) > 0
     for k in want:

@@ -236,6 +236,48 @@ def write_vcf_output(in_vcf_name, read_records, include_ambiguous, verbose, outf
         writer.write_record(v)
 
 
+def _phase_multi_gpu(snvs, svs, common):
+    """One process per GPU (torchrun): DNMs shard by kid, every rank phases its shard on its own
+    device and rank 0 gathers the records -- no collective on the data path.  The choice between
+    ``find`` and ``find_many`` depends on the number of DNMs of the WHOLE run
+    (informative_site_finder.py:190), so it is taken here and handed to the ranks as an effective
+    ``multiread_proc_min`` of 0 or "never"."""
+    import torch
+    import torch.distributed as dist
+    from . import informative_site_finder as isf
+    from .shard import cross_kid_coupling, phase_sharded
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group("cpu:gloo,cuda:nccl")
+    from .engine import Engine
+    isf._engine = Engine(local_rank)
+    pedigrees, build, mpm = common[1], common[4], common[6]
+
+    def with_mpm(n_total):
+        c = list(common)
+        c[6] = 0 if n_total >= mpm else 2 ** 31 - 1
+        return c
+
+    def phase_fn(mine):
+        my_svs = [d for d in mine if d["vartype"].upper() in SV_TYPES]
+        my_snvs = [d for d in mine if d["vartype"].upper() in SNV_TYPES]
+        out = phase_snvs(my_snvs, *with_mpm(len(snvs))) if my_snvs else {}
+        out.update(phase_svs(my_svs, *with_mpm(len(svs))) if my_svs else {})
+        return out
+
+    if cross_kid_coupling(svs, pedigrees, build, mpm):
+        # one kid's events change another kid's windows (Q12): keep the run on one GPU to stay exact
+        if dist.get_rank() != 0:
+            dist.barrier()
+            return None
+        out = phase_fn(svs + snvs)
+        dist.barrier()
+        return out
+    # a family is only cut into slices when its DNMs cannot interact (per-DNM `find` windows)
+    return phase_sharded(phase_fn, svs + snvs, split_heavy=len(snvs) < mpm and len(svs) < mpm)
+
+
 def unfazed(args):
     global QUIET_MODE
     QUIET_MODE = args.quiet
@@ -282,9 +324,14 @@ def unfazed(args):
               args.quiet, args.ab_homref, args.ab_homalt, args.ab_het, args.min_gt_qual, args.min_depth,
               args.search_dist, args.insert_size_max_sample, args.stdevs, args.min_map_qual, args.readlen,
               args.split_error_margin)
-    phased_svs = phase_svs(svs, *common) if svs else {}
-    phased = phase_snvs(snvs, *common) if snvs else {}
-    phased.update(phased_svs)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        phased = _phase_multi_gpu(snvs, svs, common)
+        if phased is None:
+            return                                  # ranks > 0 hold no output
+    else:
+        phased_svs = phase_svs(svs, *common) if svs else {}
+        phased = phase_snvs(snvs, *common) if snvs else {}
+        phased.update(phased_svs)
     if output_type == "vcf":
         write_vcf_output(args.dnms, phased, args.include_ambiguous, args.verbose, args.outfile, args.evidence_min_ratio)
     else:

@@ -100,7 +100,6 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
     __shared__ int64_t s_qa, s_qb, s_row_base, s_row_end;
     __shared__ int32_t s_rb0;
     __shared__ int32_t s_maxspan;
-    __shared__ int32_t s_wsum[RS_THREADS / 32];
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -210,19 +209,15 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
             cnt = c > 0xffff ? 0xffff : c;
         }
 
-        uint32_t hoff = 0;                       // offset inside the tile; see the pipelined kernel
+        uint32_t hoff = 0;                       // offset inside the 32-read hit tile (see the warp-specialised kernel)
         {
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
             int x = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (lane == 31) s_wsum[warp] = x;
-            __syncthreads();
-            int basew = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < RS_THREADS / 32; ++w) { if (w < warp) basew += s_wsum[w]; total += s_wsum[w]; }
-            hoff = (uint32_t)(basew + x - cnt);
-            if (threadIdx.x == 0) tile_tot[tile] = (uint32_t)total;
+            hoff = (uint32_t)(x - cnt);
+            const int64_t rw = r0 + (threadIdx.x & ~31);
+            if (lane == 31 && rw < n) tile_tot[rw >> 5] = (uint32_t)x;
         }
         // ---- low-quality bases out of the staged span ---------------------------------------
         int low = 0;
@@ -267,14 +262,354 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
 
 
 // ------------------------------------------------------------------------------------------------
-// K2, pipelined variant: used when a whole tile's quality span fits one stage
-// (tile_reads * max l_seq <= RS_STAGE - 32).
-//  * every CTA owns a CONTIGUOUS range of tiles, so the site-row window and the read block are
-//    carried from tile to tile instead of being re-searched (one binary search per CTA);
-//  * two quality stages per CTA: the TMA bulk copy of tile j+1 is issued at the top of iteration j;
-//  * headers are prefetched two tiles ahead, so the spans TMA needs are already in shared memory.
+// K2, streaming variant (used when the quality bytes of 32 reads fit a slice): one independent
+// software pipeline PER WARP, no CTA-wide synchronisation at all.
+//
+// Measured on B200 (profiles/README.md, round 1d): a single asynchronous copy stream -- one TMA bulk
+// copy or the LDGSTS copies of one warp -- moves about 7 KB/us, so a CTA-wide double buffer filled by
+// one producer tops out near 60 % of HBM bandwidth however the tiles are sized (the consumers wait
+// for the fill, the producer waits for the consumers).  What saturates HBM is MANY concurrent
+// streams, so here every warp is its own stream:
+//  * a warp owns a contiguous range of 32-read tiles ("hit tiles") and two private slices of shared
+//    memory; while it works on tile T out of one slice, the quality bytes and CIGAR words of tile
+//    T+1 -- each one contiguous span, because reads are stored in file order -- are in flight into
+//    the other slice (cp.async 16-byte chunks, one commit group per tile), and the headers of tile
+//    T+2 are in flight into registers;
+//  * the site rows a tile can overlap are a window of 64 positions carried from tile to tile (reads
+//    are sorted by start): it advances 32 rows at a time out of a register prefetched one step
+//    ahead, so the steady state issues no dependent global load for it.  When a tile runs into the
+//    next read block that block's window is opened next to it and promoted when the tiles get there;
+//  * per read: CIGAR walk out of shared memory, branch-free search of the window, two mark-prefix
+//    gathers (L2), low-quality count with 4-byte SIMD compares + DP4A out of shared memory;
+//  * hit slots are numbered per tile: one warp scan, one total per tile, no cross-warp scan.
 // ------------------------------------------------------------------------------------------------
-constexpr int RS_STAGE = 36 * 1024;
+constexpr int WP_WARPS = 7;                               // warps per CTA (3 CTAs per SM at 150-base reads)
+constexpr int WP_THREADS = WP_WARPS * 32;
+constexpr int WP_CIGW = 64;                               // staged CIGAR words per tile
+constexpr int WP_SPOS = 64;                               // site positions per window
+constexpr int WP_FIXED = 2 * WP_CIGW * 4 + 2 * WP_SPOS * 4;   // per warp, next to the two quality slices
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+// predicated 16-byte copy at a compile-time offset from both bases (no address arithmetic per chunk)
+template <int OFF>
+__device__ __forceinline__ void cp_async16_at(uint32_t dst_smem, const void* src, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+                 "@p cp.async.cg.shared.global [%0 + %3], [%1 + %3], 16;\n\t}"
+                 ::"r"(dst_smem), "l"(src), "r"((int)pred), "n"(OFF) : "memory");
+}
+template <int I, int N>
+struct CpChunks {
+    static __device__ __forceinline__ void run(uint32_t dst, const uint8_t* src, uint32_t o, uint32_t bytes) {
+        cp_async16_at<I * 512>(dst, src, o + I * 512u < bytes);
+        CpChunks<I + 1, N>::run(dst, src, o, bytes);
+    }
+};
+template <int N>
+struct CpChunks<N, N> {
+    static __device__ __forceinline__ void run(uint32_t, const uint8_t*, uint32_t, uint32_t) {}
+};
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// reference_end, query bases without a reference position and non-M/= operations of one CIGAR
+template <typename Ptr>
+__device__ __forceinline__ void cigar_summary(Ptr cg, int n_cigar, int32_t& end, int& none_cnt, int& non_m) {
+    for (int k = 0; k < n_cigar; ++k) {
+        const uint32_t w = cg[k];
+        const uint32_t op = w & 15u, ln = w >> 4;
+        if ((0x18du >> op) & 1u) end += (int32_t)ln;          // M D N = X
+        if ((0x012u >> op) & 1u) none_cnt += (int)ln;         // I S
+        non_m += (int)((0xff7eu >> op) & 1u);                 // everything but M and =
+    }
+}
+
+// first index in [lo, hi) with a[i] >= v, searched by a whole warp: 32 probes per round trip
+__device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ a, int64_t lo, int64_t hi, int32_t v, int lane) {
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 32) / 33;
+        const int64_t i = lo + (int64_t)(lane + 1) * step - 1;
+        const bool lt = i < hi && __ldg(a + i) < v;
+        const int k = __popc(__ballot_sync(0xffffffffu, lt));      // probes are monotone
+        const int64_t nhi = k < 32 ? min(hi, lo + (int64_t)(k + 1) * step - 1) : hi;
+        lo += (int64_t)k * step;
+        hi = nhi;
+    }
+    const bool lt = lo + lane < hi && __ldg(a + lo + lane) < v;
+    return lo + __popc(__ballot_sync(0xffffffffu, lt));
+}
+
+struct WpSpan {               // where the staged spans of a tile start, and whether they were staged
+    uint32_t qa_lo, ca;
+    bool q_ok, cig_ok;
+};
+
+__global__ void __launch_bounds__(WP_THREADS, 3)
+read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
+                      int qslice, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
+                      int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* my = smem + warp * (2 * qslice + WP_FIXED);
+    uint32_t* cigbuf = reinterpret_cast<uint32_t*>(my + 2 * qslice);
+    int32_t* spos = reinterpret_cast<int32_t*>(my + 2 * qslice + 2 * WP_CIGW * 4);
+
+    // read and row indices fit 32 bits (mate / row_lb are int32 in the ABI)
+    const int n = (int)reads.n_reads;
+    const int n_tiles = (n + 31) >> 5;
+    const int n_warps = (int)gridDim.x * WP_WARPS;
+    const int tpw = (n_tiles + n_warps - 1) / n_warps;
+    const int t0 = ((int)blockIdx.x * WP_WARPS + warp) * tpw;
+    const int t1 = min(t0 + tpw, n_tiles);
+    if (t0 >= t1) return;
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t minq = (uint32_t)P.min_bq;
+
+    auto load_hdr = [&](int T, uint4& a, uint4& b) {
+        a = make_uint4(0, 0, 0, 0);
+        b = a;
+        const int r = (T << 5) + lane;
+        if (T < t1 && r < n) {
+            const uint4* q = reinterpret_cast<const uint4*>(reads.hdr + r);
+            a = __ldg(q);
+            b = __ldg(q + 1);
+        }
+    };
+    // start the copies of tile T (headers a, b) into slice k; exactly one commit group per call
+    auto issue_fill = [&](int T, const uint4& a, const uint4& b, int k) -> WpSpan {
+        WpSpan sp;
+        sp.qa_lo = 0; sp.ca = 0; sp.q_ok = false; sp.cig_ok = false;
+        if (T < t1) {
+            const int nl = min(32, n - (T << 5));
+            const long long q_self = (long long)b.x | ((long long)((b.w >> 16) & 0xffu) << 32);
+            const long long f_q = __shfl_sync(FULL, q_self, 0);
+            const long long l_q = __shfl_sync(FULL, q_self + (long long)(int32_t)b.y, nl - 1);
+            const uint32_t f_c = __shfl_sync(FULL, a.w, 0);
+            const uint32_t l_c = __shfl_sync(FULL, a.w + (b.z >> 16), nl - 1);
+            const long long qa = f_q & ~15ll;
+            const long long qspan = l_q > qa ? ((l_q - qa + 15) & ~15ll) : 0;
+            const uint32_t ca = f_c & ~3u;
+            const long long cspan = l_c > ca ? (((long long)l_c - ca + 3) & ~3ll) : 0;
+            sp.q_ok = qspan <= qslice;
+            sp.cig_ok = cspan <= WP_CIGW && (long long)ca + cspan <= reads.n_cigar;
+            sp.qa_lo = (uint32_t)qa;
+            sp.ca = ca;
+            const uint32_t o = lane * 16u;
+            if (sp.q_ok) {
+                // lane-strided 16-byte chunks: the first 10 (5 KB: 32 reads of up to 152 bases) are unrolled
+                // with immediate offsets, longer slices finish in a loop
+                const uint32_t dst = smem_u32(my + k * qslice) + o;
+                const uint8_t* src = reads.qual + qa + o;
+                CpChunks<0, 10>::run(dst, src, o, (uint32_t)qspan);
+                for (uint32_t x = o + 5120u; x < (uint32_t)qspan; x += 512u) cp_async16(my + k * qslice + x, reads.qual + qa + x);
+            }
+            if (sp.cig_ok)                                      // <= 256 bytes: one chunk per lane
+                cp_async16_at<0>(smem_u32(cigbuf + k * WP_CIGW) + o, reinterpret_cast<const uint8_t*>(reads.cigar + ca) + o,
+                                 o < (uint32_t)cspan * 4u);
+        }
+        cp_async_commit();
+        return sp;
+    };
+
+    // ---- carried state: the read block of the current tile and its window of site rows -------------
+    int rb0 = 0, sblk = -1;
+    int blk_end = -1, row_base = 0, row_end = 0;
+    long long cul = -1;                                           // floor(concordant_upper_len): |insert| is an integer
+    // The window lives in shared memory only: registers written by global loads would make every hot-path
+    // instruction that reads them wait on the (statically assigned) scoreboard of whatever load is in flight.
+    int32_t w2 = 0x7fffffff;                                     // rows row_base + 64 + lane, read only when the window advances
+    int cur = 0;                                                 // first window entry >= the tile's first start (uniform)
+    int bmax = 0;                                                // longest span seen in the current block
+    int rb1 = -1, sblk1 = -1;                                    // the next block, opened when a tile runs into it
+    int blk_end1 = 0, row_base1 = 0, row_end1 = 0;
+    long long cul1 = -1;
+    // (double)ins <= c for an integer ins >= 0  <=>  ins <= floor(c); NaN and negative bounds admit nothing
+    auto cul_floor = [](double c) -> long long { return c >= 0.0 ? (c < 9.0e18 ? (long long)floor(c) : 0x7fffffffffffffffll) : -1; };
+    auto row_at = [&](int i, int rend) -> int32_t { return i < rend ? __ldg(sites.pos + i) : 0x7fffffff; };
+    auto open_block = [&](int rb, int32_t first_start, int& sb, int& bend, long long& c, int& rbase, int& rend) {
+        bend = (int)reads.blk_off[rb + 1];
+        sb = reads.blk_sblk[rb];
+        c = cul_floor(reads.blk_cul[rb]);
+        rbase = rend = 0;
+        if (sb >= 0) {
+            rend = (int)sites.blk_off[sb + 1];
+            rbase = (int)warp_lower_bound(sites.pos, sites.blk_off[sb], rend, first_start, lane);
+        }
+    };
+
+    uint4 hAa, hAb, hBa, hBb, hCa, hCb;
+    load_hdr(t0, hAa, hAb);
+    load_hdr(t0 + 1, hBa, hBb);
+    WpSpan spA = issue_fill(t0, hAa, hAb, 0), spB = spA;
+
+    for (int T = t0; T < t1; ++T) {
+        const int k = (T - t0) & 1;
+        spB = issue_fill(T + 1, hBa, hBb, k ^ 1);              // in flight while this tile is processed
+        load_hdr(T + 2, hCa, hCb);                             // consumed by the next iteration's fill
+
+        const int r0 = T << 5;
+        const int nl = min(32, n - r0);
+        const int last = r0 + nl - 1;
+        const int32_t f_start = (int32_t)__shfl_sync(FULL, hAa.x, 0);
+        if (r0 >= blk_end) {                                   // the tile starts in a new read block
+            if (blk_end < 0) rb0 = (int)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r0) - 1);
+            else do { ++rb0; } while (r0 >= reads.blk_off[rb0 + 1]);
+            if (rb0 == rb1) {                                  // opened while the previous tile ran into it
+                sblk = sblk1; blk_end = blk_end1; cul = cul1; row_base = row_base1; row_end = row_end1;
+                const int32_t a = spos[WP_SPOS + lane], b = spos[WP_SPOS + 32 + lane];
+                spos[lane] = a;
+                spos[32 + lane] = b;
+            } else {
+                open_block(rb0, f_start, sblk, blk_end, cul, row_base, row_end);
+                spos[lane] = row_at(row_base + lane, row_end);
+                spos[32 + lane] = row_at(row_base + 32 + lane, row_end);
+            }
+            w2 = row_at(row_base + 64 + lane, row_end);
+            cur = 0;
+            bmax = 0;
+            __syncwarp();
+        }
+        // reads are sorted by start: rows before the tile's first start are behind every read from here on
+        while (cur < WP_SPOS && spos[cur] < f_start) ++cur;
+        if (cur >= 32) {                                       // advance the window by 32 rows (or re-seat it after a gap)
+            if (cur == WP_SPOS) {
+                row_base = (int)warp_lower_bound(sites.pos, row_base + WP_SPOS, row_end, f_start, lane);
+                spos[lane] = row_at(row_base + lane, row_end);
+                spos[32 + lane] = row_at(row_base + 32 + lane, row_end);
+                cur = 0;
+            } else {
+                const int32_t b = spos[32 + lane];
+                spos[lane] = b;
+                spos[32 + lane] = w2;
+                row_base += 32;
+                cur -= 32;
+            }
+            w2 = row_at(row_base + 64 + lane, row_end);        // consumed at the next advance
+            __syncwarp();
+        }
+        const bool two = last >= blk_end;                      // the tile runs into the next read block
+        if (two && rb1 != rb0 + 1) {
+            rb1 = rb0 + 1;
+            const int32_t first1 = __ldg(&reads.hdr[blk_end].start);
+            open_block(rb1, first1, sblk1, blk_end1, cul1, row_base1, row_end1);
+            spos[WP_SPOS + lane] = row_at(row_base1 + lane, row_end1);
+            spos[WP_SPOS + 32 + lane] = row_at(row_base1 + 32 + lane, row_end1);
+        }
+
+        cp_async_wait<1>();                                    // this tile's spans have landed (all but the newest group)
+        __syncwarp();
+
+        // ---- one read per lane ---------------------------------------------------------------------
+        const bool live = lane < nl;
+        const int r = r0 + lane;
+        const int32_t start = (int32_t)hAa.x, tlen = (int32_t)hAa.y, mate = (int32_t)hAa.z;
+        const int l_seq = (int)hAb.y, n_cigar = (int)(hAb.z >> 16);
+        const uint32_t f = hAb.z & 0xffffu, mapq = hAb.w & 0xffu, aux = (hAb.w >> 8) & 0xffu;
+
+        // which staged block the read belongs to: 0 the tile's, 1 the next one, 2 neither (tiny blocks: rare)
+        int which = 0;
+        if (two && live && r >= blk_end) which = r < blk_end1 ? 1 : 2;
+        int rb = rb0 + which, sb = which ? sblk1 : sblk;
+        long long my_cul = which ? cul1 : cul;
+        const int rbase = which ? row_base1 : row_base, rend = which ? row_end1 : row_end;
+        if (which == 2) {
+            rb = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb0, (int64_t)reads.n_blocks + 1, r) - 1);
+            sb = reads.blk_sblk[rb];
+            my_cul = cul_floor(reads.blk_cul[rb]);
+        }
+
+        int32_t end = start;
+        uint32_t flags = 0;
+        if (live) {
+            int none_cnt = 0, non_m = 0;
+            if (spA.cig_ok) cigar_summary(cigbuf + k * WP_CIGW + (hAa.w - spA.ca), n_cigar, end, none_cnt, non_m);
+            else cigar_summary(reads.cigar + hAa.w, n_cigar, end, none_cnt, non_m);
+            const bool base_ok = !(f & (0x200u | 0x4u | 0x400u | 0x100u | 0x800u | 0x8u)) &&
+                                 (int)mapq >= P.min_mapq && (aux & 1u);
+            if (base_ok) flags |= UNFZ_RS_GOOD_DISC;
+            if (none_cnt <= 5) flags |= UNFZ_RS_NONE_OK;
+            if (non_m <= 5) flags |= UNFZ_RS_EXT_OK;
+            long long ins = (long long)tlen - 2ll * P.readlen;
+            if (ins < 0) ins = -ins;
+            if (ins <= my_cul) flags |= UNFZ_RS_INS_OK;
+            if ((f & 1u) && !(f & 8u) && mate >= 0) flags |= UNFZ_RS_HAS_MATE;
+        }
+        // longest reference span per read block (bounds the fetch windows of the chaining kernels)
+        {
+            const int span = live ? end - start : 0;
+            const int m0 = __reduce_max_sync(FULL, which == 0 ? span : 0);
+            if (m0 > bmax) {
+                bmax = m0;
+                if (lane == 0) atomicMax(blk_maxspan + rb0, m0);
+            }
+            if (two) {
+                const int m1 = __reduce_max_sync(FULL, which == 1 ? span : 0);
+                if (lane == 0 && m1 > 0) atomicMax(blk_maxspan + rb0 + 1, m1);
+                if (which == 2 && span > 0) atomicMax(blk_maxspan + rb, span);
+            }
+        }
+
+        // ---- marked-site overlap: rows with start <= pos < end ----------------------------------------
+        int32_t fmark = 0, cnt = 0;
+        int lbs = 0, lbe = 0;
+        if (live && sb >= 0) {
+            if (which < 2) {
+                // the tile's reads start within a row or two of the cursor and span a row or two: probe forward
+                const int32_t* win = spos + which * WP_SPOS;
+                int lo = which ? 0 : cur;
+                while (lo < WP_SPOS && win[lo] < start) ++lo;
+                int lo2 = lo;
+                while (lo2 < WP_SPOS && win[lo2] < end) ++lo2;
+                lbs = rbase + lo;
+                lbe = rbase + lo2;
+                if (lo2 == WP_SPOS) {                          // ran off the staged window: finish in global memory
+                    if (lo == WP_SPOS) lbs = (int)lower_bound_dev(sites.pos, rbase + WP_SPOS - 1, rend, start);
+                    lbe = (int)lower_bound_dev(sites.pos, max(lbs, rbase + WP_SPOS - 1), rend, end);
+                }
+            } else {
+                const int64_t a = sites.blk_off[sb], b = sites.blk_off[sb + 1];
+                lbs = (int)lower_bound_dev(sites.pos, a, b, start);
+                lbe = (int)lower_bound_dev(sites.pos, lbs, b, end);
+            }
+            fmark = __ldg(mark_prefix + lbs);
+            const int32_t c = __ldg(mark_prefix + lbe) - fmark;
+            cnt = c > 0xffff ? 0xffff : c;
+        }
+
+        // ---- goodread: low-quality bases out of the staged span ---------------------------------------
+        int low = 0;
+        if (live && l_seq > 0) {
+            if (spA.q_ok) {
+                const int off = (int)(hAb.x - spA.qa_lo);
+                low = count_low_quals(my + k * qslice, off, off + l_seq, minq);
+            } else {
+                const int64_t q0 = (int64_t)hAb.x | ((int64_t)((hAb.w >> 16) & 0xffu) << 32);
+                const int off = (int)(q0 & 15);
+                low = count_low_quals(reads.qual + (q0 - off), off, off + l_seq, minq);
+            }
+        }
+        if (live && (flags & UNFZ_RS_GOOD_DISC) && low <= 10 && n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
+
+        // ---- hit slots: offset inside the tile + the tile's total -----------------------------------------
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) tile_tot[T] = (uint32_t)incl;
+        if (live) {
+            UnfzReadSum o;
+            o.end = end; o.fmark = fmark; o.flags = (uint16_t)flags; o.cnt = (uint16_t)cnt;
+            o.hoff = (uint32_t)(incl - cnt);
+            *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
+            if (row_lb) row_lb[r] = lbs;
+        }
+        __syncwarp();                                          // the slice may be refilled by the next iteration
+        hAa = hBa; hAb = hBb; hBa = hCa; hBb = hCb;
+        spA = spB;
+    }
+    cp_async_wait<0>();
+}
 
 // query index of reference position p, or -1 (pysam get_reference_positions(full_length=True).index)
 __device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n_cigar, int32_t start, int32_t p) {
@@ -299,239 +634,6 @@ __device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n
 
 
 
-__global__ void __launch_bounds__(RS_THREADS)
-read_scan_pipe_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
-                      int tile_reads, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
-                      int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* stage[2] = {smem, smem + RS_STAGE};
-    int32_t* spos = reinterpret_cast<int32_t*>(smem + 2 * RS_STAGE);
-    __shared__ __align__(8) uint64_t bar[2];
-    __shared__ int64_t s_qa[3], s_qb[3];
-    __shared__ int32_t s_wsum[RS_THREADS / 32];
-    __shared__ int64_t s_base, s_row_end;
-    __shared__ int32_t s_rb0, s_maxspan;
-
-    const int64_t n = reads.n_reads;
-    const int64_t n_tiles = (n + tile_reads - 1) / tile_reads;
-    const int64_t tpc = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t0 = (int64_t)blockIdx.x * tpc;
-    const int64_t t1 = min(t0 + tpc, n_tiles);
-    if (t0 >= t1) return;
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_barrier_init();
-    }
-    uint32_t phase[2] = {0, 0};
-    const bool lane_ok = (int)threadIdx.x < tile_reads;
-
-    auto hdr_of = [&](int64_t tile, bool& live) -> UnfzRead {
-        const int64_t r = tile * tile_reads + threadIdx.x;
-        live = lane_ok && tile < t1 && r < n;
-        UnfzRead h;
-        h.start = 0; h.l_seq = 0; h.n_cigar = 0; h.qoff_lo = 0; h.qoff_hi = 0;
-        if (live) h = load_read(reads.hdr + r);
-        return h;
-    };
-    auto publish_span = [&](int64_t tile, const UnfzRead& h, bool live) {     // slot tile % 3
-        if (tile >= t1) return;
-        const int64_t r0 = tile * tile_reads;
-        const int64_t last = min(r0 + tile_reads, n) - 1;
-        const int64_t r = r0 + threadIdx.x;
-        const int slot = (int)((tile - t0) % 3);
-        if (threadIdx.x == 0) s_qa[slot] = read_qoff(h);
-        if (live && r == last) s_qb[slot] = read_qoff(h) + h.l_seq;
-    };
-    auto issue = [&](int64_t tile) {                                          // thread 0 only
-        const int slot = (int)((tile - t0) % 3), st = (int)((tile - t0) & 1);
-        const int64_t qa = s_qa[slot], qb = s_qb[slot];
-        if (qb > qa) {
-            const int64_t ga = qa & ~(int64_t)15;
-            const uint32_t bytes = (uint32_t)(((qb - ga) + 15) & ~(int64_t)15);
-            fence_proxy_async();
-            mbar_expect_tx(&bar[st], bytes);
-            tma_bulk_g2s(stage[st], reads.qual + ga, bytes, &bar[st]);
-        }
-    };
-
-    bool live, live1, live2 = false;
-    UnfzRead h = hdr_of(t0, live);
-    UnfzRead h1 = hdr_of(t0 + 1, live1);
-    UnfzRead h2 = h1;
-    publish_span(t0, h, live);
-    publish_span(t0 + 1, h1, live1);
-    if (threadIdx.x == 0) {
-        const int64_t r0 = t0 * tile_reads;
-        const int rb = (int)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r0) - 1);
-        s_rb0 = rb;
-        const int sb0 = reads.blk_sblk[rb];
-        int64_t rowb = 0, rowe = 0;
-        if (sb0 >= 0) {
-            rowe = sites.blk_off[sb0 + 1];
-            rowb = lower_bound_dev(sites.pos, sites.blk_off[sb0], rowe, h.start);
-        }
-        s_base = rowb;
-        s_row_end = rowe;
-        s_maxspan = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) issue(t0);
-
-    struct Pending { bool live; int64_t r; int64_t tile; UnfzReadSum o; int32_t lbs; } pend;
-    pend.live = false; pend.tile = -1;
-    auto flush = [&]() {                                       // after a barrier that follows the s_wsum writes
-        if (pend.tile < 0) return;
-        const int warp = threadIdx.x >> 5;
-        int basew = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < RS_THREADS / 32; ++w) { const int v = s_wsum[w]; if (w < warp) basew += v; total += v; }
-        if (threadIdx.x == 0) tile_tot[pend.tile] = (uint32_t)total;
-        if (pend.live) {
-            pend.o.hoff += (uint32_t)basew;
-            *reinterpret_cast<int4*>(out + pend.r) = *reinterpret_cast<const int4*>(&pend.o);
-            if (row_lb) row_lb[pend.r] = pend.lbs;
-        }
-    };
-    for (int64_t tile = t0; tile < t1; ++tile) {
-        const int st = (int)((tile - t0) & 1);
-        const int slot = (int)((tile - t0) % 3);
-        flush();                                               // results of the previous tile
-        h2 = hdr_of(tile + 2, live2);                        // in flight during this iteration
-        if (threadIdx.x == 0 && tile + 1 < t1) issue(tile + 1);
-        const int64_t r0 = tile * tile_reads;
-        const int64_t r = r0 + threadIdx.x;
-        const int rb0 = s_rb0;
-        const int64_t row_base = s_base, row_end = s_row_end;
-        for (int i = threadIdx.x; i < RS_SPOS; i += RS_THREADS)
-            spos[i] = (row_base + i < row_end) ? __ldg(sites.pos + row_base + i) : 0x7fffffff;
-        int rb = rb0;
-        if (live && r >= reads.blk_off[rb + 1])
-            rb = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb, (int64_t)reads.n_blocks + 1, r) - 1);
-        const int sb = live ? reads.blk_sblk[rb] : -1;
-
-        int32_t end = 0;
-        uint32_t flags = 0;
-        if (live) {
-            int none_cnt = 0, non_m = 0;
-            end = h.start;
-            const uint32_t* cg = reads.cigar + h.cigar_off;
-            for (int k = 0; k < h.n_cigar; ++k) {
-                const uint32_t w = __ldg(cg + k);
-                const uint32_t op = w & 15u, ln = w >> 4;
-                if (op == 0 || op == 7 || op == 8 || op == 2 || op == 3) end += (int32_t)ln;
-                if (op == 1 || op == 4) none_cnt += (int)ln;
-                if (op != 0 && op != 7) ++non_m;
-            }
-            const uint32_t f = h.flag;
-            const bool base_ok = !(f & (0x200u | 0x4u | 0x400u | 0x100u | 0x800u | 0x8u)) &&
-                                 (int)h.mapq >= P.min_mapq && (h.aux & 1u);
-            if (base_ok) flags |= UNFZ_RS_GOOD_DISC;
-            if (none_cnt <= 5) flags |= UNFZ_RS_NONE_OK;
-            if (non_m <= 5) flags |= UNFZ_RS_EXT_OK;
-            long long ins = (long long)h.tlen - 2ll * P.readlen;
-            if (ins < 0) ins = -ins;
-            if ((double)ins <= reads.blk_cul[rb]) flags |= UNFZ_RS_INS_OK;
-            if ((f & 1u) && !(f & 8u) && h.mate >= 0) flags |= UNFZ_RS_HAS_MATE;
-            atomicMax(&s_maxspan, end - h.start);
-        }
-        __syncthreads();   // spos visible
-
-        int32_t fmark = 0, cnt = 0;
-        int64_t lbs = 0, lbe = 0;
-        if (live && sb >= 0) {
-            if (rb == rb0) {
-                // a tile spans a few site rows only: gallop from the front of the staged window
-                int lo = 0, hi = 8;
-                while (hi < RS_SPOS && spos[hi - 1] < h.start) { lo = hi; hi = min(hi * 2, RS_SPOS); }
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h.start) lo = mid + 1; else hi = mid; }
-                int lo2 = lo; hi = min(lo + 4, RS_SPOS);
-                while (hi < RS_SPOS && spos[hi - 1] < end) { lo2 = hi; hi = min(hi + 8, RS_SPOS); }
-                while (lo2 < hi) { int mid = (lo2 + hi) >> 1; if (spos[mid] < end) lo2 = mid + 1; else hi = mid; }
-                lbs = row_base + lo;
-                lbe = row_base + lo2;
-                if (lo2 == RS_SPOS) {
-                    if (lo == RS_SPOS) lbs = lower_bound_dev(sites.pos, row_base + RS_SPOS - 1, row_end, h.start);
-                    lbe = lower_bound_dev(sites.pos, lbs, row_end, end);
-                }
-            } else {
-                const int64_t a = sites.blk_off[sb], b = sites.blk_off[sb + 1];
-                lbs = lower_bound_dev(sites.pos, a, b, h.start);
-                lbe = lower_bound_dev(sites.pos, lbs, b, end);
-            }
-            fmark = __ldg(mark_prefix + lbs);
-            const int32_t c = __ldg(mark_prefix + lbe) - fmark;
-            cnt = c > 0xffff ? 0xffff : c;
-        }
-
-        // ---- hit slots: offset of the read inside its tile (block scan of cnt) + the tile's total; the
-        // pipeline scans the tile totals, so hoff(read) = tile_base[tile] + local offset.  Only the warp
-        // part of the scan runs here; it is finished after the tile's closing barrier (see `pending`),
-        // so the scan costs no barrier of its own.
-        int warp_incl = cnt;
-        {
-            const int lane = threadIdx.x & 31;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, warp_incl, o); if (lane >= o) warp_incl += y; }
-        }
-
-        int low = 0;
-        const int64_t qa = s_qa[slot], qb = s_qb[slot];
-        if (qb > qa) {
-            mbar_wait(&bar[st], phase[st]);
-            phase[st] ^= 1u;
-            if (live && h.l_seq > 0) {
-                const int off = (int)(read_qoff(h) - (qa & ~(int64_t)15));
-                low = count_low_quals(stage[st], off, off + h.l_seq, (uint32_t)P.min_bq);
-            }
-        }
-        if (live && (flags & UNFZ_RS_GOOD_DISC) && low <= 10 && h.n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
-        // stash this tile's results; they are written once the block scan is complete
-        pend.live = live; pend.r = r; pend.tile = tile;
-        pend.o.end = end; pend.o.fmark = fmark; pend.o.flags = (uint16_t)flags; pend.o.cnt = (uint16_t)cnt;
-        pend.o.hoff = (uint32_t)(warp_incl - cnt);
-        pend.lbs = (int32_t)lbs;
-        if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = warp_incl;
-        // ---- hand-over to the next tile ---------------------------------------------------------
-        publish_span(tile + 2, h2, live2);                   // slot (tile+2)%3 is not in use
-        if (threadIdx.x == 0) {
-            const int64_t rn = (tile + 1) * tile_reads;
-            // flush the span of this tile to every block it touches, then carry the window forward
-            const int64_t last = min(r0 + tile_reads, n) - 1;
-            int rb_last = rb0;
-            if (last >= reads.blk_off[rb0 + 1])
-                rb_last = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb0, (int64_t)reads.n_blocks + 1, last) - 1);
-            if (s_maxspan > 0)
-                for (int b = rb0; b <= rb_last; ++b) atomicMax(blk_maxspan + b, s_maxspan);
-            s_maxspan = 0;
-            if (tile + 1 < t1 && rn < n) {
-                if (rn >= reads.blk_off[rb0 + 1]) {           // next tile starts in another read block
-                    const int rbn = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb0, (int64_t)reads.n_blocks + 1, rn) - 1);
-                    s_rb0 = rbn;
-                    const int sbn = reads.blk_sblk[rbn];
-                    int64_t rowb = 0, rowe = 0;
-                    if (sbn >= 0) {
-                        rowe = sites.blk_off[sbn + 1];
-                        rowb = lower_bound_dev(sites.pos, sites.blk_off[sbn], rowe, h1.start);
-                    }
-                    s_base = rowb;
-                    s_row_end = rowe;
-                } else {
-                    int lo = 0, hi = RS_SPOS;                 // first staged row with pos >= next tile's first start
-                    while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h1.start) lo = mid + 1; else hi = mid; }
-                    int64_t nb = row_base + lo;
-                    if (lo == RS_SPOS) nb = lower_bound_dev(sites.pos, row_base + RS_SPOS - 1, row_end, h1.start);
-                    s_base = nb;
-                }
-            }
-        }
-        h = h1; live = live1;
-        h1 = h2; live1 = live2;
-        __syncthreads();   // stage st, spos, s_wsum and the carried state are consistent for the next tile
-    }
-    flush();
-}
 
 // ------------------------------------------------------------------------------------------------
 // K3: read x marked-site allele lookup
@@ -576,15 +678,11 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
 
 }  // namespace
 
-static int scan_tile_reads(int32_t max_l_seq) {
-    if (max_l_seq > 0 && (int64_t)max_l_seq + 32 <= RS_STAGE) {
-        int t = (RS_STAGE - 32) / max_l_seq;
-        return t > RS_THREADS ? RS_THREADS : t;
-    }
-    return RS_THREADS;
-}
+// bytes of one quality slice of the streaming kernel: 32 reads + 16-byte alignment slop on either side
+static int wp_slice_bytes(int32_t max_l_seq) { return ((32 * max_l_seq + 15) & ~15) + 32; }
 
-extern "C" int32_t unfz_read_scan_tile_reads(int32_t max_l_seq) { return scan_tile_reads(max_l_seq); }
+// hit slots are numbered per tile of this many consecutive reads (tile_tot / tile_base granularity)
+extern "C" int32_t unfz_read_scan_tile_reads(int32_t max_l_seq) { (void)max_l_seq; return 32; }
 
 extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                               const int32_t* mark_prefix, const UnfzParams* hp, int32_t max_l_seq, UnfzReadSum* out,
@@ -595,18 +693,21 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     double bq = hp->min_gt_qual;
     P.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));
     P.readlen = hp->readlen;
-    if (max_l_seq > 0 && (int64_t)max_l_seq + 32 <= RS_STAGE) {
-        const int tile_reads = scan_tile_reads(max_l_seq);
-        const size_t smem2 = 2 * RS_STAGE + RS_SPOS * sizeof(int32_t);
-        static bool attr2 = false;
-        if (!attr2) {
-            UNFZ_CHECK(ctx, cudaFuncSetAttribute(read_scan_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            attr2 = true;
+    const int qslice = max_l_seq > 0 ? wp_slice_bytes(max_l_seq) : 0;
+    const size_t smem2 = (size_t)WP_WARPS * (2 * (size_t)qslice + WP_FIXED);
+    if (max_l_seq > 0 && smem2 <= 200 * 1024) {
+        static size_t attr2 = 0;
+        if (smem2 > attr2) {
+            UNFZ_CHECK(ctx, cudaFuncSetAttribute(read_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            attr2 = smem2;
         }
-        const int64_t tiles = (reads->n_reads + tile_reads - 1) / tile_reads;
-        int64_t g = (int64_t)ctx->sm_count * 3;     // 3 CTAs x 72 KB of staging per SM
-        if (g > tiles) g = tiles;
-        read_scan_pipe_kernel<<<(unsigned)g, RS_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, tile_reads,
+        int per_sm = (int)((size_t)(228 * 1024) / (smem2 + 1024));
+        if (per_sm > 3) per_sm = 3;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t tiles = (reads->n_reads + 31) / 32;
+        int64_t g = (int64_t)ctx->sm_count * per_sm;
+        if (g * WP_WARPS > tiles) g = (tiles + WP_WARPS - 1) / WP_WARPS;
+        read_scan_warp_kernel<<<(unsigned)g, WP_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, qslice,
                                                                                      out, row_lb, blk_maxspan, tile_tot);
         UNFZ_LAUNCH_CHECK(ctx);
         return 0;

@@ -283,7 +283,11 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
 //    gathers (L2), low-quality count with 4-byte SIMD compares + DP4A out of shared memory;
 //  * hit slots are numbered per tile: one warp scan, one total per tile, no cross-warp scan.
 // ------------------------------------------------------------------------------------------------
-constexpr int WP_WARPS = 7;                               // warps per CTA (3 CTAs per SM at 150-base reads)
+// 5 warps x 4 CTAs per SM: the 20 warps spread evenly over the four sub-partitions (16 K registers each),
+// which leaves 96 registers per thread; 7 x 3 puts 6 warps on one sub-partition, caps the kernel at 80
+// registers and spills (measured: 0.42 ms vs 0.35 ms at 4000 DNMs)
+#define WP_MINB 4
+constexpr int WP_WARPS = 5;
 constexpr int WP_THREADS = WP_WARPS * 32;
 constexpr int WP_CIGW = 64;                               // staged CIGAR words per tile
 constexpr int WP_SPOS = 64;                               // site positions per window
@@ -346,7 +350,7 @@ struct WpSpan {               // where the staged spans of a tile start, and whe
     bool q_ok, cig_ok;
 };
 
-__global__ void __launch_bounds__(WP_THREADS, 3)
+__global__ void __launch_bounds__(WP_THREADS, WP_MINB)
 read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
                       int qslice, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
                       int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot) {
@@ -552,7 +556,7 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
         }
 
         // ---- marked-site overlap: rows with start <= pos < end ----------------------------------------
-        int32_t fmark = 0, cnt = 0;
+        int32_t fmark = 0, emark = 0;
         int lbs = 0, lbe = 0;
         if (live && sb >= 0) {
             if (which < 2) {
@@ -573,9 +577,8 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
                 lbs = (int)lower_bound_dev(sites.pos, a, b, start);
                 lbe = (int)lower_bound_dev(sites.pos, lbs, b, end);
             }
-            fmark = __ldg(mark_prefix + lbs);
-            const int32_t c = __ldg(mark_prefix + lbe) - fmark;
-            cnt = c > 0xffff ? 0xffff : c;
+            fmark = __ldg(mark_prefix + lbs);                  // two L2 gathers, in flight during the quality count below
+            emark = __ldg(mark_prefix + lbe);
         }
 
         // ---- goodread: low-quality bases out of the staged span ---------------------------------------
@@ -592,6 +595,7 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
         }
         if (live && (flags & UNFZ_RS_GOOD_DISC) && low <= 10 && n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
 
+        const int32_t cnt = min(emark - fmark, 0xffff);
         // ---- hit slots: offset inside the tile + the tile's total -----------------------------------------
         int incl = cnt;
 #pragma unroll
@@ -702,7 +706,7 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
             attr2 = smem2;
         }
         int per_sm = (int)((size_t)(228 * 1024) / (smem2 + 1024));
-        if (per_sm > 3) per_sm = 3;
+        if (per_sm > WP_MINB) per_sm = WP_MINB;
         if (per_sm < 1) per_sm = 1;
         const int64_t tiles = (reads->n_reads + 31) / 32;
         int64_t g = (int64_t)ctx->sm_count * per_sm;

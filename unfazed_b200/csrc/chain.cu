@@ -336,8 +336,23 @@ __device__ uint8_t allele_info(const ChainArgs& A, const Scratch& S, int64_t e0,
     return out;
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 8)
+#ifdef CH_DEBUG
+__device__ unsigned long long g_ch_dbg[16];
+#define CH_MARK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_ch_dbg[i], (unsigned long long)(t_ - ch_t0)); ch_t0 = t_; } } while (0)
+#else
+#define CH_MARK(i)
+#endif
+
+// 16 CTAs per SM (32 registers, ~150 B of spills): the kernel is a chain of dependent gathers, so resident
+// warps matter more than registers (measured at 4000 DNMs: 8 CTAs 0.348 ms, 12 CTAs 0.310 ms, 16 CTAs 0.292 ms)
+#ifndef CH_MINB
+#define CH_MINB 16
+#endif
+__global__ void __launch_bounds__(CH_THREADS, CH_MINB)
 chain_kernel(ChainArgs A) {
+#ifdef CH_DEBUG
+    long long ch_t0 = clock64();
+#endif
     const int d = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const UnfzDnm dn = A.dnms[d];
@@ -424,6 +439,7 @@ chain_kernel(ChainArgs A) {
     }
     __syncthreads();
 
+    CH_MARK(0);
     // ---------------------------------------------------------------- phase 1: seed reads
     // seeds are kept as ENTRIES (one read per entry) in the order the reference appends them
     int n_seed = 0;
@@ -501,6 +517,7 @@ chain_kernel(ChainArgs A) {
     }
     __syncthreads();
 
+    CH_MARK(1);
     for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) init_slot(x); }
     __syncthreads();
     int n_inc = 0, n_sinc = 0;
@@ -530,37 +547,78 @@ chain_kernel(ChainArgs A) {
         for (int i = tid; i <= nh; i += CH_THREADS) site_off[i] = 0x7fffffff;
         __syncthreads();
         const int n_candidates = cand_off[nh];
-        // (c) one ordered pass over all (site, read) candidates
-        for (int base = 0; base < n_candidates; base += CH_THREADS) {
-            const int c = base + tid;
-            bool ok = false;
-            int i = 0;
-            int64_t r = 0;
-            if (c < n_candidates) {
+    CH_MARK(2);
+        // (c) one ordered pass over all (site, read) candidates.  The filter (three dependent gathers per
+        // candidate) runs without any barrier: each batch of CH_THREADS candidates leaves only its four warp
+        // ballots in shared memory; one scan over the ballots then gives every survivor its slot, and a second,
+        // load-free pass writes them in candidate order.
+        constexpr int CH_SB = 32;                                  // batches per round (ballots kept in smem)
+        __shared__ uint32_t s_bal[CH_SB * CH_WARPS];
+        __shared__ int32_t s_bpre[CH_SB * CH_WARPS];
+        __shared__ int32_t s_btot;
+        for (int c0 = 0; c0 < n_candidates; c0 += CH_SB * CH_THREADS) {
+            const int nb = min(CH_SB, (n_candidates - c0 + CH_THREADS - 1) / CH_THREADS);
+            int i0 = 0;                                            // site of this thread's first candidate
+            if (c0 + tid < n_candidates) {
                 int lo = 0, hi = nh;                               // last i with cand_off[i] <= c
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_off[mid] <= c) lo = mid; else hi = mid; }
-                i = lo;
-                r = blk_lo + site_base[i] + (c - cand_off[i]);
-                const int32_t p = spos[i];
-                bool ov = A.rsum[r].end > p;
-                if (ov && site_cnt[i] > A.ext_goal) {              // Q2: `i > EXTENDED_RB_READ_GOAL` (never in practice)
-                    int idx = 0;
-                    for (int64_t q = blk_lo + site_base[i]; q < r; ++q) idx += A.rsum[q].end > p;
-                    ov = idx <= A.ext_goal;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_off[mid] <= c0 + tid) lo = mid; else hi = mid; }
+                i0 = lo;
+            }
+            int i = i0;
+#pragma unroll 4
+            for (int b = 0; b < nb; ++b) {
+                const int c = c0 + b * CH_THREADS + tid;
+                bool ok = false;
+                if (c < n_candidates) {
+                    while (cand_off[i + 1] <= c) ++i;              // candidates are site-major: the cursor only moves forward
+                    const int64_t r = blk_lo + site_base[i] + (c - cand_off[i]);
+                    const int32_t p = spos[i];
+                    bool ov = A.rsum[r].end > p;
+                    if (ov && site_cnt[i] > A.ext_goal) {          // Q2: `i > EXTENDED_RB_READ_GOAL` (never in practice)
+                        int idx = 0;
+                        for (int64_t q = blk_lo + site_base[i]; q < r; ++q) idx += A.rsum[q].end > p;
+                        ov = idx <= A.ext_goal;
+                    }
+                    ok = ov && pair_ok(A, r, true);
                 }
-                ok = ov && pair_ok(A, r, true);
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) s_bal[b * CH_WARPS + warp] = bal;
             }
-            int tot;
-            const int k = n_inc + block_prefix(ok, &tot);
-            if (ok && k < cap_inc) {
-                const int x = canon(r);
-                inc_r[k] = (int32_t)r;
-                inc_x[k] = x;
-                inc_site[k] = i;
-                inc_sidx[k] = i;      // order key inside read_sites[x]: registered sites come in site order
+            __syncthreads();
+            if (warp == 0) {                                       // exclusive prefix of the ballot populations
+                int run = 0;
+                for (int j0 = 0; j0 < nb * CH_WARPS; j0 += 32) {
+                    const int j = j0 + lane;
+                    const int v = j < nb * CH_WARPS ? __popc(s_bal[j]) : 0;
+                    int x = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                    if (j < nb * CH_WARPS) s_bpre[j] = run + x - v;
+                    run += __shfl_sync(0xffffffffu, x, 31);
+                }
+                if (lane == 0) s_btot = run;
             }
-            n_inc += tot;
+            __syncthreads();
+            i = i0;
+            for (int b = 0; b < nb; ++b) {
+                const int c = c0 + b * CH_THREADS + tid;
+                const unsigned bal = s_bal[b * CH_WARPS + warp];
+                if (c < n_candidates && ((bal >> lane) & 1u)) {
+                    while (cand_off[i + 1] <= c) ++i;
+                    const int64_t r = blk_lo + site_base[i] + (c - cand_off[i]);
+                    const int k = n_inc + s_bpre[b * CH_WARPS + warp] + __popc(bal & ((1u << lane) - 1u));
+                    if (k < cap_inc) {
+                        inc_r[k] = (int32_t)r;
+                        inc_x[k] = canon(r);
+                        inc_site[k] = i;
+                        inc_sidx[k] = i;      // order key inside read_sites[x]: registered sites come in site order
+                    }
+                }
+            }
+            n_inc += s_btot;
+            __syncthreads();                                       // the ballots are reused by the next round
         }
+    CH_MARK(3);
         if (n_inc > cap_inc) { n_inc = (int)cap_inc; T.status |= 2; }
         __syncthreads();
         for (int k = tid; k < n_inc; k += CH_THREADS) {
@@ -582,6 +640,7 @@ chain_kernel(ChainArgs A) {
         __syncthreads();
     }
     {
+    CH_MARK(4);
         // ------------------------------------------------------------ phase 3: seed registration
         // Entries register in the order "ref" list then "alt" list (:226-249); the level-0 visit order
         // is "alt" list first (Q19).  Everything is resolved with order keys instead of a serial loop:
@@ -667,6 +726,7 @@ chain_kernel(ChainArgs A) {
         __syncthreads();
     }
     if (!A.no_extended) {
+    CH_MARK(5);
         // ------------------------------------------------------------ phase 3.5: allele codes
         for (int k = tid; k < n_inc; k += CH_THREADS) {
             const int i = inc_site[k];
@@ -678,6 +738,7 @@ chain_kernel(ChainArgs A) {
         }
         __syncthreads();
 
+    CH_MARK(6);
         // ------------------------------------------------------------ phase 4: level-synchronous BFS
         for (int k = tid; k < n_inc; k += CH_THREADS) minkey[inc_x[k]] = KEY_NONE;
         __syncthreads();
@@ -769,6 +830,7 @@ chain_kernel(ChainArgs A) {
         __syncthreads();
     }
 
+    CH_MARK(7);
     // ---------------------------------------------------------------- phase 5: matching + evidence
     int has_rec = 0;
     for (int x = tid; x < W; x += CH_THREADS) {
@@ -817,6 +879,7 @@ chain_kernel(ChainArgs A) {
     }
     __syncthreads();
 
+    CH_MARK(8);
     // ---------------------------------------------------------------- phase 6: tally
     int ds = 0, ms = 0, dr = 0, mr = 0;
     for (int j = tid; j < nc; j += CH_THREADS) {
@@ -840,6 +903,7 @@ chain_kernel(ChainArgs A) {
         T.has_record = has_rec > 0;
         A.tally[d] = T;
     }
+    CH_MARK(9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1073,6 +1137,16 @@ extern "C" int unfz_chain_size(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
+
+#ifdef CH_DEBUG
+extern "C" int unfz_debug_chain(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_ch_dbg, sizeof(g_ch_dbg));
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_ch_dbg, z, sizeof(z));
+    return 0;
+}
+#endif
 
 extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSegIn* segs,
                                 const int64_t* seg_pair_off, const UnfzSiteCols* sites, const UnfzReadCols* reads,

@@ -333,7 +333,7 @@ def run_b200(args):
             "kernel": dom, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
             "achieved": domk.get("gbps"), "frac": domk.get("frac"), "traffic": traffic,
             "ms_per_launch": domk["ms"],
-            "kernels": kern,
+            "kernels": kern, "stages_ms": {k: round(v, 4) for k, v in stage.items()},
             "classify_sites_saturating": sat,
             "read_allele_lookup_survey_bytes": {
                 "bytes": survey_read_bytes, "ms": lookup_ms,

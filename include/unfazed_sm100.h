@@ -190,6 +190,19 @@ int         unfz_ctx_create(int device, UnfzCtx** out);
 void        unfz_ctx_destroy(UnfzCtx* ctx);
 const char* unfz_last_error(UnfzCtx* ctx);
 
+/* Speculative sizing (no reference counterpart: the reference has no device).  The sizes of the variable
+ * outputs -- pairs, hits, chaining scratch -- are only known on the device.  A caller that allocated them
+ * from the capacities of an earlier, similar batch calls unfz_check_caps() instead of reading the totals
+ * back: it compares up to 8 device-resident int64 totals (h_totals[i] is a device address) with
+ * h_caps[i], stores them in actual[0..k) and ORs 1 into *flag when one is exceeded.  While a flag is
+ * installed with unfz_ctx_set_guard(), classify_sites / compact_sites / read_scan / chain_size /
+ * read_site_alleles / chain_tally return immediately once it is set, so nothing is written out of bounds;
+ * the caller then re-runs the batch with exact sizes.  unfz_classify_sites treats n_pairs as the capacity
+ * of out_class and reads the batch's own total from seg_pair_off[n_segs].  Pass NULL to remove the guard. */
+int unfz_ctx_set_guard(UnfzCtx*, const int32_t* flag);
+int unfz_check_caps(UnfzCtx*, int32_t k, const int64_t* const* h_totals, const int64_t* h_caps, int32_t* flag,
+                    int64_t* actual, void* stream);
+
 /* Exclusive prefix sums (device-wide).  `work` needs unfz_scan_work_bytes(n) bytes. */
 int64_t unfz_scan_work_bytes(int64_t n);
 int unfz_exclusive_scan_i64(UnfzCtx*, const int64_t* in, int64_t* out, int64_t n, void* work, void* stream);

@@ -77,6 +77,8 @@ SYMBOLS = {
     "unfz_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "unfz_ctx_destroy": (None, [_P]),
     "unfz_last_error": (C.c_char_p, [_P]),
+    "unfz_ctx_set_guard": (C.c_int, [_P, _P]),
+    "unfz_check_caps": (C.c_int, [_P, c_int32, _P, _P, _P, _P, _P]),
     "unfz_scan_work_bytes": (c_int64, [c_int64]),
     "unfz_exclusive_scan_i64": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
     "unfz_exclusive_scan_u8_i32": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),

@@ -21,9 +21,8 @@ constexpr unsigned long long KEY_NONE = ~0ull;
 constexpr int CH_SMEM_SITES = 256;         // per-site state lives in shared memory up to this many het sites
 
 struct Scratch {
-    // per window slot
-    int32_t* prim; uint32_t* ord; int32_t* lvl; int32_t* fpos;
-    unsigned long long* minkey; int32_t* tmp;
+    // per window slot: one 32-byte record (a single DRAM sector) per read pair, see SlotField
+    char* slot;
     // per het-site incidence
     int32_t* inc_r; int32_t* inc_x; int32_t* inc_site; int32_t* inc_sidx; uint8_t* inc_al;
     // seeds
@@ -35,6 +34,17 @@ struct Scratch {
     unsigned long long* bestkey; int32_t* site_cnt; int32_t* site_base;
     // per candidate site
     int32_t* cpos;
+};
+
+// The per-pair state used to be six arrays; a touched pair then cost six sectors.  Packed as
+//   minkey u64 @0 | prim i32 @8 | ord u32 @12 | lvl i32 @16 | fpos i32 @20 | tmp i32 @24 | pad
+// it costs one.  SlotField keeps the array syntax (f[x], f + x) over the strided records.
+constexpr int SLOT_BYTES = 32;
+template <typename T, int OFF>
+struct SlotField {
+    char* base;
+    __device__ __forceinline__ T& operator[](int x) const { return *reinterpret_cast<T*>(base + (size_t)x * SLOT_BYTES + OFF); }
+    __device__ __forceinline__ T* operator+(int x) const { return reinterpret_cast<T*>(base + (size_t)x * SLOT_BYTES + OFF); }
 };
 
 struct ChainArgs {
@@ -49,6 +59,7 @@ struct ChainArgs {
     const int32_t* site_lo; const int32_t* site_n; const int32_t* seed_win;   // fetch ranges found by chain_size
     int32_t readlen, min_bq, ext_goal, no_extended;
     uint8_t* slot_label; uint8_t* slot_evid; uint8_t* cand_evid; UnfzTally* tally;
+    const int32_t* guard;
     Scratch S;
 };
 
@@ -350,6 +361,7 @@ __device__ unsigned long long g_ch_dbg[16];
 #endif
 __global__ void __launch_bounds__(CH_THREADS, CH_MINB)
 chain_kernel(ChainArgs A) {
+    UNFZ_GUARD(A.guard);
 #ifdef CH_DEBUG
     long long ch_t0 = clock64();
 #endif
@@ -379,9 +391,13 @@ chain_kernel(ChainArgs A) {
     const int64_t cap_sinc = off[3 * n1 + d + 1] - o_sinc;
 
     // per-DNM views
-    int32_t* prim = S0.prim + o_slot; uint32_t* ord = S0.ord + o_slot; int32_t* lvl = S0.lvl + o_slot;
-    int32_t* fpos = S0.fpos + o_slot;
-    unsigned long long* minkey = S0.minkey + o_slot; int32_t* tmp = S0.tmp + o_slot;
+    char* slot_base = S0.slot + o_slot * SLOT_BYTES;
+    const SlotField<unsigned long long, 0> minkey{slot_base};
+    const SlotField<int32_t, 8> prim{slot_base};
+    const SlotField<uint32_t, 12> ord{slot_base};
+    const SlotField<int32_t, 16> lvl{slot_base};
+    const SlotField<int32_t, 20> fpos{slot_base};
+    const SlotField<int32_t, 24> tmp{slot_base};
     uint8_t* label = A.slot_label + o_slot; uint8_t* evid = A.slot_evid + o_slot;
     int32_t* inc_r = S0.inc_r + o_inc; int32_t* inc_x = S0.inc_x + o_inc; int32_t* inc_site = S0.inc_site + o_inc;
     int32_t* inc_sidx = S0.inc_sidx + o_inc; uint8_t* inc_al = S0.inc_al + o_inc;
@@ -427,7 +443,11 @@ chain_kernel(ChainArgs A) {
 
     // per-slot state is initialised lazily, only for the pairs that get touched (seeds + registered
     // reads); slot_label / slot_evid are zero-filled by the caller
-    auto init_slot = [&](int x) { prim[x] = -1; lvl[x] = -1; fpos[x] = -1; ord[x] = 0xffffffffu; tmp[x] = 0; minkey[x] = 0ull; };
+    auto init_slot = [&](int x) {                                 // two 16-byte stores
+        int4* rec = reinterpret_cast<int4*>(slot_base + (size_t)x * SLOT_BYTES);
+        rec[0] = make_int4(0, 0, -1, -1);                          // minkey = 0, prim = -1, ord = 0xffffffff
+        rec[1] = make_int4(-1, -1, 0, 0);                          // lvl = -1, fpos = -1, tmp = 0
+    };
     for (int i = tid; i < nh; i += CH_THREADS) {
         const int64_t row = H[i];
         spos[i] = __ldg(A.sites.pos + row);
@@ -931,7 +951,9 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
                   const int32_t* __restrict__ blk_maxspan, const int32_t* __restrict__ het_list,
                   const int32_t* __restrict__ n_het, const uint32_t* __restrict__ cand_list,
                   const int32_t* __restrict__ n_cand, int32_t* __restrict__ win, int64_t* __restrict__ need,
-                  int32_t* __restrict__ site_lo, int32_t* __restrict__ site_n, int32_t* __restrict__ seed_win) {
+                  int32_t* __restrict__ site_lo, int32_t* __restrict__ site_n, int32_t* __restrict__ seed_win,
+                  const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
     const int lane = threadIdx.x & 31;
     const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_dnms) return;
@@ -1094,10 +1116,7 @@ Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_
                   int64_t n_dnms, int64_t* total) {
     Scratch S;
     char* p = base;
-    S.prim = (int32_t*)carve<int32_t>(p, slots); S.ord = (uint32_t*)carve<uint32_t>(p, slots);
-    S.lvl = (int32_t*)carve<int32_t>(p, slots); S.fpos = (int32_t*)carve<int32_t>(p, slots);
-    S.minkey = (unsigned long long*)carve<unsigned long long>(p, slots);
-    S.tmp = (int32_t*)carve<int32_t>(p, slots);
+    S.slot = carve<char>(p, slots * SLOT_BYTES);                  // first: the base is 256-byte aligned
     S.inc_r = (int32_t*)carve<int32_t>(p, incs); S.inc_x = (int32_t*)carve<int32_t>(p, incs);
     S.inc_site = (int32_t*)carve<int32_t>(p, incs); S.inc_sidx = (int32_t*)carve<int32_t>(p, incs);
     S.inc_al = (uint8_t*)carve<uint8_t>(p, incs);
@@ -1133,7 +1152,7 @@ extern "C" int unfz_chain_size(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms
     if (n_dnms <= 0) return 0;
     chain_size_kernel<<<(n_dnms + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         dnms, n_dnms, seg_pair_off, *sites, *reads, rsum, blk_maxspan, het_list, n_het, cand_list, n_cand, win, need,
-        site_lo, site_n, seed_win);
+        site_lo, site_n, seed_win, ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1175,6 +1194,7 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     uintptr_t base = ((uintptr_t)scratch + 255) & ~(uintptr_t)255;
     A.S = carve_all((char*)base, h_totals[0], h_totals[1], h_totals[2], h_totals[3], h_totals[4], h_totals[5], n_dnms, &total);
     if ((int64_t)(base - (uintptr_t)scratch) + total > scratch_bytes) return unfz_fail(ctx, -20, "chain scratch too small");
+    A.guard = ctx->guard;
     chain_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;

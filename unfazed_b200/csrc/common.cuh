@@ -10,8 +10,12 @@
 struct UnfzCtx {
     int device;
     int sm_count;
+    const int32_t* guard;     // device flag of the speculative-sizing mode (unfz_ctx_set_guard), or null
     char err[512];
 };
+
+// every kernel that writes into speculatively sized buffers starts with this
+#define UNFZ_GUARD(g) do { if ((g) != nullptr && *(g) != 0) return; } while (0)
 
 #define UNFZ_CHECK(ctx, expr)                                                                   \
     do {                                                                                        \

@@ -92,7 +92,8 @@ __device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, in
 __global__ void __launch_bounds__(RS_THREADS)
 read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
                  UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb, int32_t* __restrict__ blk_maxspan,
-                 uint32_t* __restrict__ tile_tot) {
+                 uint32_t* __restrict__ tile_tot, const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* qbuf = smem;                                             // RS_QBUF + 16
     int32_t* spos = reinterpret_cast<int32_t*>(smem + RS_QBUF + 16);  // RS_SPOS
@@ -353,7 +354,8 @@ struct WpSpan {               // where the staged spans of a tile start, and whe
 __global__ void __launch_bounds__(WP_THREADS, WP_MINB)
 read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
                       int qslice, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
-                      int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot) {
+                      int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot, const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* my = smem + warp * (2 * qslice + WP_FIXED);
@@ -646,7 +648,8 @@ __global__ void __launch_bounds__(256)
 read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
                          const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
                          const int32_t* __restrict__ row_lb, const uint32_t* __restrict__ tile_base, int32_t tile_reads,
-                         uint32_t* __restrict__ hits) {
+                         uint32_t* __restrict__ hits, const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= reads.n_reads) return;
     const UnfzReadSum s = load_rsum(rsum + r);
@@ -712,7 +715,7 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
         int64_t g = (int64_t)ctx->sm_count * per_sm;
         if (g * WP_WARPS > tiles) g = (tiles + WP_WARPS - 1) / WP_WARPS;
         read_scan_warp_kernel<<<(unsigned)g, WP_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, qslice,
-                                                                                     out, row_lb, blk_maxspan, tile_tot);
+                                                                                     out, row_lb, blk_maxspan, tile_tot, ctx->guard);
         UNFZ_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -725,7 +728,7 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     const int64_t n_tiles = (reads->n_reads + RS_THREADS - 1) / RS_THREADS;
     int64_t grid = (int64_t)ctx->sm_count * 4;     // 4 x ~49 KB of staging per SM
     if (grid > n_tiles) grid = n_tiles;
-    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan, tile_tot);
+    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan, tile_tot, ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -737,7 +740,7 @@ extern "C" int unfz_read_site_alleles(UnfzCtx* ctx, const UnfzReadCols* reads, c
     if (reads->n_reads <= 0) return 0;
     const int64_t blocks = (reads->n_reads + 255) / 256;
     read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, row_lb,
-                                                                                 tile_base, tile_reads, hits);
+                                                                                 tile_base, tile_reads, hits, ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

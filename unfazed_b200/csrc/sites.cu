@@ -143,8 +143,11 @@ constexpr int CLS_SMEM_SEGS = 512;
 // inclusive prefix is the index of the last segment starting at or before the pair).
 __global__ void __launch_bounds__(CLS_THREADS)
 classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const int32_t* __restrict__ seg_row_lo,
-                const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs, ClsParams P,
-                uint8_t* __restrict__ out) {
+                const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs_cap, ClsParams P,
+                uint8_t* __restrict__ out, const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
+    // the launch is sized for n_pairs_cap (the caller's buffer); the batch's own total is on the device
+    const int64_t n_pairs = min(n_pairs_cap, seg_pair_off[n_segs]);
     __shared__ int32_t s_off[CLS_SMEM_SEGS + 1];     // pair offset of the segment relative to the tile
     __shared__ int4 s_seg[CLS_SMEM_SEGS];            // row_lo, mult | mode << 24, excl_lo, excl_hi
     __shared__ int32_t s_map[CLS_TILE];
@@ -267,7 +270,8 @@ compact_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const UnfzSegIn
                const int32_t* __restrict__ seg_row_lo, const int64_t* __restrict__ seg_pair_off,
                const uint8_t* __restrict__ cls, int32_t* __restrict__ het_list, int32_t* __restrict__ n_het,
                uint32_t* __restrict__ cand_list, int32_t* __restrict__ n_cand, int32_t* __restrict__ cnv_dad,
-               int32_t* __restrict__ cnv_mom, uint8_t* __restrict__ row_mark) {
+               int32_t* __restrict__ cnv_mom, uint8_t* __restrict__ row_mark, const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
     const int lane = threadIdx.x & 31;
     const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_dnms) return;
@@ -355,7 +359,7 @@ extern "C" int unfz_classify_sites(UnfzCtx* ctx, const UnfzSiteCols* sites, cons
     int64_t grid = (int64_t)ctx->sm_count * 8;
     if (grid > n_tiles) grid = n_tiles;
     classify_kernel<<<(unsigned)grid, CLS_THREADS, 0, (cudaStream_t)stream>>>(
-        *sites, segs, seg_row_lo, seg_pair_off, n_segs, n_pairs, P, out_class);
+        *sites, segs, seg_row_lo, seg_pair_off, n_segs, n_pairs, P, out_class, ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -367,7 +371,8 @@ extern "C" int unfz_compact_sites(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_d
     if (n_dnms <= 0) return 0;
     const int warps_per_block = 8;
     compact_kernel<<<(n_dnms + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, (cudaStream_t)stream>>>(
-        dnms, n_dnms, segs, seg_row_lo, seg_pair_off, cls, het_list, n_het, cand_list, n_cand, cnv_dad, cnv_mom, row_mark);
+        dnms, n_dnms, segs, seg_row_lo, seg_pair_off, cls, het_list, n_het, cand_list, n_cand, cnv_dad, cnv_mom, row_mark,
+        ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -274,12 +274,27 @@ class Engine:
         return self._empty(self.lib.unfz_scan_work_bytes(int(n)), torch.uint8)
 
     # ------------------------------------------------------------------------------------
+    def _download(self, t: torch.Tensor) -> np.ndarray:
+        """Device bytes -> a fresh host array, staged through a pinned buffer the engine keeps
+        (a pageable D2H copy is several times slower and serialises with the driver)."""
+        nb = t.numel()
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < nb:
+            buf = torch.empty((max(nb, 1 << 20),), dtype=torch.uint8).pin_memory()
+            self._pinned = buf
+        buf[:nb].copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return buf[:nb].numpy().copy()
+
     def run(self, dsites: DeviceSites, dreads: Optional[DeviceReads], plan: Plan, params: L.Params,
             blk_cul: Optional[np.ndarray] = None, time_stages: bool = False, download: bool = True,
-            keep_device: bool = True) -> BatchResult:
-        """One batch through the pipeline.  Two host syncs size the variable outputs (pairs; hits +
-        chain scratch), everything else is asynchronous; all per-DNM results come back in ONE D2H
-        copy.  Device memory comes from three arenas (one torch allocation each)."""
+            keep_device: bool = True, speculative: bool = True) -> BatchResult:
+        """One batch through the pipeline.  The sizes of the variable outputs (pairs; hits + chain
+        scratch) are only known on the device.  The first batch reads them back (two host syncs); later
+        batches allocate from the capacities the engine has seen (+25 %), have the device check them
+        (unfz_check_caps) and run without any host round trip -- if a capacity is exceeded the guarded
+        kernels return at once and the batch is re-run with exact sizes.  All per-DNM results come back
+        in ONE D2H copy.  Device memory comes from three arenas (one torch allocation each)."""
         lib, ctx, dev = self.lib, self.ctx, self.device
         st = torch.cuda.current_stream(dev)
         s = C.c_void_p(st.cuda_stream)
@@ -288,6 +303,8 @@ class Engine:
         N = int(dreads.n_reads) if dreads is not None else 0
         ev: List = []
         launches = 0
+        caps = getattr(self, "_caps", None)
+        spec = bool(speculative and download and caps is not None)
 
         def mark(name):
             if time_stages:
@@ -311,9 +328,18 @@ class Engine:
                 self_.view = {nm: self_.buf[off: off + nb] for nm, off, nb in self_.items}
 
         # ---- plan upload: one H2D ----------------------------------------------------------------
-        hp = np.concatenate([plan.dnm.view(np.uint8).reshape(-1), plan.seg.view(np.uint8).reshape(-1), plan.alleles,
-                             np.zeros(16, np.uint8)])
-        d_plan = torch.from_numpy(hp).to(dev)
+        # (a plan that is run again -- same object, same device -- is already resident)
+        cached = getattr(plan, "_resident", None)
+        if cached is not None and cached[0] == dev and cached[2] == (plan.dnm.nbytes, plan.seg.nbytes, plan.alleles.nbytes):
+            d_plan = cached[1]
+        else:
+            hp = np.concatenate([plan.dnm.view(np.uint8).reshape(-1), plan.seg.view(np.uint8).reshape(-1), plan.alleles,
+                                 np.zeros(16, np.uint8)])
+            d_plan = torch.from_numpy(hp).to(dev)
+            try:
+                plan._resident = (dev, d_plan, (plan.dnm.nbytes, plan.seg.nbytes, plan.alleles.nbytes))
+            except AttributeError:
+                pass
         p_dnm = d_plan.data_ptr()
         p_seg = p_dnm + plan.dnm.nbytes
         p_all = p_seg + plan.seg.nbytes
@@ -329,8 +355,13 @@ class Engine:
         for nm, cnt in r_fields:
             r_off[nm] = acc
             acc += cnt
+        # everything the host reads back sits at the front of the arena: one contiguous download
         z1.add("result", 4 * acc)
+        z1.add("guard", 256)                      # int32 flag + int64 actual[8] at +64
         z1.add("seg_pair_off", 8 * (S + 1))
+        if has_reads:
+            z1.add("off", 8 * (6 * (n + 1) + 1))
+        dl_end = z1.size
         z1.add("row_mark", V)
         z1.add("mark_prefix", 4 * (V + 1))
         e1.add("seg_count", 8 * S)
@@ -338,7 +369,6 @@ class Engine:
         if has_reads:
             z1.add("blk_maxspan", 4 * max(dreads.table.n_blocks, 1))
             z1.add("need", 8 * 6 * n)
-            z1.add("off", 8 * (6 * (n + 1) + 1))
             e1.add("rsum", 16 * N)
             e1.add("row_lb", 4 * N)
             tile_reads = int(lib.unfz_read_scan_tile_reads(dreads.max_l_seq))
@@ -349,6 +379,37 @@ class Engine:
         e1.alloc()
         R = z1.ptr["result"]
         rp = {nm: R + 4 * o for nm, o in r_off.items()}
+
+        # ---- arena 2: per-pair outputs; arena 3: hits + chain scratch + labels ------------------------
+        def arena2(n_pairs_):
+            z, e = Arena(True), Arena(False)
+            e.add("cls", n_pairs_)
+            e.add("het_list", 4 * n_pairs_)
+            e.add("cand_list", 4 * n_pairs_)
+            if has_reads:
+                e.add("site_lo", 4 * n_pairs_)
+                e.add("site_n", 4 * n_pairs_)
+                e.add("seed_win", 16 * n)
+            z.add("cand_evid", n_pairs_ + 8)
+            z.alloc()
+            e.alloc()
+            return z, e
+
+        def arena3(totals_, n_hits_):
+            z, e = Arena(True), Arena(False)
+            nb = lib.unfz_chain_scratch_bytes(*(int(x) for x in totals_), n)
+            e.add("hits", 4 * max(n_hits_, 1))
+            e.add("scratch", nb)
+            z.add("slot_label", int(totals_[0]) + 4)
+            z.add("slot_evid", int(totals_[0]) + 4)
+            z.alloc()
+            e.alloc()
+            return z, e, nb
+
+        if spec:                                   # sizes come from the capacities: allocate before anything runs
+            z2, e2 = arena2(int(caps["pairs"]))
+            if has_reads:
+                z3, e3, nbytes = arena3(caps["chain"], int(caps["hits"]))
         mark("start")
 
         # ---- K0 + scan ---------------------------------------------------------------------
@@ -356,21 +417,26 @@ class Engine:
         self._check(lib.unfz_exclusive_scan_i64(ctx, e1.ptr["seg_count"], z1.ptr["seg_pair_off"], S, e1.ptr["scan_work"], s), "scan(pairs)")
         launches += 4
         mark("window_search")
-        h_pair_off = z1.view["seg_pair_off"].cpu().numpy().view(np.int64)[: S + 1]      # host sync 1
-        n_pairs = int(h_pair_off[S]) if S > 0 else 0
+        guard_ptr, actual_ptr = z1.ptr["guard"], z1.ptr["guard"] + 64
 
-        # ---- arena 2: per-pair outputs ---------------------------------------------------------------
-        z2, e2 = Arena(True), Arena(False)
-        e2.add("cls", n_pairs)
-        e2.add("het_list", 4 * n_pairs)
-        e2.add("cand_list", 4 * n_pairs)
-        if has_reads:
-            e2.add("site_lo", 4 * n_pairs)
-            e2.add("site_n", 4 * n_pairs)
-            e2.add("seed_win", 16 * n)
-        z2.add("cand_evid", n_pairs + 8)
-        z2.alloc()
-        e2.alloc()
+        def check_caps(ptrs, limits, slot):
+            k = len(ptrs)
+            a_t = (C.c_void_p * k)(*ptrs)
+            a_c = (C.c_int64 * k)(*[int(x) for x in limits])
+            self._check(lib.unfz_check_caps(ctx, k, a_t, a_c, guard_ptr, actual_ptr + 8 * slot, s), "check_caps")
+
+        h_pair_off = None
+        if spec:
+            lib.unfz_ctx_set_guard(ctx, guard_ptr)
+            n_pairs = int(caps["pairs"])                                                 # capacity, not the total
+            check_caps([z1.ptr["seg_pair_off"] + 8 * S], [n_pairs], 0)
+            launches += 1
+        else:
+            h_pair_off = z1.view["seg_pair_off"].cpu().numpy().view(np.int64)[: S + 1]      # host sync 1
+            n_pairs = int(h_pair_off[S]) if S > 0 else 0
+
+        if not spec:
+            z2, e2 = arena2(n_pairs)
         mark("alloc1")
         self._check(lib.unfz_classify_sites(ctx, sc, p_seg, rp["seg_row_lo"], z1.ptr["seg_pair_off"], S, n_pairs,
                                             C.byref(params), e2.ptr["cls"], s), "classify_sites")
@@ -391,12 +457,26 @@ class Engine:
 
         if has_reads:
             rc_ = C.byref(dreads.cols)
-            sb = np.full(max(dreads.table.n_blocks, 1), -1, dtype=np.int32)
-            for rb, sblk in plan.rblk_sblk.items():
-                sb[rb] = sblk
-            dreads.blk_sblk.copy_(torch.from_numpy(sb))
-            if blk_cul is not None:
-                dreads.blk_cul[: blk_cul.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(blk_cul, dtype=np.float64)))
+            # read block -> site block map and the per-block insert bound: uploaded unless the same plan and
+            # bounds are already bound to these read columns
+            cul_bytes = None if blk_cul is None else np.ascontiguousarray(blk_cul, dtype=np.float64).tobytes()
+            token = getattr(plan, "_token", None)
+            if token is None:
+                token = object()
+                try:
+                    plan._token = token
+                except AttributeError:
+                    pass
+            bound = (token, cul_bytes)
+            if getattr(dreads, "_bound", None) != bound:
+                sb = np.full(max(dreads.table.n_blocks, 1), -1, dtype=np.int32)
+                if plan.rblk_sblk:
+                    keys = np.fromiter(plan.rblk_sblk.keys(), dtype=np.int64, count=len(plan.rblk_sblk))
+                    sb[keys] = np.fromiter(plan.rblk_sblk.values(), dtype=np.int32, count=len(plan.rblk_sblk))
+                dreads.blk_sblk.copy_(torch.from_numpy(sb))
+                if blk_cul is not None:
+                    dreads.blk_cul[: blk_cul.shape[0]].copy_(torch.from_numpy(np.frombuffer(cul_bytes, dtype=np.float64).copy()))
+                dreads._bound = bound
             # ---- K2 + scan(tile hit totals) + chain sizing; ONE host sync for all the sizes ------------
             off_ptr = z1.ptr["off"]
             total_hits_ptr = off_ptr + 8 * 6 * (n + 1)
@@ -415,23 +495,24 @@ class Engine:
                                             e2.ptr["seed_win"], s), "chain_size")
             self._check(lib.unfz_exclusive_scan_rows_i64(ctx, z1.ptr["need"], off_ptr, 6, n, s), "scan(need)")
             launches += 2
-            h_all = z1.view["off"].cpu().numpy().view(np.int64)                          # host sync 2
-            h_off = h_all[: 6 * (n + 1)].reshape(6, n + 1)
-            n_hits = int(h_all[6 * (n + 1)])
-            totals = np.ascontiguousarray(h_off[:, n]).astype(np.int64)
+            h_off = None
+            if spec:
+                totals = np.asarray(caps["chain"], dtype=np.int64).copy()
+                n_hits = int(caps["hits"])
+                check_caps([off_ptr + 8 * ((i + 1) * (n + 1) - 1) for i in range(6)] + [total_hits_ptr],
+                           list(totals) + [n_hits], 1)
+                launches += 1
+            else:
+                h_all = z1.view["off"].cpu().numpy().view(np.int64)                      # host sync 2
+                h_off = h_all[: 6 * (n + 1)].reshape(6, n + 1)
+                n_hits = int(h_all[6 * (n + 1)])
+                totals = np.ascontiguousarray(h_off[:, n]).astype(np.int64)
             mark("chain_size")
             if n_hits >= 2**32:
                 raise RuntimeError("more than 2^32 read x site hits in one batch")
             res.n_hits = n_hits
-            # ---- arena 3: hits + chain scratch + labels -------------------------------------------------
-            z3, e3 = Arena(True), Arena(False)
-            nbytes = lib.unfz_chain_scratch_bytes(*(int(x) for x in totals), n)
-            e3.add("hits", 4 * max(n_hits, 1))
-            e3.add("scratch", nbytes)
-            z3.add("slot_label", int(totals[0]) + 4)
-            z3.add("slot_evid", int(totals[0]) + 4)
-            z3.alloc()
-            e3.alloc()
+            if not spec:
+                z3, e3, nbytes = arena3(totals, n_hits)
             mark("alloc3")
             self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, z1.ptr["row_mark"], z1.ptr["mark_prefix"], e1.ptr["rsum"],
                                                    e1.ptr["row_lb"], e1.ptr["tile_base"], tile_reads, e3.ptr["hits"], s),
@@ -452,14 +533,47 @@ class Engine:
                       tile_base=e1.view["tile_base"].view(torch.int32), tile_reads=tile_reads, slot_label=z3.view["slot_label"],
                       slot_evid=z3.view["slot_evid"], row_mark=z1.view["row_mark"],
                       mark_prefix=z1.view["mark_prefix"].view(torch.int32), _keep3=(z3, e3))
-            res.slot_off = h_off[0].copy()
+            if h_off is not None:
+                res.slot_off = h_off[0].copy()
         self._check(lib.unfz_summarize(ctx, p_dnm, n, rp["tally"], rp["cnv_dad"], rp["cnv_mom"], rp["n_cand"], C.byref(params),
                                        rp["calls_s"], rp["calls_a"], s), "summarize")
         launches += 1
         mark("summarize")
         # ---- results: ONE device-to-host copy of the int32 result block ----------------------------
+        if spec:
+            lib.unfz_ctx_set_guard(ctx, None)
         if download:
-            hr = z1.view["result"].cpu().numpy().view(np.int32)
+            front = self._download(z1.buf[:dl_end])
+            item = {nm: (off, nb) for nm, off, nb in z1.items}
+            sect = lambda nm: front[item[nm][0]: item[nm][0] + item[nm][1]]
+            hr = sect("result").view(np.int32)
+            if spec:
+                g_ = sect("guard")
+                actual = g_[64: 64 + 64].view(np.int64)
+                if int(g_[:4].view(np.int32)[0]) != 0:
+                    # a capacity was exceeded: nothing was written out of bounds, run again with exact sizes
+                    self._caps = None
+                    dv.clear()
+                    return self.run(dsites, dreads, plan, params, blk_cul=blk_cul, time_stages=time_stages,
+                                    download=download, keep_device=keep_device, speculative=False)
+                h_pair_off = sect("seg_pair_off").view(np.int64)[: S + 1].copy()
+                res.seg_pair_off = h_pair_off
+                res.n_pairs = int(actual[0])
+                if has_reads:
+                    h_off = sect("off").view(np.int64)[: 6 * (n + 1)].reshape(6, n + 1)
+                    res.slot_off = h_off[0].copy()
+                    res.n_hits = int(actual[7])
+            # capacities for the next batch: what this one needed, plus a quarter
+            need_now = {"pairs": res.n_pairs, "hits": res.n_hits,
+                        "chain": [int(x) for x in (h_off[:, n] if (has_reads and h_off is not None) else np.zeros(6, np.int64))]}
+            grow = lambda v: int(v * 1.25) + 4096
+            if caps is None:
+                self._caps = {"pairs": grow(need_now["pairs"]), "hits": grow(need_now["hits"]),
+                              "chain": [grow(v) for v in need_now["chain"]]}
+            else:
+                caps["pairs"] = max(caps["pairs"], grow(need_now["pairs"]) if need_now["pairs"] > 0.9 * caps["pairs"] else 0)
+                caps["hits"] = max(caps["hits"], grow(need_now["hits"]) if need_now["hits"] > 0.9 * caps["hits"] else 0)
+                caps["chain"] = [max(c, grow(v) if v > 0.9 * c else 0) for c, v in zip(caps["chain"], need_now["chain"])]
             g = lambda nm, cnt: hr[r_off[nm]: r_off[nm] + cnt]
             res.seg_row_lo = g("seg_row_lo", S)
             res.n_het, res.n_cand = g("n_het", n), g("n_cand", n)

@@ -275,16 +275,13 @@ class Engine:
 
     # ------------------------------------------------------------------------------------
     def _download(self, t: torch.Tensor) -> np.ndarray:
-        """Device bytes -> a fresh host array, staged through a pinned buffer the engine keeps
-        (a pageable D2H copy is several times slower and serialises with the driver)."""
-        nb = t.numel()
-        buf = getattr(self, "_pinned", None)
-        if buf is None or buf.numel() < nb:
-            buf = torch.empty((max(nb, 1 << 20),), dtype=torch.uint8).pin_memory()
-            self._pinned = buf
-        buf[:nb].copy_(t, non_blocking=True)
+        """Device bytes -> host array in pinned memory (torch's caching host allocator recycles the
+        buffers; a pageable D2H copy is several times slower and serialises with the driver).  The
+        arrays of the result are views of it."""
+        buf = torch.empty((t.numel(),), dtype=torch.uint8, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return buf[:nb].numpy().copy()
+        return buf.numpy()
 
     def run(self, dsites: DeviceSites, dreads: Optional[DeviceReads], plan: Plan, params: L.Params,
             blk_cul: Optional[np.ndarray] = None, time_stages: bool = False, download: bool = True,
@@ -359,9 +356,10 @@ class Engine:
         z1.add("result", 4 * acc)
         z1.add("guard", 256)                      # int32 flag + int64 actual[8] at +64
         z1.add("seg_pair_off", 8 * (S + 1))
+        dl_end = z1.size
         if has_reads:
             z1.add("off", 8 * (6 * (n + 1) + 1))
-        dl_end = z1.size
+            dl_end += 8 * (n + 1)                 # row 0 of `off` (slot offsets); the totals travel in `guard`
         z1.add("row_mark", V)
         z1.add("mark_prefix", 4 * (V + 1))
         e1.add("seg_count", 8 * S)
@@ -560,12 +558,14 @@ class Engine:
                 res.seg_pair_off = h_pair_off
                 res.n_pairs = int(actual[0])
                 if has_reads:
-                    h_off = sect("off").view(np.int64)[: 6 * (n + 1)].reshape(6, n + 1)
-                    res.slot_off = h_off[0].copy()
+                    o0 = item["off"][0]
+                    res.slot_off = front[o0: o0 + 8 * (n + 1)].view(np.int64).copy()
                     res.n_hits = int(actual[7])
+                    chain_now = [int(x) for x in actual[1:7]]
+            elif has_reads:
+                chain_now = [int(x) for x in h_off[:, n]]
             # capacities for the next batch: what this one needed, plus a quarter
-            need_now = {"pairs": res.n_pairs, "hits": res.n_hits,
-                        "chain": [int(x) for x in (h_off[:, n] if (has_reads and h_off is not None) else np.zeros(6, np.int64))]}
+            need_now = {"pairs": res.n_pairs, "hits": res.n_hits, "chain": chain_now if has_reads else [0] * 6}
             grow = lambda v: int(v * 1.25) + 4096
             if caps is None:
                 self._caps = {"pairs": grow(need_now["pairs"]), "hits": grow(need_now["hits"]),

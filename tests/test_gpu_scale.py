@@ -159,3 +159,45 @@ def test_long_reads_take_the_chunked_scan_kernel(engine):
     for r in range(0, ds.reads.n_reads, 3):
         assert bool(rs["flags"][r] & L.RS_GOOD_CONC) == port.goodread(bam, r, p), r
         assert bool(rs["flags"][r] & L.RS_GOOD_DISC) == port.goodread(bam, r, p, True), r
+
+
+def test_speculative_sizing_equals_the_exact_path_and_survives_an_overflow():
+    """Engine.run sizes its variable buffers from the previous batch (device-side capacity check, guarded
+    kernels).  A batch that fits, a batch that overflows every capacity (re-run on the exact path) and a
+    batch after the capacities grew must all give the results of the exact, two-sync path."""
+    from unfazed_b200.engine import Engine
+    from unfazed_b200.phaser import BatchPhaser
+    eng = Engine(0)
+    ds = make_dataset(SynthConfig(dnms_per_trio=120, seed=909, coverage=20.0))
+    bp = BatchPhaser(eng, ds.sites, ds.reads, ds.pedigrees)
+    small, large = ds.dnms[:10], ds.dnms
+
+    def fields(res):
+        return (res.n_pairs, res.n_hits, res.tally.copy(), res.calls_strict.copy(), res.calls_ambiguous.copy(),
+                res.seg_pair_off.copy(), res.slot_off.copy(), res.n_het.copy(), res.n_cand.copy())
+
+    def same(a, b):
+        return all(np.array_equal(x, y) for x, y in zip(a, b))
+
+    eng._caps = None
+    exact_small = fields(bp.run(small, [])[0])            # first batch: exact path, capacities recorded
+    caps_small = dict(eng._caps)
+    exact_large_ref = None
+    spec_small = fields(bp.run(small, [])[0])             # fits: speculative
+    assert same(exact_small, spec_small)
+    over = fields(bp.run(large, [])[0])                   # exceeds every capacity: guard + exact re-run
+    assert eng._caps["pairs"] > caps_small["pairs"] and eng._caps["hits"] > caps_small["hits"]
+    eng._caps = None
+    exact_large_ref = fields(bp.run(large, [])[0])
+    assert same(over, exact_large_ref)
+    spec_large = fields(bp.run(large, [])[0])             # now speculative with the grown capacities
+    assert same(spec_large, exact_large_ref)
+    spec_small2 = fields(bp.run(small, [])[0])            # a smaller batch inside large capacities
+    assert same(spec_small2, exact_small)
+    # labels / evidence accessors work on speculatively sized buffers
+    res, _ = bp.run(large, [])
+    res_exact = None
+    eng._caps = None
+    res_exact, _ = bp.run(large, [])
+    for d in range(0, len(large), 17):
+        assert bp.labels(res, d) == bp.labels(res_exact, d)

@@ -261,15 +261,31 @@ def run_b200(args):
     host_site_t = _pin_table(ds.sites)
     host_read_t = _pin_table(ds.reads)
 
-    def step_e2e():
+    e2e_parts = {}
+
+    def step_e2e(probe=False):
         # the H2D copies are asynchronous (pinned source): the host plans the windows while they fly
+        if probe:
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+        h0 = time.perf_counter()
         dsites = eng.upload_sites(host_site_t, pin=False)
         dreads = eng.upload_reads(host_read_t, pin=False)
+        h1 = time.perf_counter()
+        if probe:
+            eb.record()
         pl = plan_find(ds.dnms, ds.pedigrees, bp.sidx, ds.reads, **plan_kw)
-        return eng.run(dsites, dreads, pl, params, blk_cul=cul, download=True, keep_device=False)
+        h2 = time.perf_counter()
+        out = eng.run(dsites, dreads, pl, params, blk_cul=cul, download=True, keep_device=False)
+        h3 = time.perf_counter()
+        if probe:       # one untimed step: where the end-to-end time goes
+            e2e_parts.update(h2d_copies_gpu_ms=ea.elapsed_time(eb), issue_uploads_host_ms=(h1 - h0) * 1e3,
+                             plan_host_ms=(h2 - h1) * 1e3, run_until_results_host_ms=(h3 - h2) * 1e3)
+        return out
 
     for _ in range(2):
         step_e2e()
+    step_e2e(probe=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -357,7 +373,8 @@ def run_b200(args):
             "roofline": roof,
             "e2e": {"value": all_dnms / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_ms,
-                    "includes": "host window planning + H2D of all site/read columns + kernels + D2H of tallies/calls"},
+                    "includes": "host window planning + H2D of all site/read columns + kernels + D2H of tallies/calls",
+                    "breakdown_ms": {k: round(v, 3) for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }

@@ -82,7 +82,7 @@ class DeviceReads:
     def __init__(self, table: ReadTable, device: torch.device, pin: bool = False):
         self.table = table
         self.n_reads = table.n_reads
-        self.max_l_seq = int(table.hdr["l_seq"].max()) if table.n_reads else 0
+        self.max_l_seq = table.max_l_seq()
         up = lambda a, pad=0: _to_device(np.ascontiguousarray(a), device, pin, pad)
         self.blk_off = up(table.blk_off.astype(np.int64))
         self.hdr = up(table.hdr.view(np.uint8).reshape(-1))

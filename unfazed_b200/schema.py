@@ -149,6 +149,14 @@ class ReadTable:
     def n_reads(self) -> int:
         return int(self.hdr.shape[0])
 
+    def max_l_seq(self) -> int:
+        """Longest read (cached: a pass over the strided header field costs tens of ms at 20 M reads)."""
+        m = self.__dict__.get("_max_l_seq")
+        if m is None or m[0] != self.hdr.shape[0]:
+            m = (self.hdr.shape[0], int(self.hdr["l_seq"].max()) if self.hdr.shape[0] else 0)
+            self.__dict__["_max_l_seq"] = m
+        return m[1]
+
     @property
     def n_blocks(self) -> int:
         return int(self.blk_kid.shape[0])

@@ -108,27 +108,30 @@ __device__ __forceinline__ char hit_char(uint32_t w) {
 }
 
 // hit word of (read e, site row) or 0
+// The lookups below are chains of dependent gathers; everything that does not depend on an earlier
+// result is loaded up front (no early-out between the loads), so a lookup costs two round trips, not four.
 __device__ __forceinline__ uint32_t hit_lookup(const ChainArgs& A, int64_t e, int64_t row) {
     const UnfzReadSum s = load_rsum(A.rsum + e);
-    const int k = __ldg(A.mp + row) - s.fmark;
+    const int mp = __ldg(A.mp + row);
+    const uint32_t tb = __ldg(A.hit_tile_base + (uint32_t)e / (uint32_t)A.hit_tile_reads);
+    const int k = mp - s.fmark;
     if (k < 0 || k >= (int)s.cnt) return 0;
-    const int64_t base = (int64_t)__ldg(A.hit_tile_base + (uint32_t)e / (uint32_t)A.hit_tile_reads) + s.hoff;
-    return __ldg(A.hits + base + k);
+    return __ldg(A.hits + (int64_t)tb + s.hoff + k);
 }
 
 // goodread + insert + mate + None-count + mate-overlap (read_collector.py:181-214, :395-418)
 __device__ bool pair_ok(const ChainArgs& A, int64_t r, bool ext) {
     const UnfzReadSum s = load_rsum(A.rsum + r);
+    const int4 hr = __ldg(reinterpret_cast<const int4*>(A.reads.hdr + r));      // start, tlen, mate, cigar_off
     uint32_t need = UNFZ_RS_GOOD_CONC | UNFZ_RS_INS_OK | UNFZ_RS_HAS_MATE | UNFZ_RS_NONE_OK;
     if (ext) need |= UNFZ_RS_EXT_OK;
-    if ((s.flags & need) != need) return false;
-    const int64_t m = rd_mate(A.reads, r);
+    const bool ok_r = (s.flags & need) == need;                                  // HAS_MATE: mate >= 0
+    const int64_t m = ok_r ? (int64_t)hr.z : r;
     const UnfzReadSum sm = load_rsum(A.rsum + m);
+    const int32_t m0 = rd_start(A.reads, m);
     const uint32_t needm = UNFZ_RS_GOOD_CONC | UNFZ_RS_NONE_OK;
-    if ((sm.flags & needm) != needm) return false;
-    const int32_t r0 = rd_start(A.reads, r), r1 = s.end, m0 = rd_start(A.reads, m), m1 = sm.end;
-    if ((m0 <= r0 && r0 <= m1) || (m0 <= r1 && r1 <= m1)) return false;
-    return true;
+    const int32_t r0 = hr.x, r1 = s.end, m1 = sm.end;
+    return ok_r && (sm.flags & needm) == needm && !((m0 <= r0 && r0 <= m1) || (m0 <= r1 && r1 <= m1));
 }
 
 // snv_match_alleles (:296-336) through get_allele_at (:56-73): 0 none, 1 ref, 2 alt
@@ -328,10 +331,10 @@ __device__ int bisect_pivot(const int32_t* __restrict__ spos, int n, int32_t sta
 // bits2-3 target (needs the position in the PRIMARY read and base quality >= min)
 __device__ uint8_t allele_info(const ChainArgs& A, const Scratch& S, int64_t e0, int64_t row, char ref, char alt) {
     if (e0 < 0) return 0;
+    const int64_t e1 = rd_mate(A.reads, e0);          // in flight with the first lookup
     const uint32_t h0 = hit_lookup(A, e0, row);
     uint32_t h = h0;
     if (!(h0 & 0xffffu)) {
-        const int64_t e1 = rd_mate(A.reads, e0);
         if (e1 < 0) return 0;
         h = hit_lookup(A, e1, row);
         if (!(h & 0xffffu)) return 0;

@@ -948,6 +948,29 @@ __device__ __forceinline__ int64_t warp_max64(int64_t v) {
     return v;
 }
 
+// lb_start by a whole warp: 32 probes per round trip (all lanes get the result)
+__device__ __forceinline__ int64_t warp_lb_start(const UnfzReadCols& R, int64_t lo, int64_t hi, int64_t v, int lane) {
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 32) / 33;
+        const int64_t i = lo + (int64_t)(lane + 1) * step - 1;
+        const bool lt = i < hi && (int64_t)rd_start(R, i) < v;
+        const int k = __popc(__ballot_sync(0xffffffffu, lt));
+        const int64_t nhi = k < 32 ? min(hi, lo + (int64_t)(k + 1) * step - 1) : hi;
+        lo += (int64_t)k * step;
+        hi = nhi;
+    }
+    const bool lt = lo + lane < hi && (int64_t)rd_start(R, lo + lane) < v;
+    return lo + __popc(__ballot_sync(0xffffffffu, lt));
+}
+// lb_start when the answer is expected a few dozen reads after lo: gallop, then bisect
+__device__ __forceinline__ int64_t lb_start_near(const UnfzReadCols& R, int64_t lo, int64_t hi, int64_t v) {
+    int64_t step = 32, top = lo;
+    while (top + step < hi && (int64_t)rd_start(R, top + step - 1) < v) { top += step; step <<= 1; }
+    return lb_start(R, top, min(hi, top + step), v);
+}
+
+constexpr int CS_HP = 128;                 // het positions staged per warp
+
 __global__ void __launch_bounds__(128)
 chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_t* __restrict__ seg_pair_off,
                   UnfzSiteCols sites, UnfzReadCols reads, const UnfzReadSum* __restrict__ rsum,
@@ -957,9 +980,11 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
                   int32_t* __restrict__ site_lo, int32_t* __restrict__ site_n, int32_t* __restrict__ seed_win,
                   const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
+    __shared__ int32_t s_hp[4][CS_HP];
     const int lane = threadIdx.x & 31;
     const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_dnms) return;
+    int32_t* hp = s_hp[threadIdx.x >> 5];
     const UnfzDnm dn = dnms[d];
     int64_t nd[6] = {0, 0, 0, 0, 0, 0};
     int64_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
@@ -986,21 +1011,23 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
         int64_t incs = 0;
         for (int i = lane; i < nh; i += 32) {
             const int64_t p = sites.pos[H[i]];
+            if (i < CS_HP) hp[i] = (int32_t)p;
             if (p < mid) { minA = min(minA, p); maxA = max(maxA, p + 1); }
             else { minB = min(minB, p); maxB = max(maxB, p + 1); }
             const int64_t a = lb_start(reads, blk_lo, blk_hi, p - maxspan + 1);
-            const int64_t b = lb_start(reads, a, blk_hi, p + 1);
+            const int64_t b = lb_start_near(reads, a, blk_hi, p + 1);
             site_lo[lbase + i] = (int32_t)(a - blk_lo);
             site_n[lbase + i] = (int32_t)(b - a);
             incs += b - a;
         }
         minA = warp_min64(minA); maxA = warp_max64(maxA); minB = warp_min64(minB); maxB = warp_max64(maxB);
         nd[1] = warp_sum64(incs);
-        a_lo = lb_start(reads, blk_lo, blk_hi, minA - maxspan + 1);
-        a_hi = lb_start(reads, a_lo, blk_hi, maxA);
+        __syncwarp();
+        a_lo = warp_lb_start(reads, blk_lo, blk_hi, minA - maxspan + 1, lane);
+        a_hi = warp_lb_start(reads, a_lo, blk_hi, maxA, lane);
         if (maxB > minB) {
-            b_lo = lb_start(reads, blk_lo, blk_hi, minB - maxspan + 1);
-            b_hi = lb_start(reads, b_lo, blk_hi, maxB);
+            b_lo = warp_lb_start(reads, blk_lo, blk_hi, minB - maxspan + 1, lane);
+            b_hi = warp_lb_start(reads, b_lo, blk_hi, maxB, lane);
             if (b_lo <= a_hi) { a_hi = max(a_hi, b_hi); a_lo = min(a_lo, b_lo); b_lo = b_hi = 0; }
         }
         nd[0] = ((a_hi - a_lo) + (b_hi - b_lo) + 3) & ~(int64_t)3;   // word-aligned label/evidence regions
@@ -1008,8 +1035,8 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
         int64_t seeds = 0, sincs = 0;
         for (int wdx = 0; wdx < (sv ? 2 : 1); ++wdx) {
             const int64_t flo = wdx ? sb_lo : sa_lo, fhi = wdx ? sb_hi : sa_hi;
-            const int64_t a = lb_start(reads, blk_lo, blk_hi, flo - maxspan + 1);
-            const int64_t b = lb_start(reads, a, blk_hi, fhi);
+            const int64_t a = warp_lb_start(reads, blk_lo, blk_hi, flo - maxspan + 1, lane);
+            const int64_t b = warp_lb_start(reads, a, blk_hi, fhi, lane);
             if (lane == 0) { seed_win[4 * (int64_t)d + 2 * wdx] = (int32_t)a; seed_win[4 * (int64_t)d + 2 * wdx + 1] = (int32_t)b; }
             seeds += 2 * (b - a);
             for (int64_t r = a + lane; r < b; r += 32) {
@@ -1019,9 +1046,16 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
                     if (e < 0) continue;
                     const int64_t st = reads.hdr[e].start, en = rsum[e].end;
                     int l = 0, h = nh;
-                    while (l < h) { const int m2 = (l + h) >> 1; if (sites.pos[H[m2]] < st) l = m2 + 1; else h = m2; }
-                    int u = l; h = nh;
-                    while (u < h) { const int m2 = (u + h) >> 1; if (sites.pos[H[m2]] <= en) u = m2 + 1; else h = m2; }
+                    int u;
+                    if (nh <= CS_HP) {                               // het positions staged per warp
+                        while (l < h) { const int m2 = (l + h) >> 1; if (hp[m2] < st) l = m2 + 1; else h = m2; }
+                        u = l; h = nh;
+                        while (u < h) { const int m2 = (u + h) >> 1; if (hp[m2] <= en) u = m2 + 1; else h = m2; }
+                    } else {
+                        while (l < h) { const int m2 = (l + h) >> 1; if (sites.pos[H[m2]] < st) l = m2 + 1; else h = m2; }
+                        u = l; h = nh;
+                        while (u < h) { const int m2 = (u + h) >> 1; if (sites.pos[H[m2]] <= en) u = m2 + 1; else h = m2; }
+                    }
                     sincs += u - l;
                 }
             }

@@ -13,6 +13,7 @@ Pipeline (one stream, in order):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -302,6 +303,9 @@ class Engine:
         launches = 0
         caps = getattr(self, "_caps", None)
         spec = bool(speculative and download and caps is not None)
+        reuse = not keep_device and not os.environ.get("UNFZ_NO_ARENA_REUSE")
+        pool = self.__dict__.setdefault("_arena_pool", {})
+        arenas: List = []
 
         def mark(name):
             if time_stages:
@@ -318,8 +322,17 @@ class Engine:
                 self.size += (int(nbytes) + 255) & ~255
 
             def alloc(self_):
-                fn = torch.zeros if self_.zero else torch.empty
-                self_.buf = fn((max(self_.size, 256),), dtype=torch.uint8, device=dev)
+                # a run that keeps nothing on the device hands its buffers back (see the end of run());
+                # the next run with the same layout reuses them and only clears the zero-initialised ones
+                self_.key = (self_.zero, tuple(self_.items))
+                buf = pool.pop(self_.key, None) if reuse else None
+                if buf is None:
+                    fn = torch.zeros if self_.zero else torch.empty
+                    buf = fn((max(self_.size, 256),), dtype=torch.uint8, device=dev)
+                elif self_.zero:
+                    buf.zero_()
+                self_.buf = buf
+                arenas.append(self_)
                 base = self_.buf.data_ptr()
                 self_.ptr = {nm: base + off for nm, off, _ in self_.items}
                 self_.view = {nm: self_.buf[off: off + nb] for nm, off, nb in self_.items}
@@ -590,4 +603,8 @@ class Engine:
                 res.timings_ms[n1] = res.timings_ms.get(n1, 0.0) + e0.elapsed_time(e1_)
         if not keep_device:
             dv.clear()
+            if len(pool) > 12:
+                pool.clear()
+            for a_ in arenas:
+                pool[a_.key] = a_.buf
         return res

@@ -787,10 +787,11 @@ chain_kernel(ChainArgs A) {
             __syncthreads();
             // b. earliest claiming key per unlabelled pair
             for (int k = tid; k < n_inc; k += CH_THREADS) {
+                const unsigned long long bk = bestkey[inc_site[k]];
+                if (bk == KEY_NONE) continue;                        // no finder at this site: no gathers
                 const int x = inc_x[k];
                 if (label[x] != 0 || !(inc_al[k] >> 2)) continue;
-                const unsigned long long bk = bestkey[inc_site[k]];
-                if (bk != KEY_NONE) atomicMin(minkey + x, bk);
+                atomicMin(minkey + x, bk);
             }
             __syncthreads();
             // c. claim, one warp per site, in the order of the site's read list
@@ -834,6 +835,9 @@ chain_kernel(ChainArgs A) {
             if (assigned == 0) break;
             // e. commit the new level
             for (int k = tid; k < n_inc; k += CH_THREADS) {
+                // an incidence at a site without a finder neither claimed nor touched minkey in (b): if its pair
+                // was touched through another site, that incidence re-arms / commits it
+                if (bestkey[inc_site[k]] == KEY_NONE) continue;
                 const int x = inc_x[k];
                 if (label[x] != 0) continue;
                 const int t = tmp[x];

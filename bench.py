@@ -226,6 +226,11 @@ def run_b200(args):
     def step_resident():
         return eng.run(bp.dsites, bp.dreads, plan, params, blk_cul=cul, download=True, keep_device=False)
 
+    # The synthetic dataset is millions of long-lived Python objects; a generation-2 garbage collection in
+    # the middle of a step costs tens of milliseconds of host time.  Collect once, then park the survivors.
+    import gc
+    gc.collect()
+    gc.freeze()
     res = None
     for _ in range(max(args.warmup, 3)):
         res = step_resident()

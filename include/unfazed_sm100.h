@@ -110,7 +110,8 @@ typedef struct {
     const double*   blk_cul;     /* [n_blocks] concordant_upper_len of the kid */
     const UnfzRead* hdr;
     const uint32_t* cigar;       /* BAM encoding len<<4|op */
-    const uint8_t*  qual;        /* bit7: base is not ACGT */
+    const uint8_t*  qual;        /* bit7: base is not ACGT; readable for 32 bytes past n_qual (the scan copies
+                                    16-byte chunks) */
     const uint8_t*  seq2;        /* 2-bit bases, base i at bits 2*(i&3) of byte i>>2 */
     int64_t         n_qual;
     int64_t         n_cigar;

@@ -2,12 +2,13 @@
 // and the read-by-site allele lookup.
 //
 // read_scan is the bandwidth kernel of the read path: per read it must see the 32 B header, the
-// CIGAR words and every quality byte.  Reads are stored in file order, so the quality bytes of a
-// tile of consecutive reads are one contiguous span: a single elected thread moves that span into
-// shared memory with TMA bulk copies (cp.async.bulk, completion on an mbarrier) while the other
-// threads walk their CIGARs; then every thread counts the low-quality bases of its own read out of
-// shared memory with 4-byte SIMD compares.  Several CTAs are resident per SM, so one CTA's bulk
-// copy overlaps the others' compute.
+// CIGAR words and every quality byte.  Reads are stored in file order, so the quality bytes (and the
+// CIGAR words) of consecutive reads are one contiguous span that is staged in shared memory by
+// asynchronous copies while earlier reads are being processed; every thread then counts the
+// low-quality bases of its own read out of shared memory with 4-byte SIMD compares.
+//   read_scan_warp_kernel  one cp.async pipeline per warp, 32 reads per tile (the kernel that runs)
+//   read_scan_kernel       CTA-wide tiles with chunked TMA bulk copies (cp.async.bulk + mbarrier) for
+//                          reads too long for a warp's slice
 #include "common.cuh"
 
 namespace {

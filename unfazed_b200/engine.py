@@ -88,7 +88,7 @@ class DeviceReads:
         self.blk_off = up(table.blk_off.astype(np.int64))
         self.hdr = up(table.hdr.view(np.uint8).reshape(-1))
         self.cigar = up(table.cigar)
-        # tail padding: the TMA bulk copies round the staged span up to 16 B
+        # tail padding: the scan's asynchronous copies round the staged span up to 16 B
         self.qual = up(table.qual, 32)
         self.seq2 = up(table.seq2, 16)
         self.blk_sblk = torch.full((max(table.n_blocks, 1),), -1, dtype=torch.int32, device=device)

@@ -249,7 +249,10 @@ int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* site
                    int32_t max_l_seq /* longest read, 0 = unknown: picks the staging strategy */, UnfzReadSum* out,
                    int32_t* row_lb /* [n_reads] first site row with pos >= start (input of unfz_read_site_alleles) */,
                    int32_t* blk_maxspan /* [n_blocks], zeroed by the caller: max(end-start) */,
-                   uint32_t* tile_tot /* [ceil(n_reads / tile_reads)] */, void* stream);
+                   uint32_t* tile_tot /* [ceil(n_reads / tile_reads)] */,
+                   uint32_t* tile_info /* [2 * n_tiles] or NULL: per tile {bit i: read i has hits, read block of the
+                                          tile's first read}; lets the lookup skip reads without hits unseen */,
+                   void* stream);
 
 /* Read-by-site allele lookup: get_reference_positions(full_length=True).index(pos) + base +
  * quality for every (read x marked site) overlap (get_allele_at :56-73, phase_by_reads
@@ -258,7 +261,8 @@ int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* site
 int unfz_read_site_alleles(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                            const uint8_t* row_mark, const int32_t* mark_prefix,
                            const UnfzReadSum* rsum, const int32_t* row_lb, const uint32_t* tile_base,
-                           int32_t tile_reads, uint32_t* hits, void* stream);
+                           int32_t tile_reads, uint32_t* hits, const uint32_t* tile_info /* from unfz_read_scan, or NULL */,
+                           void* stream);
 
 /* Sizing pass of unfz_chain_tally: per DNM read window and scratch needs (need[6][n_dnms] int64:
  * window slots, het incidences, seed entries, seed incidences, het sites, candidate sites). */

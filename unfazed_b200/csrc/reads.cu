@@ -93,7 +93,7 @@ __device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, in
 __global__ void __launch_bounds__(RS_THREADS)
 read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
                  UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb, int32_t* __restrict__ blk_maxspan,
-                 uint32_t* __restrict__ tile_tot, const int32_t* __restrict__ guard) {
+                 uint32_t* __restrict__ tile_tot, uint2* __restrict__ tile_info, const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* qbuf = smem;                                             // RS_QBUF + 16
@@ -220,6 +220,9 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
             hoff = (uint32_t)(x - cnt);
             const int64_t rw = r0 + (threadIdx.x & ~31);
             if (lane == 31 && rw < n) tile_tot[rw >> 5] = (uint32_t)x;
+            const unsigned has = __ballot_sync(0xffffffffu, cnt > 0);
+            if (tile_info && lane == 0 && rw < n)                 // who has hits + the block of the tile's first read
+                tile_info[rw >> 5] = make_uint2(has, (uint32_t)(upper_bound_dev(reads.blk_off, (int64_t)s_rb0, (int64_t)reads.n_blocks + 1, rw) - 1));
         }
         // ---- low-quality bases out of the staged span ---------------------------------------
         int low = 0;
@@ -355,7 +358,8 @@ struct WpSpan {               // where the staged spans of a tile start, and whe
 __global__ void __launch_bounds__(WP_THREADS, WP_MINB)
 read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
                       int qslice, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
-                      int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot, const int32_t* __restrict__ guard) {
+                      int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot, uint2* __restrict__ tile_info,
+                      const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -604,6 +608,10 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
         if (lane == 31) tile_tot[T] = (uint32_t)incl;
+        {
+            const unsigned has = __ballot_sync(FULL, cnt > 0);    // who has hits + the tile's read block, for the lookup kernel
+            if (tile_info && lane == 0) tile_info[T] = make_uint2(has, (uint32_t)rb0);
+        }
         if (live) {
             UnfzReadSum o;
             o.end = end; o.fmark = fmark; o.flags = (uint16_t)flags; o.cnt = (uint16_t)cnt;
@@ -649,14 +657,24 @@ __global__ void __launch_bounds__(256)
 read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
                          const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
                          const int32_t* __restrict__ row_lb, const uint32_t* __restrict__ tile_base, int32_t tile_reads,
-                         uint32_t* __restrict__ hits, const int32_t* __restrict__ guard) {
+                         uint32_t* __restrict__ hits, const uint2* __restrict__ tile_info, const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= reads.n_reads) return;
+    // 8 bytes per 32 reads say who has hits at all (84 % of the reads of a 30x trio have none and their
+    // summaries are never loaded) and in which read block the tile starts
+    int rb_hint = -1;
+    if (tile_info) {
+        const uint2 ti = __ldg(tile_info + (r >> 5));
+        if (!((ti.x >> (r & 31)) & 1u)) return;
+        rb_hint = (int)ti.y;
+    }
     const UnfzReadSum s = load_rsum(rsum + r);
     if (s.cnt == 0) return;
     const UnfzRead h = load_read(reads.hdr + r);
-    const int rb = (int)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r) - 1);
+    int rb;
+    if (rb_hint >= 0) { rb = rb_hint; while (r >= reads.blk_off[rb + 1]) ++rb; }
+    else rb = (int)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r) - 1);
     const int sb = reads.blk_sblk[rb];
     if (sb < 0) return;
     const int64_t b = sites.blk_off[sb + 1];
@@ -694,7 +712,7 @@ extern "C" int32_t unfz_read_scan_tile_reads(int32_t max_l_seq) { (void)max_l_se
 
 extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                               const int32_t* mark_prefix, const UnfzParams* hp, int32_t max_l_seq, UnfzReadSum* out,
-                              int32_t* row_lb, int32_t* blk_maxspan, uint32_t* tile_tot, void* stream) {
+                              int32_t* row_lb, int32_t* blk_maxspan, uint32_t* tile_tot, uint32_t* tile_info, void* stream) {
     if (reads->n_reads <= 0) return 0;
     ScanParams P;
     P.min_mapq = hp->min_map_qual;
@@ -716,7 +734,8 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
         int64_t g = (int64_t)ctx->sm_count * per_sm;
         if (g * WP_WARPS > tiles) g = (tiles + WP_WARPS - 1) / WP_WARPS;
         read_scan_warp_kernel<<<(unsigned)g, WP_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, qslice,
-                                                                                     out, row_lb, blk_maxspan, tile_tot, ctx->guard);
+                                                                                     out, row_lb, blk_maxspan, tile_tot,
+                                                                                     reinterpret_cast<uint2*>(tile_info), ctx->guard);
         UNFZ_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -729,7 +748,8 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     const int64_t n_tiles = (reads->n_reads + RS_THREADS - 1) / RS_THREADS;
     int64_t grid = (int64_t)ctx->sm_count * 4;     // 4 x ~49 KB of staging per SM
     if (grid > n_tiles) grid = n_tiles;
-    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan, tile_tot, ctx->guard);
+    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan, tile_tot,
+                                                                                 reinterpret_cast<uint2*>(tile_info), ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -737,11 +757,12 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
 extern "C" int unfz_read_site_alleles(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                                       const uint8_t* row_mark, const int32_t* mark_prefix,
                                       const UnfzReadSum* rsum, const int32_t* row_lb, const uint32_t* tile_base,
-                                      int32_t tile_reads, uint32_t* hits, void* stream) {
+                                      int32_t tile_reads, uint32_t* hits, const uint32_t* tile_info, void* stream) {
     if (reads->n_reads <= 0) return 0;
     const int64_t blocks = (reads->n_reads + 255) / 256;
     read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, row_lb,
-                                                                                 tile_base, tile_reads, hits, ctx->guard);
+                                                                                 tile_base, tile_reads, hits,
+                                                                                 tile_reads == 32 ? reinterpret_cast<const uint2*>(tile_info) : nullptr, ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

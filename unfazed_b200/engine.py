@@ -386,6 +386,7 @@ class Engine:
             n_tiles = (N + tile_reads - 1) // tile_reads
             e1.add("tile_tot", 4 * n_tiles)
             e1.add("tile_base", 4 * (n_tiles + 1))
+            e1.add("tile_info", 8 * n_tiles)
         z1.alloc()
         e1.alloc()
         R = z1.ptr["result"]
@@ -493,7 +494,8 @@ class Engine:
             total_hits_ptr = off_ptr + 8 * 6 * (n + 1)
             mark("alloc2")
             self._check(lib.unfz_read_scan(ctx, rc_, sc, z1.ptr["mark_prefix"], C.byref(params), dreads.max_l_seq, e1.ptr["rsum"],
-                                           e1.ptr["row_lb"], z1.ptr["blk_maxspan"], e1.ptr["tile_tot"], s), "read_scan")
+                                           e1.ptr["row_lb"], z1.ptr["blk_maxspan"], e1.ptr["tile_tot"], e1.ptr["tile_info"], s),
+                        "read_scan")
             launches += 1
             mark("read_scan")
             self._check(lib.unfz_exclusive_scan_u32(ctx, e1.ptr["tile_tot"], e1.ptr["tile_base"], n_tiles, total_hits_ptr,
@@ -526,7 +528,8 @@ class Engine:
                 z3, e3, nbytes = arena3(totals, n_hits)
             mark("alloc3")
             self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, z1.ptr["row_mark"], z1.ptr["mark_prefix"], e1.ptr["rsum"],
-                                                   e1.ptr["row_lb"], e1.ptr["tile_base"], tile_reads, e3.ptr["hits"], s),
+                                                   e1.ptr["row_lb"], e1.ptr["tile_base"], tile_reads, e3.ptr["hits"],
+                                                   e1.ptr["tile_info"], s),
                         "read_site_alleles")
             launches += 1
             mark("read_site_alleles")

@@ -312,6 +312,39 @@ int unfz_summarize(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzTall
                    const UnfzParams* h_params,
                    UnfzCall* calls_strict, UnfzCall* calls_ambiguous, void* stream);
 
+/* One batch, one call: the sequence window_search -> scan -> check_caps -> classify -> compact -> scan ->
+ * [read_scan -> scan -> chain_size -> scan -> check_caps -> read_site_alleles -> chain_tally] -> summarize
+ * on buffers the caller allocated from capacities (speculative sizing, see unfz_check_caps).  It exists
+ * because a host language pays per call: ~40 ctypes calls cost more than the small kernels they launch.
+ * All pointers are device pointers except h_params.  reads == NULL runs the site part only.  The flag
+ * `guard` (zeroed by the caller) is installed for the duration of the call; actual[0] receives the pair
+ * total, actual[1..6] the chaining totals, actual[7] the hit total. */
+typedef struct {
+    const UnfzSiteCols* sites;        /* HOST structs, as for the single entry points */
+    const UnfzReadCols* reads;
+    const UnfzParams*   h_params;
+    const UnfzDnm*  dnms;     int32_t n_dnms;  int32_t n_segs;
+    const UnfzSegIn* segs;    const uint8_t* alleles;
+    int32_t max_l_seq;        int32_t tile_reads;
+    int64_t n_tiles;
+    int64_t cap_pairs, cap_hits, cap_chain[6];
+    /* sized up front */
+    int32_t* seg_row_lo;  int64_t* seg_count;  int64_t* seg_pair_off;  void* scan_work;
+    uint8_t* row_mark;    int32_t* mark_prefix;
+    int32_t* guard;       int64_t* actual;
+    int32_t* n_het;  int32_t* n_cand;  int32_t* cnv_dad;  int32_t* cnv_mom;
+    UnfzTally* tally;  UnfzCall* calls_strict;  UnfzCall* calls_ambiguous;  int32_t* win;
+    int32_t* blk_maxspan;  int64_t* need;  int64_t* off;          /* off: 6*(n_dnms+1) + 1 entries */
+    UnfzReadSum* rsum;  int32_t* row_lb;  uint32_t* tile_tot;  uint32_t* tile_base;  uint32_t* tile_info;
+    /* sized by cap_pairs */
+    uint8_t* cls;  int32_t* het_list;  uint32_t* cand_list;  int32_t* site_lo;  int32_t* site_n;  int32_t* seed_win;
+    uint8_t* cand_evid;
+    /* sized by cap_hits / cap_chain */
+    uint32_t* hits;  void* scratch;  int64_t scratch_bytes;  uint8_t* slot_label;  uint8_t* slot_evid;
+} UnfzBatch;
+int unfz_run_batch(UnfzCtx*, const UnfzBatch* h_batch, void* stream);
+int unfz_batch_struct_bytes(void);      /* sizeof(UnfzBatch), for bindings to check their mirror */
+
 #ifdef __cplusplus
 }
 #endif

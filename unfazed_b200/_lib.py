@@ -44,6 +44,28 @@ class Params(C.Structure):
     ]
 
 
+class Batch(C.Structure):
+    """UnfzBatch of include/unfazed_sm100.h."""
+    _fields_ = [
+        ("sites", c_void_p), ("reads", c_void_p), ("h_params", c_void_p),
+        ("dnms", c_void_p), ("n_dnms", c_int32), ("n_segs", c_int32),
+        ("segs", c_void_p), ("alleles", c_void_p),
+        ("max_l_seq", c_int32), ("tile_reads", c_int32),
+        ("n_tiles", c_int64),
+        ("cap_pairs", c_int64), ("cap_hits", c_int64), ("cap_chain", c_int64 * 6),
+        ("seg_row_lo", c_void_p), ("seg_count", c_void_p), ("seg_pair_off", c_void_p), ("scan_work", c_void_p),
+        ("row_mark", c_void_p), ("mark_prefix", c_void_p),
+        ("guard", c_void_p), ("actual", c_void_p),
+        ("n_het", c_void_p), ("n_cand", c_void_p), ("cnv_dad", c_void_p), ("cnv_mom", c_void_p),
+        ("tally", c_void_p), ("calls_strict", c_void_p), ("calls_ambiguous", c_void_p), ("win", c_void_p),
+        ("blk_maxspan", c_void_p), ("need", c_void_p), ("off", c_void_p),
+        ("rsum", c_void_p), ("row_lb", c_void_p), ("tile_tot", c_void_p), ("tile_base", c_void_p), ("tile_info", c_void_p),
+        ("cls", c_void_p), ("het_list", c_void_p), ("cand_list", c_void_p), ("site_lo", c_void_p), ("site_n", c_void_p),
+        ("seed_win", c_void_p), ("cand_evid", c_void_p),
+        ("hits", c_void_p), ("scratch", c_void_p), ("scratch_bytes", c_int64), ("slot_label", c_void_p), ("slot_evid", c_void_p),
+    ]
+
+
 SEG_DTYPE = np.dtype([
     ("sblk", "<i4"), ("lo_pos", "<i4"), ("hi_pos", "<i4"), ("mult", "<i4"),
     ("dnm", "<i4"), ("excl_lo", "<i4"), ("excl_hi", "<i4"), ("mode", "<i4"),
@@ -79,6 +101,8 @@ SYMBOLS = {
     "unfz_last_error": (C.c_char_p, [_P]),
     "unfz_ctx_set_guard": (C.c_int, [_P, _P]),
     "unfz_check_caps": (C.c_int, [_P, c_int32, _P, _P, _P, _P, _P]),
+    "unfz_run_batch": (C.c_int, [_P, C.POINTER(Batch), _P]),
+    "unfz_batch_struct_bytes": (C.c_int, []),
     "unfz_scan_work_bytes": (c_int64, [c_int64]),
     "unfz_exclusive_scan_i64": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
     "unfz_exclusive_scan_u8_i32": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
@@ -124,5 +148,7 @@ def load():
         fn.argtypes = args
     if lib.unfz_abi_version() != 1:
         raise LibraryMissing("ABI version mismatch in %s" % LIB_PATH)
+    if lib.unfz_batch_struct_bytes() != C.sizeof(Batch):
+        raise LibraryMissing("UnfzBatch layout mismatch between %s and _lib.Batch" % LIB_PATH)
     _lib = lib
     return lib

@@ -63,3 +63,58 @@ extern "C" int unfz_check_caps(UnfzCtx* ctx, int32_t k, const int64_t* const* to
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// One batch in one call (speculatively sized buffers): the body of Engine.run without the per-call
+// cost of the host language.
+// ------------------------------------------------------------------------------------------------
+#define UNFZ_RC(expr) do { const int rc_ = (expr); if (rc_ != 0) { ctx->guard = nullptr; return rc_; } } while (0)
+
+extern "C" int unfz_batch_struct_bytes(void) { return (int)sizeof(UnfzBatch); }
+
+extern "C" int unfz_run_batch(UnfzCtx* ctx, const UnfzBatch* b, void* s) {
+    if (!ctx || !b) return -1;
+    const int32_t n = b->n_dnms, S = b->n_segs;
+    const int64_t V = b->sites->n_rows;
+    ctx->guard = b->guard;
+    UNFZ_RC(unfz_window_search(ctx, b->sites, b->segs, S, b->seg_row_lo, b->seg_count, s));
+    UNFZ_RC(unfz_exclusive_scan_i64(ctx, b->seg_count, b->seg_pair_off, S, b->scan_work, s));
+    {
+        const int64_t* t[1] = {b->seg_pair_off + S};
+        const int64_t c[1] = {b->cap_pairs};
+        UNFZ_RC(unfz_check_caps(ctx, 1, t, c, b->guard, b->actual, s));
+    }
+    UNFZ_RC(unfz_classify_sites(ctx, b->sites, b->segs, b->seg_row_lo, b->seg_pair_off, S, b->cap_pairs, b->h_params, b->cls, s));
+    UNFZ_RC(unfz_compact_sites(ctx, b->dnms, n, b->segs, b->seg_row_lo, b->seg_pair_off, b->cls, b->het_list, b->n_het,
+                               b->cand_list, b->n_cand, b->cnv_dad, b->cnv_mom, b->row_mark, s));
+    UNFZ_RC(unfz_exclusive_scan_u8_i32(ctx, b->row_mark, b->mark_prefix, V, b->scan_work, s));
+    if (b->reads != nullptr) {
+        int64_t* total_hits = b->off + 6 * ((int64_t)n + 1);
+        UNFZ_RC(unfz_read_scan(ctx, b->reads, b->sites, b->mark_prefix, b->h_params, b->max_l_seq, b->rsum, b->row_lb,
+                               b->blk_maxspan, b->tile_tot, b->tile_info, s));
+        UNFZ_RC(unfz_exclusive_scan_u32(ctx, b->tile_tot, b->tile_base, b->n_tiles, total_hits, b->scan_work, s));
+        UNFZ_RC(unfz_chain_size(ctx, b->dnms, n, b->segs, b->seg_pair_off, b->sites, b->reads, b->rsum, b->blk_maxspan,
+                                b->het_list, b->n_het, b->cand_list, b->n_cand, b->win, b->need, b->site_lo, b->site_n,
+                                b->seed_win, s));
+        UNFZ_RC(unfz_exclusive_scan_rows_i64(ctx, b->need, b->off, 6, n, s));
+        {
+            const int64_t* t[7];
+            int64_t c[7];
+            for (int i = 0; i < 6; ++i) { t[i] = b->off + (int64_t)(i + 1) * (n + 1) - 1; c[i] = b->cap_chain[i]; }
+            t[6] = total_hits;
+            c[6] = b->cap_hits;
+            UNFZ_RC(unfz_check_caps(ctx, 7, t, c, b->guard, b->actual + 1, s));
+        }
+        UNFZ_RC(unfz_read_site_alleles(ctx, b->reads, b->sites, b->row_mark, b->mark_prefix, b->rsum, b->row_lb, b->tile_base,
+                                       b->tile_reads, b->hits, b->tile_info, s));
+        UNFZ_RC(unfz_chain_tally(ctx, b->dnms, n, b->segs, b->seg_pair_off, b->sites, b->reads, b->rsum, b->blk_maxspan,
+                                 b->hits, b->tile_base, b->tile_reads, b->mark_prefix, b->het_list, b->n_het, b->cand_list,
+                                 b->n_cand, b->alleles, b->win, b->site_lo, b->site_n, b->seed_win, b->off, b->cap_chain,
+                                 b->h_params, b->scratch, b->scratch_bytes, b->slot_label, b->slot_evid, b->cand_evid,
+                                 b->tally, s));
+    }
+    UNFZ_RC(unfz_summarize(ctx, b->dnms, n, b->tally, b->cnv_dad, b->cnv_mom, b->n_cand, b->h_params, b->calls_strict,
+                           b->calls_ambiguous, s));
+    ctx->guard = nullptr;
+    return 0;
+}

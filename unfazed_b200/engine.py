@@ -424,51 +424,7 @@ class Engine:
                 z3, e3, nbytes = arena3(caps["chain"], int(caps["hits"]))
         mark("start")
 
-        # ---- K0 + scan ---------------------------------------------------------------------
-        self._check(lib.unfz_window_search(ctx, sc, p_seg, S, rp["seg_row_lo"], e1.ptr["seg_count"], s), "window_search")
-        self._check(lib.unfz_exclusive_scan_i64(ctx, e1.ptr["seg_count"], z1.ptr["seg_pair_off"], S, e1.ptr["scan_work"], s), "scan(pairs)")
-        launches += 4
-        mark("window_search")
-        guard_ptr, actual_ptr = z1.ptr["guard"], z1.ptr["guard"] + 64
-
-        def check_caps(ptrs, limits, slot):
-            k = len(ptrs)
-            a_t = (C.c_void_p * k)(*ptrs)
-            a_c = (C.c_int64 * k)(*[int(x) for x in limits])
-            self._check(lib.unfz_check_caps(ctx, k, a_t, a_c, guard_ptr, actual_ptr + 8 * slot, s), "check_caps")
-
-        h_pair_off = None
-        if spec:
-            lib.unfz_ctx_set_guard(ctx, guard_ptr)
-            n_pairs = int(caps["pairs"])                                                 # capacity, not the total
-            check_caps([z1.ptr["seg_pair_off"] + 8 * S], [n_pairs], 0)
-            launches += 1
-        else:
-            h_pair_off = z1.view["seg_pair_off"].cpu().numpy().view(np.int64)[: S + 1]      # host sync 1
-            n_pairs = int(h_pair_off[S]) if S > 0 else 0
-
-        if not spec:
-            z2, e2 = arena2(n_pairs)
-        mark("alloc1")
-        self._check(lib.unfz_classify_sites(ctx, sc, p_seg, rp["seg_row_lo"], z1.ptr["seg_pair_off"], S, n_pairs,
-                                            C.byref(params), e2.ptr["cls"], s), "classify_sites")
-        launches += 1 if n_pairs else 0
-        mark("classify_sites")
-        self._check(lib.unfz_compact_sites(ctx, p_dnm, n, p_seg, rp["seg_row_lo"], z1.ptr["seg_pair_off"], e2.ptr["cls"],
-                                           e2.ptr["het_list"], rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], rp["cnv_dad"],
-                                           rp["cnv_mom"], z1.ptr["row_mark"], s), "compact_sites")
-        self._check(lib.unfz_exclusive_scan_u8_i32(ctx, z1.ptr["row_mark"], z1.ptr["mark_prefix"], V, e1.ptr["scan_work"], s), "scan(marks)")
-        launches += 4
-        mark("compact_sites")
-
-        res = BatchResult(plan=plan, n_pairs=n_pairs, n_hits=0, seg_row_lo=None, seg_pair_off=h_pair_off,
-                          n_het=None, n_cand=None, cnv_dad=None, cnv_mom=None)
-        dv = res._dev
-        dv.update(cls=e2.view["cls"], het_list=e2.view["het_list"].view(torch.int32), cand_list=e2.view["cand_list"].view(torch.int32),
-                  cand_evid=z2.view["cand_evid"], _keep=(z1, e1, z2, e2, d_plan))
-
-        if has_reads:
-            rc_ = C.byref(dreads.cols)
+        def bind_blocks():
             # read block -> site block map and the per-block insert bound: uploaded unless the same plan and
             # bounds are already bound to these read columns
             cul_bytes = None if blk_cul is None else np.ascontiguousarray(blk_cul, dtype=np.float64).tobytes()
@@ -489,70 +445,161 @@ class Engine:
                 if blk_cul is not None:
                     dreads.blk_cul[: blk_cul.shape[0]].copy_(torch.from_numpy(np.frombuffer(cul_bytes, dtype=np.float64).copy()))
                 dreads._bound = bound
-            # ---- K2 + scan(tile hit totals) + chain sizing; ONE host sync for all the sizes ------------
-            off_ptr = z1.ptr["off"]
-            total_hits_ptr = off_ptr + 8 * 6 * (n + 1)
-            mark("alloc2")
-            self._check(lib.unfz_read_scan(ctx, rc_, sc, z1.ptr["mark_prefix"], C.byref(params), dreads.max_l_seq, e1.ptr["rsum"],
-                                           e1.ptr["row_lb"], z1.ptr["blk_maxspan"], e1.ptr["tile_tot"], e1.ptr["tile_info"], s),
-                        "read_scan")
-            launches += 1
-            mark("read_scan")
-            self._check(lib.unfz_exclusive_scan_u32(ctx, e1.ptr["tile_tot"], e1.ptr["tile_base"], n_tiles, total_hits_ptr,
-                                                    e1.ptr["scan_work"], s), "scan(hits)")
-            launches += 3
-            mark("scan_hits")
-            self._check(lib.unfz_chain_size(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
-                                            z1.ptr["blk_maxspan"], e2.ptr["het_list"], rp["n_het"], e2.ptr["cand_list"],
-                                            rp["n_cand"], rp["win"], z1.ptr["need"], e2.ptr["site_lo"], e2.ptr["site_n"],
-                                            e2.ptr["seed_win"], s), "chain_size")
-            self._check(lib.unfz_exclusive_scan_rows_i64(ctx, z1.ptr["need"], off_ptr, 6, n, s), "scan(need)")
-            launches += 2
-            h_off = None
+
+        fast = spec and not time_stages
+        if fast:
+            # ---- the whole batch in ONE call (unfz_run_batch) ------------------------------------------
+            if has_reads:
+                bind_blocks()
+            b = L.Batch()
+            b.sites = C.addressof(dsites.cols)
+            b.reads = C.addressof(dreads.cols) if has_reads else None
+            b.h_params = C.addressof(params)
+            b.dnms, b.n_dnms, b.n_segs, b.segs, b.alleles = p_dnm, n, S, p_seg, p_all
+            b.cap_pairs = int(caps["pairs"])
+            b.seg_row_lo, b.seg_count, b.seg_pair_off = rp["seg_row_lo"], e1.ptr["seg_count"], z1.ptr["seg_pair_off"]
+            b.scan_work, b.row_mark, b.mark_prefix = e1.ptr["scan_work"], z1.ptr["row_mark"], z1.ptr["mark_prefix"]
+            b.guard, b.actual = z1.ptr["guard"], z1.ptr["guard"] + 64
+            b.n_het, b.n_cand, b.cnv_dad, b.cnv_mom = rp["n_het"], rp["n_cand"], rp["cnv_dad"], rp["cnv_mom"]
+            b.tally, b.calls_strict, b.calls_ambiguous, b.win = rp["tally"], rp["calls_s"], rp["calls_a"], rp["win"]
+            b.cls, b.het_list, b.cand_list = e2.ptr["cls"], e2.ptr["het_list"], e2.ptr["cand_list"]
+            b.cand_evid = z2.ptr["cand_evid"]
+            if has_reads:
+                b.max_l_seq, b.tile_reads, b.n_tiles = dreads.max_l_seq, tile_reads, n_tiles
+                b.cap_hits = int(caps["hits"])
+                for i_, v_ in enumerate(caps["chain"]):
+                    b.cap_chain[i_] = int(v_)
+                b.blk_maxspan, b.need, b.off = z1.ptr["blk_maxspan"], z1.ptr["need"], z1.ptr["off"]
+                b.rsum, b.row_lb = e1.ptr["rsum"], e1.ptr["row_lb"]
+                b.tile_tot, b.tile_base, b.tile_info = e1.ptr["tile_tot"], e1.ptr["tile_base"], e1.ptr["tile_info"]
+                b.site_lo, b.site_n, b.seed_win = e2.ptr["site_lo"], e2.ptr["site_n"], e2.ptr["seed_win"]
+                b.hits, b.scratch, b.scratch_bytes = e3.ptr["hits"], e3.ptr["scratch"], nbytes
+                b.slot_label, b.slot_evid = z3.ptr["slot_label"], z3.ptr["slot_evid"]
+            self._check(lib.unfz_run_batch(ctx, C.byref(b), s), "run_batch")
+            launches += 20 if has_reads else 11
+            h_pair_off, h_off = None, None
+            res = BatchResult(plan=plan, n_pairs=int(caps["pairs"]), n_hits=int(caps["hits"]) if has_reads else 0,
+                              seg_row_lo=None, seg_pair_off=None, n_het=None, n_cand=None, cnv_dad=None, cnv_mom=None)
+            dv = res._dev
+            dv.update(cls=e2.view["cls"], het_list=e2.view["het_list"].view(torch.int32),
+                      cand_list=e2.view["cand_list"].view(torch.int32), cand_evid=z2.view["cand_evid"],
+                      _keep=(z1, e1, z2, e2, d_plan))
+            if has_reads:
+                dv.update(rsum=e1.view["rsum"], hits=e3.view["hits"].view(torch.int32),
+                          tile_base=e1.view["tile_base"].view(torch.int32), tile_reads=tile_reads,
+                          slot_label=z3.view["slot_label"], slot_evid=z3.view["slot_evid"], row_mark=z1.view["row_mark"],
+                          mark_prefix=z1.view["mark_prefix"].view(torch.int32), _keep3=(z3, e3))
+        else:
+            # ---- K0 + scan ---------------------------------------------------------------------
+            self._check(lib.unfz_window_search(ctx, sc, p_seg, S, rp["seg_row_lo"], e1.ptr["seg_count"], s), "window_search")
+            self._check(lib.unfz_exclusive_scan_i64(ctx, e1.ptr["seg_count"], z1.ptr["seg_pair_off"], S, e1.ptr["scan_work"], s), "scan(pairs)")
+            launches += 4
+            mark("window_search")
+            guard_ptr, actual_ptr = z1.ptr["guard"], z1.ptr["guard"] + 64
+
+            def check_caps(ptrs, limits, slot):
+                k = len(ptrs)
+                a_t = (C.c_void_p * k)(*ptrs)
+                a_c = (C.c_int64 * k)(*[int(x) for x in limits])
+                self._check(lib.unfz_check_caps(ctx, k, a_t, a_c, guard_ptr, actual_ptr + 8 * slot, s), "check_caps")
+
+            h_pair_off = None
             if spec:
-                totals = np.asarray(caps["chain"], dtype=np.int64).copy()
-                n_hits = int(caps["hits"])
-                check_caps([off_ptr + 8 * ((i + 1) * (n + 1) - 1) for i in range(6)] + [total_hits_ptr],
-                           list(totals) + [n_hits], 1)
+                lib.unfz_ctx_set_guard(ctx, guard_ptr)
+                n_pairs = int(caps["pairs"])                                                 # capacity, not the total
+                check_caps([z1.ptr["seg_pair_off"] + 8 * S], [n_pairs], 0)
                 launches += 1
             else:
-                h_all = z1.view["off"].cpu().numpy().view(np.int64)                      # host sync 2
-                h_off = h_all[: 6 * (n + 1)].reshape(6, n + 1)
-                n_hits = int(h_all[6 * (n + 1)])
-                totals = np.ascontiguousarray(h_off[:, n]).astype(np.int64)
-            mark("chain_size")
-            if n_hits >= 2**32:
-                raise RuntimeError("more than 2^32 read x site hits in one batch")
-            res.n_hits = n_hits
+                h_pair_off = z1.view["seg_pair_off"].cpu().numpy().view(np.int64)[: S + 1]      # host sync 1
+                n_pairs = int(h_pair_off[S]) if S > 0 else 0
+
             if not spec:
-                z3, e3, nbytes = arena3(totals, n_hits)
-            mark("alloc3")
-            self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, z1.ptr["row_mark"], z1.ptr["mark_prefix"], e1.ptr["rsum"],
-                                                   e1.ptr["row_lb"], e1.ptr["tile_base"], tile_reads, e3.ptr["hits"],
-                                                   e1.ptr["tile_info"], s),
-                        "read_site_alleles")
+                z2, e2 = arena2(n_pairs)
+            mark("alloc1")
+            self._check(lib.unfz_classify_sites(ctx, sc, p_seg, rp["seg_row_lo"], z1.ptr["seg_pair_off"], S, n_pairs,
+                                                C.byref(params), e2.ptr["cls"], s), "classify_sites")
+            launches += 1 if n_pairs else 0
+            mark("classify_sites")
+            self._check(lib.unfz_compact_sites(ctx, p_dnm, n, p_seg, rp["seg_row_lo"], z1.ptr["seg_pair_off"], e2.ptr["cls"],
+                                               e2.ptr["het_list"], rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], rp["cnv_dad"],
+                                               rp["cnv_mom"], z1.ptr["row_mark"], s), "compact_sites")
+            self._check(lib.unfz_exclusive_scan_u8_i32(ctx, z1.ptr["row_mark"], z1.ptr["mark_prefix"], V, e1.ptr["scan_work"], s), "scan(marks)")
+            launches += 4
+            mark("compact_sites")
+
+            res = BatchResult(plan=plan, n_pairs=n_pairs, n_hits=0, seg_row_lo=None, seg_pair_off=h_pair_off,
+                              n_het=None, n_cand=None, cnv_dad=None, cnv_mom=None)
+            dv = res._dev
+            dv.update(cls=e2.view["cls"], het_list=e2.view["het_list"].view(torch.int32), cand_list=e2.view["cand_list"].view(torch.int32),
+                      cand_evid=z2.view["cand_evid"], _keep=(z1, e1, z2, e2, d_plan))
+
+            if has_reads:
+                rc_ = C.byref(dreads.cols)
+                bind_blocks()
+                # ---- K2 + scan(tile hit totals) + chain sizing; ONE host sync for all the sizes ------------
+                off_ptr = z1.ptr["off"]
+                total_hits_ptr = off_ptr + 8 * 6 * (n + 1)
+                mark("alloc2")
+                self._check(lib.unfz_read_scan(ctx, rc_, sc, z1.ptr["mark_prefix"], C.byref(params), dreads.max_l_seq, e1.ptr["rsum"],
+                                               e1.ptr["row_lb"], z1.ptr["blk_maxspan"], e1.ptr["tile_tot"], e1.ptr["tile_info"], s),
+                            "read_scan")
+                launches += 1
+                mark("read_scan")
+                self._check(lib.unfz_exclusive_scan_u32(ctx, e1.ptr["tile_tot"], e1.ptr["tile_base"], n_tiles, total_hits_ptr,
+                                                        e1.ptr["scan_work"], s), "scan(hits)")
+                launches += 3
+                mark("scan_hits")
+                self._check(lib.unfz_chain_size(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
+                                                z1.ptr["blk_maxspan"], e2.ptr["het_list"], rp["n_het"], e2.ptr["cand_list"],
+                                                rp["n_cand"], rp["win"], z1.ptr["need"], e2.ptr["site_lo"], e2.ptr["site_n"],
+                                                e2.ptr["seed_win"], s), "chain_size")
+                self._check(lib.unfz_exclusive_scan_rows_i64(ctx, z1.ptr["need"], off_ptr, 6, n, s), "scan(need)")
+                launches += 2
+                h_off = None
+                if spec:
+                    totals = np.asarray(caps["chain"], dtype=np.int64).copy()
+                    n_hits = int(caps["hits"])
+                    check_caps([off_ptr + 8 * ((i + 1) * (n + 1) - 1) for i in range(6)] + [total_hits_ptr],
+                               list(totals) + [n_hits], 1)
+                    launches += 1
+                else:
+                    h_all = z1.view["off"].cpu().numpy().view(np.int64)                      # host sync 2
+                    h_off = h_all[: 6 * (n + 1)].reshape(6, n + 1)
+                    n_hits = int(h_all[6 * (n + 1)])
+                    totals = np.ascontiguousarray(h_off[:, n]).astype(np.int64)
+                mark("chain_size")
+                if n_hits >= 2**32:
+                    raise RuntimeError("more than 2^32 read x site hits in one batch")
+                res.n_hits = n_hits
+                if not spec:
+                    z3, e3, nbytes = arena3(totals, n_hits)
+                mark("alloc3")
+                self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, z1.ptr["row_mark"], z1.ptr["mark_prefix"], e1.ptr["rsum"],
+                                                       e1.ptr["row_lb"], e1.ptr["tile_base"], tile_reads, e3.ptr["hits"],
+                                                       e1.ptr["tile_info"], s),
+                            "read_site_alleles")
+                launches += 1
+                mark("read_site_alleles")
+                self._check(lib.unfz_chain_tally(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
+                                                 z1.ptr["blk_maxspan"], e3.ptr["hits"], e1.ptr["tile_base"], tile_reads, z1.ptr["mark_prefix"],
+                                                 e2.ptr["het_list"],
+                                                 rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], p_all, rp["win"], e2.ptr["site_lo"], e2.ptr["site_n"],
+                                                 e2.ptr["seed_win"], off_ptr,
+                                                 totals.ctypes.data, C.byref(params), e3.ptr["scratch"], nbytes,
+                                                 z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"], s),
+                            "chain_tally")
+                launches += 1
+                mark("chain_tally")
+                dv.update(rsum=e1.view["rsum"], hits=e3.view["hits"].view(torch.int32),
+                          tile_base=e1.view["tile_base"].view(torch.int32), tile_reads=tile_reads, slot_label=z3.view["slot_label"],
+                          slot_evid=z3.view["slot_evid"], row_mark=z1.view["row_mark"],
+                          mark_prefix=z1.view["mark_prefix"].view(torch.int32), _keep3=(z3, e3))
+                if h_off is not None:
+                    res.slot_off = h_off[0].copy()
+            self._check(lib.unfz_summarize(ctx, p_dnm, n, rp["tally"], rp["cnv_dad"], rp["cnv_mom"], rp["n_cand"], C.byref(params),
+                                           rp["calls_s"], rp["calls_a"], s), "summarize")
             launches += 1
-            mark("read_site_alleles")
-            self._check(lib.unfz_chain_tally(ctx, p_dnm, n, p_seg, z1.ptr["seg_pair_off"], sc, rc_, e1.ptr["rsum"],
-                                             z1.ptr["blk_maxspan"], e3.ptr["hits"], e1.ptr["tile_base"], tile_reads, z1.ptr["mark_prefix"],
-                                             e2.ptr["het_list"],
-                                             rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], p_all, rp["win"], e2.ptr["site_lo"], e2.ptr["site_n"],
-                                             e2.ptr["seed_win"], off_ptr,
-                                             totals.ctypes.data, C.byref(params), e3.ptr["scratch"], nbytes,
-                                             z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"], s),
-                        "chain_tally")
-            launches += 1
-            mark("chain_tally")
-            dv.update(rsum=e1.view["rsum"], hits=e3.view["hits"].view(torch.int32),
-                      tile_base=e1.view["tile_base"].view(torch.int32), tile_reads=tile_reads, slot_label=z3.view["slot_label"],
-                      slot_evid=z3.view["slot_evid"], row_mark=z1.view["row_mark"],
-                      mark_prefix=z1.view["mark_prefix"].view(torch.int32), _keep3=(z3, e3))
-            if h_off is not None:
-                res.slot_off = h_off[0].copy()
-        self._check(lib.unfz_summarize(ctx, p_dnm, n, rp["tally"], rp["cnv_dad"], rp["cnv_mom"], rp["n_cand"], C.byref(params),
-                                       rp["calls_s"], rp["calls_a"], s), "summarize")
-        launches += 1
-        mark("summarize")
+            mark("summarize")
         # ---- results: ONE device-to-host copy of the int32 result block ----------------------------
         if spec:
             lib.unfz_ctx_set_guard(ctx, None)

@@ -85,7 +85,11 @@ typedef struct {
     const int32_t*  dep;         /* [n_rows][6],  8-byte aligned */
 } UnfzSiteCols;
 
-/* 32-byte read header (schema.READ_HDR) */
+/* 32-byte read header (schema.READ_HDR).
+ * Layout contract of the read columns: reads of a block are sorted by start (BAM file order), and the
+ * CIGAR words / quality bytes / bases of consecutive reads are stored back to back in read order
+ * (cigar_off and the 40-bit quality offset never decrease with the read index) -- the scan stages the
+ * span of 32 consecutive reads with one contiguous copy.  Read and site-row indices fit 31 bits. */
 typedef struct {
     int32_t  start;
     int32_t  tlen;

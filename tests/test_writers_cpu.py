@@ -1,4 +1,4 @@
-"""CPU, build container only: `write_vcf_output` of the drop-in against the reference's own
+"""CPU, build container only: the output writers. `write_vcf_output` of the drop-in against the reference's own
 (`unfazed/unfazed.py:336-440`), both over one recording cyvcf2 stand-in: same header additions, same
 phased genotypes, same UOPS / UET arrays for every variant and sample."""
 import copy
@@ -92,3 +92,31 @@ def test_vcf_writer_matches_reference(include_ambiguous, monkeypatch):
     assert log_new.records == log_ref.records
     phased = sum(1 for r in log_ref.records for g in r[3] if g[2] is True)
     assert phased >= 3
+
+
+@pytest.mark.parametrize("include_ambiguous,verbose", [(False, False), (True, True), (False, True)])
+def test_bed_writer_matches_reference(include_ambiguous, verbose, tmp_path):
+    """`write_bed_output` (`unfazed.py:443-515`) on the same records: same header, same rows (the read-name
+    columns are a joined Python set in the reference, Q23: compared as sets)."""
+    from unfazed_b200 import unfazed as new_mod
+    ds = make_dataset(SynthConfig(dnms_per_trio=14, seed=402, coverage=20.0, n_trios=2, sv_frac=0.3, sv_max_len=20000,
+                                  sex_chrom_frac=0.2, male_frac=1.0))
+    records = port.Phaser(ds.sites, ds.reads, ds.pedigrees, port_params()).phase(copy.deepcopy(ds.dnms))
+    ref_mod = ref_driver.modules()["unfazed"]
+    a, b = str(tmp_path / "ref.bed"), str(tmp_path / "new.bed")
+    ref_mod.write_bed_output(copy.deepcopy(records), include_ambiguous, verbose, a, 10)
+    new_mod.write_bed_output(copy.deepcopy(records), include_ambiguous, verbose, b, 10)
+
+    def rows(path):
+        out = []
+        for line in open(path).read().strip().split("\n"):
+            f = line.split("\t")
+            if not line.startswith("#") and len(f) == 13:
+                f[10] = ",".join(sorted(f[10].split(",")))
+                f[12] = ",".join(sorted(f[12].split(",")))
+            out.append(f)
+        return out
+
+    ra, rb = rows(a), rows(b)
+    assert ra[0] == rb[0] and ra[0][0].startswith("#")
+    assert ra == rb and len(ra) > 3

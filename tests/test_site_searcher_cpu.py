@@ -1,0 +1,68 @@
+"""CPU, build container only: the per-variant interface mirror `unfazed_b200.site_searcher` against the
+reference's `unfazed/site_searcher.py` on random inputs (the order pivot / right run / left run of
+`binary_search`, Q16, and the parent-consistency filter of `match_informative_sites`), and
+`informative_site_finder.autophaseable` against the reference's PAR tables."""
+import random
+import types
+
+import pytest
+
+from oracle import ref_driver
+from unfazed_b200 import site_searcher as new
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_driver.available(), reason="reference checkout not mounted")]
+
+
+def _sites(rng, n):
+    pos = sorted(rng.sample(range(0, 3000), n)) if n else []
+    if n > 3 and rng.random() < 0.5:                       # duplicate positions (overlapping windows, Q9)
+        pos = sorted(pos + [pos[n // 2], pos[n // 3]])
+    return [{"pos": p, "ref_parent": rng.choice(["dad", "mom"]), "alt_parent": rng.choice(["dad", "mom"]),
+             "ref_allele": "A", "alt_allele": "C"} for p in pos]
+
+
+def test_binary_search_random():
+    ref = ref_driver.modules()["site_searcher"]
+    rng = random.Random(7)
+    for _ in range(3000):
+        sites = _sites(rng, rng.randint(0, 40))
+        a = rng.randint(-50, 3050)
+        b = a + rng.choice([0, 1, 2, 30, 151, 400, 2000])
+        assert new.binary_search(a, b, sites) == ref.binary_search(a, b, sites), (a, b, [s["pos"] for s in sites])
+
+
+def test_match_informative_sites_random():
+    ref = ref_driver.modules()["site_searcher"]
+    rng = random.Random(11)
+    for _ in range(300):
+        sites = _sites(rng, rng.randint(1, 30))
+        reads = {}
+        for hap in ("ref", "alt"):
+            lst = []
+            for _r in range(rng.randint(0, 12)):
+                st = rng.randint(0, 2900)
+                lst.append(types.SimpleNamespace(reference_start=st, reference_end=st + rng.choice([1, 50, 151, 600])))
+            reads[hap] = lst
+        assert new.match_informative_sites(reads, sites) == ref.match_informative_sites(reads, sites)
+
+
+def test_autophaseable_matches_reference():
+    ref = ref_driver.modules()["informative_site_finder"]
+    from unfazed_b200.informative_site_finder import autophaseable
+    peds = {"boy": {"kid": "boy", "dad": "d", "mom": "m", "sex": "1"}, "girl": {"kid": "girl", "dad": "d", "mom": "m", "sex": "2"}}
+    rng = random.Random(5)
+    edges = [10000, 10001, 60001, 2699520, 2699521, 2781479, 2781480, 154931044, 155260560, 155701383, 156030895,
+             57227415, 59034050, 59363566, 56887903]
+    for build in ("37", "38", 37, 38, "19"):
+        for chrom in ("X", "Y", "chrX", "chrY", "x", "7", "chr7"):
+            for kid in ("boy", "girl"):
+                for start in edges + [rng.randint(1, 160000000) for _ in range(6)]:
+                    dn = {"chrom": chrom, "start": start, "end": start + 1, "kid": kid, "vartype": "POINT"}
+                    try:
+                        want = ref.autophaseable(dict(dn), peds, build)
+                    except Exception as e:                # e.g. an unknown build in the reference's tables
+                        with pytest.raises(type(e)):
+                            autophaseable(dict(dn), peds, build)
+                        continue
+                    assert bool(autophaseable(dict(dn), peds, build)) == bool(want), (build, chrom, kid, start)

@@ -264,7 +264,7 @@ def run_b200(args):
     del bp.dsites, bp.dreads
     torch.cuda.empty_cache()
     host_site_t = _pin_table(ds.sites)
-    host_read_t = _pin_table(ds.reads)
+    host_read_t = eng.pack_reads(ds.reads, min_gt_qual=20, pin=True)
 
     e2e_parts = {}
 
@@ -316,7 +316,7 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         hd = ds.reads.hdr
-        rs_bytes = float(32 * n_reads + 4 * int(hd["n_cigar"].sum()) + int(hd["l_seq"].sum()) + 20 * n_reads)
+        rs_bytes = float(32 * n_reads + 4 * int(hd["n_cigar"].sum()) + int(hd["l_seq"].sum()) / 8.0 + 20 * n_reads)
         survey_read_bytes = float(24 * n_reads + 4 * int(hd["n_cigar"].sum()) + int(np.ceil(hd["l_seq"] / 4).sum())
                                   + int(hd["l_seq"].sum()) + 4 * n_hits)
         kern = {
@@ -462,7 +462,7 @@ def _pin_table(t):
     import copy
     import torch
     out = copy.copy(t)
-    for name in ("pos", "flag", "ref", "alt", "gt", "gq", "rd", "ad", "cigar", "qual", "seq2"):
+    for name in ("pos", "flag", "ref", "alt", "gt", "gq", "rd", "ad"):
         if hasattr(t, name):
             a = getattr(t, name)
             p = torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UNFZ_ABI_VERSION 1
+#define UNFZ_ABI_VERSION 2
 
 /* ---- class code of one (DNM x site) pair, written by unfz_classify_sites ------------------- */
 #define UNFZ_CLS_HET        0x01  /* usable for extended read-backed phasing (het_sites)         */
@@ -100,7 +100,7 @@ typedef struct {
     uint16_t flag;
     uint16_t n_cigar;
     uint8_t  mapq;
-    uint8_t  aux;         /* bit0 next_ref==ref, bit1 has SA tag */
+    uint8_t  aux;         /* bit0 next_ref==ref, bit1 has SA tag, bit2 (device only) a base of the read is not ACGT */
     uint8_t  qoff_hi;
     uint8_t  pad;
 } UnfzRead;
@@ -114,10 +114,15 @@ typedef struct {
     const double*   blk_cul;     /* [n_blocks] concordant_upper_len of the kid */
     const UnfzRead* hdr;
     const uint32_t* cigar;       /* BAM encoding len<<4|op */
-    const uint8_t*  qual;        /* bit7: base is not ACGT; readable for 32 bytes past n_qual (the scan copies
-                                    16-byte chunks) */
-    const uint8_t*  seq2;        /* 2-bit bases, base i at bits 2*(i&3) of byte i>>2 */
-    int64_t         n_qual;
+    const uint32_t* lowq;        /* 1 bit per query base (bit i&31 of word i>>5): base quality < --min-gt-qual.
+                                    Every use of a base quality on this path is that one comparison (goodread
+                                    read_collector.py:44-46, connect_reads :123, indel_match_alleles :281-284), so the
+                                    host packs the comparison, not the byte: 8x fewer bytes over PCIe and through the
+                                    scan.  16-byte aligned, readable for 48 bytes past ceil(n_qual/8) */
+    const uint32_t* nmask;       /* 1 bit per query base: the base is not A/C/G/T (built on the device from the sparse
+                                    index list by unfz_expand_nlist; reads that own such a base carry aux bit2) */
+    const uint8_t*  seq2;        /* 2-bit bases, base i at bits 2*(i&3) of byte i>>2; a masked base has code 0 for N */
+    int64_t         n_qual;      /* number of query bases */
     int64_t         n_cigar;
 } UnfzReadCols;
 
@@ -240,6 +245,13 @@ int unfz_compact_sites(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const Unfz
                        int32_t* het_list, int32_t* n_het, uint32_t* cand_list, int32_t* n_cand,
                        int32_t* cnv_dad, int32_t* cnv_mom, uint8_t* row_mark, void* stream);
 
+/* Device-side completion of the read columns after an upload: the host ships the positions of the (rare)
+ * non-ACGT bases as a sorted list of base indices; this sets their bits in `nmask` (zeroed by the caller,
+ * ceil(n_qual/32)+12 words) and bit2 of hdr[].aux of the reads that own them.  No reference counterpart
+ * (pysam hands out query_sequence as a string). */
+int unfz_expand_nlist(UnfzCtx*, const UnfzReadCols* reads, UnfzRead* hdr_rw, uint32_t* nmask_rw,
+                      const int64_t* nidx, int64_t n_idx, void* stream);
+
 /* Read scan: goodread :28-53, insert-size / None-count / CIGAR-op filters :181-203 :395-408,
  * reference_end and the number of marked site rows each read overlaps.
  * mark_prefix = exclusive scan of row_mark (n_rows+1 entries).
@@ -261,7 +273,7 @@ int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* site
 /* Read-by-site allele lookup: get_reference_positions(full_length=True).index(pos) + base +
  * quality for every (read x marked site) overlap (get_allele_at :56-73, phase_by_reads
  * snv_phaser.py:16-70).  Hit word: bits0-15 query index+1 (0: position not aligned),
- * bits16-23 raw quality byte, bits24-25 base code, bit26: index+1 < l_seq. */
+ * bit16 base quality < --min-gt-qual, bit23 base is not ACGT, bits24-25 base code, bit26: index+1 < l_seq. */
 int unfz_read_site_alleles(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                            const uint8_t* row_mark, const int32_t* mark_prefix,
                            const UnfzReadSum* rsum, const int32_t* row_lb, const uint32_t* tile_base,
@@ -294,7 +306,20 @@ int unfz_chain_tally(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSe
                      const int32_t* site_lo, const int32_t* site_n, const int32_t* seed_win, const int64_t* off, const int64_t* h_totals /* off[k][n_dnms], k<6 */,
                      const UnfzParams* h_params, void* scratch, int64_t scratch_bytes,
                      uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid,
-                     UnfzTally* tally, void* stream);
+                     UnfzTally* tally,
+                     int64_t* ev_need /* [2][n_dnms] or NULL: pairs / candidate entries with evidence, for unfz_evidence_lists */,
+                     void* stream);
+
+/* The entries behind the tallies, per DNM and in order: what snv_phaser.py:169-203 puts into the record's
+ * dad_reads / mom_reads (ev_read = read index of the pair's window slot, ev_rbits bit0 dad / bit1 mom) and
+ * dad_sites / mom_sites (ev_pos = 0-based position of the informative site, ev_sbits likewise; duplicates of a
+ * site are kept, the reference builds a set).  ev_off[2][n_dnms+1] = exclusive scans of ev_need
+ * (unfz_exclusive_scan_rows_i64); slot_off = row 0 of unfz_chain_tally's `off`. */
+int unfz_evidence_lists(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const int64_t* seg_pair_off,
+                        const UnfzSiteCols* sites, const uint32_t* cand_list, const int32_t* n_cand,
+                        const uint8_t* cand_evid, const int32_t* win, const int64_t* slot_off,
+                        const uint8_t* slot_evid, const int64_t* ev_off, int32_t* ev_read, uint8_t* ev_rbits,
+                        int32_t* ev_pos, uint8_t* ev_sbits, void* stream);
 int64_t unfz_chain_scratch_bytes(int64_t slots, int64_t incs, int64_t seeds, int64_t seed_incs,
                                  int64_t het_sites, int64_t cand_sites, int64_t n_dnms);
 
@@ -345,6 +370,9 @@ typedef struct {
     uint8_t* cand_evid;
     /* sized by cap_hits / cap_chain */
     uint32_t* hits;  void* scratch;  int64_t scratch_bytes;  uint8_t* slot_label;  uint8_t* slot_evid;
+    /* evidence lists (all NULL: not wanted).  ev_need 2*n_dnms, ev_off 2*(n_dnms+1); ev_read / ev_rbits hold
+     * cap_chain[0] entries, ev_pos / ev_sbits cap_pairs entries (upper bounds of what can carry evidence) */
+    int64_t* ev_need;  int64_t* ev_off;  int32_t* ev_read;  uint8_t* ev_rbits;  int32_t* ev_pos;  uint8_t* ev_sbits;
 } UnfzBatch;
 int unfz_run_batch(UnfzCtx*, const UnfzBatch* h_batch, void* stream);
 int unfz_batch_struct_bytes(void);      /* sizeof(UnfzBatch), for bindings to check their mirror */

@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_abi_version_without_gpu(lib):
     lib.unfz_abi_version.restype = ctypes.c_int
-    assert lib.unfz_abi_version() == 1
+    assert lib.unfz_abi_version() == L.ABI_VERSION == 2
     lib.unfz_scan_work_bytes.restype = ctypes.c_int64
     lib.unfz_scan_work_bytes.argtypes = [ctypes.c_int64]
     assert lib.unfz_scan_work_bytes(10_000_000) > 0

@@ -130,9 +130,10 @@ def test_more_het_sites_than_the_shared_memory_budget(engine):
     assert n >= 2
 
 
-def test_long_reads_take_the_chunked_scan_kernel(engine):
-    """40 kb reads do not fit a TMA stage: read_scan falls back to the chunked kernel; read summaries
-    (reference_end, goodread, filters) and records must still match the oracle."""
+def test_long_reads_are_counted_out_of_global_memory(engine):
+    """The quality bits of 32 reads of 40 kb do not fit a warp's shared-memory slice: read_scan counts them
+    straight out of global memory; read summaries (reference_end, goodread, filters) and records must
+    still match the oracle."""
     from unfazed_b200.phaser import BatchPhaser
     cfg = SynthConfig(dnms_per_trio=4, seed=501, readlen=40000, frag_mean=90000.0, frag_sd=3000.0, search_dist=3000,
                       coverage=40.0, read_margin=100000, noise=False)

@@ -29,7 +29,7 @@ class ReadCols(C.Structure):
     _fields_ = [
         ("n_reads", c_int64), ("n_blocks", c_int32), ("_pad", c_int32),
         ("blk_off", c_void_p), ("blk_sblk", c_void_p), ("blk_cul", c_void_p),
-        ("hdr", c_void_p), ("cigar", c_void_p), ("qual", c_void_p), ("seq2", c_void_p),
+        ("hdr", c_void_p), ("cigar", c_void_p), ("lowq", c_void_p), ("nmask", c_void_p), ("seq2", c_void_p),
         ("n_qual", c_int64), ("n_cigar", c_int64),
     ]
 
@@ -90,6 +90,7 @@ KIND_SKIP, KIND_SNV, KIND_INDEL, KIND_SV = 0, 1, 2, 3
 ORIGIN_NONE, ORIGIN_DAD, ORIGIN_MOM, ORIGIN_BOTH = 0, 1, 2, 3
 EV_READBACKED, EV_ALLELE_BALANCE, EV_AMBIG_READBACKED, EV_AMBIG_ALLELE_BAL, EV_AMBIG_BOTH, EV_SEX_CHROM = 1, 2, 4, 8, 16, 32
 DNM_AUTOPHASE, DNM_AUTOPHASE_Y, DNM_SV_QUIRK, DNM_FALLBACK_FETCH = 1, 2, 4, 8
+ABI_VERSION = 2
 RS_GOOD_CONC, RS_GOOD_DISC, RS_NONE_OK, RS_EXT_OK, RS_INS_OK, RS_HAS_MATE = 1, 2, 4, 8, 16, 32
 
 # every symbol the header declares: (name, restype, argtypes)
@@ -111,6 +112,7 @@ SYMBOLS = {
     "unfz_window_search": (C.c_int, [_P, C.POINTER(SiteCols), _P, c_int32, _P, _P, _P]),
     "unfz_classify_sites": (C.c_int, [_P, C.POINTER(SiteCols), _P, _P, _P, c_int32, c_int64, C.POINTER(Params), _P, _P]),
     "unfz_compact_sites": (C.c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "unfz_expand_nlist": (C.c_int, [_P, C.POINTER(ReadCols), _P, _P, _P, c_int64, _P]),
     "unfz_read_scan_tile_reads": (c_int32, [c_int32]),
     "unfz_read_scan": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, C.POINTER(Params), c_int32, _P, _P, _P, _P, _P, _P]),
     "unfz_read_site_alleles": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, _P, _P, _P, _P, c_int32, _P, _P, _P]),
@@ -146,7 +148,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.unfz_abi_version() != 1:
+    if lib.unfz_abi_version() != ABI_VERSION:
         raise LibraryMissing("ABI version mismatch in %s" % LIB_PATH)
     if lib.unfz_batch_struct_bytes() != C.sizeof(Batch):
         raise LibraryMissing("UnfzBatch layout mismatch between %s and _lib.Batch" % LIB_PATH)

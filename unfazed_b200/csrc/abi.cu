@@ -16,6 +16,7 @@ extern "C" int unfz_ctx_create(int device, UnfzCtx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->guard = nullptr;
+    c->scan_smem_attr = 0;
     c->err[0] = 0;
     *out = c;
     return 0;
@@ -111,7 +112,13 @@ extern "C" int unfz_run_batch(UnfzCtx* ctx, const UnfzBatch* b, void* s) {
                                  b->hits, b->tile_base, b->tile_reads, b->mark_prefix, b->het_list, b->n_het, b->cand_list,
                                  b->n_cand, b->alleles, b->win, b->site_lo, b->site_n, b->seed_win, b->off, b->cap_chain,
                                  b->h_params, b->scratch, b->scratch_bytes, b->slot_label, b->slot_evid, b->cand_evid,
-                                 b->tally, s));
+                                 b->tally, b->ev_need, s));
+        if (b->ev_need != nullptr) {
+            UNFZ_RC(unfz_exclusive_scan_rows_i64(ctx, b->ev_need, b->ev_off, 2, n, s));
+            UNFZ_RC(unfz_evidence_lists(ctx, b->dnms, n, b->seg_pair_off, b->sites, b->cand_list, b->n_cand, b->cand_evid,
+                                        b->win, b->off, b->slot_evid, b->ev_off, b->ev_read, b->ev_rbits, b->ev_pos,
+                                        b->ev_sbits, s));
+        }
     }
     UNFZ_RC(unfz_summarize(ctx, b->dnms, n, b->tally, b->cnv_dad, b->cnv_mom, b->n_cand, b->h_params, b->calls_strict,
                            b->calls_ambiguous, s));

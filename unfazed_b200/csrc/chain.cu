@@ -57,8 +57,9 @@ struct ChainArgs {
     int32_t split_margin;
     const uint32_t* hit_tile_base; int32_t hit_tile_reads;
     const int32_t* site_lo; const int32_t* site_n; const int32_t* seed_win;   // fetch ranges found by chain_size
-    int32_t readlen, min_bq, ext_goal, no_extended;
+    int32_t readlen, ext_goal, no_extended;
     uint8_t* slot_label; uint8_t* slot_evid; uint8_t* cand_evid; UnfzTally* tally;
+    int64_t* ev_need;             // [2][n_dnms] or null: pairs / candidate entries that carry evidence
     const int32_t* guard;
     Scratch S;
 };
@@ -95,10 +96,12 @@ __device__ __forceinline__ int cigar_qpos2(const uint32_t* __restrict__ cg, int 
     return -1;
 }
 
+__device__ __forceinline__ uint32_t plane_bit(const uint32_t* __restrict__ plane, int64_t g) {
+    return (__ldg(plane + (g >> 5)) >> (g & 31)) & 1u;
+}
 __device__ __forceinline__ char base_char(const UnfzReadCols& R, int64_t g) {
-    const uint32_t qb = __ldg(R.qual + g);
     const uint32_t code = (__ldg(R.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
-    if (qb & 0x80u) return code == 0 ? 'N' : '?';
+    if (plane_bit(R.nmask, g)) return code == 0 ? 'N' : '?';
     return "ACGT"[code];
 }
 __device__ __forceinline__ char hit_char(uint32_t w) {
@@ -168,7 +171,7 @@ __device__ int seed_indel(const ChainArgs& A, const UnfzDnm& dn, int64_t r) {
     const int n = dn.ref_len > dn.alt_len ? dn.ref_len : dn.alt_len;
     const int64_t g0 = read_qoff(h);
     for (int i = q; i < q + n && i < h.l_seq; ++i)
-        if ((int)(__ldg(A.reads.qual + g0 + i) & 0x7fu) < A.min_bq) return 0;
+        if (plane_bit(A.reads.lowq, g0 + i)) return 0;
     bool has_id = false;
     int64_t eo = 0, npos = 0;
     for (int k = 0; k < h.n_cigar; ++k) {
@@ -346,7 +349,7 @@ __device__ uint8_t allele_info(const ChainArgs& A, const Scratch& S, int64_t e0,
     const uint8_t code = c == ref ? 1 : (c == alt ? 2 : 0);
     if (!code) return 0;
     uint8_t out = code;
-    if ((h0 & 0xffffu) && (int)((h0 >> 16) & 0x7fu) >= A.min_bq) out |= code << 2;
+    if ((h0 & 0xffffu) && !(h0 & (1u << 16))) out |= code << 2;       // base quality >= min (hit word bit16: below)
     return out;
 }
 
@@ -380,7 +383,10 @@ chain_kernel(ChainArgs A) {
     T.status = 0;
     const int nh = A.n_het[d], nc = A.n_cand[d];
     if (dn.kind == UNFZ_KIND_SKIP || dn.rblk < 0 || nc <= 0 || dn.seg_hi <= dn.seg_lo) {
-        if (tid == 0) A.tally[d] = T;
+        if (tid == 0) {
+            A.tally[d] = T;
+            if (A.ev_need) { A.ev_need[d] = 0; A.ev_need[(int64_t)A.n_dnms + d] = 0; }
+        }
         return;
     }
     const int64_t lbase = A.seg_pair_off[dn.seg_lo];
@@ -908,9 +914,10 @@ chain_kernel(ChainArgs A) {
 
     CH_MARK(8);
     // ---------------------------------------------------------------- phase 6: tally
-    int ds = 0, ms = 0, dr = 0, mr = 0;
+    int ds = 0, ms = 0, dr = 0, mr = 0, er = 0, es = 0;
     for (int j = tid; j < nc; j += CH_THREADS) {
         const uint8_t b = cev[j];
+        es += b != 0;
         for (int bit = 1; bit <= 2; ++bit) {
             if (!(b & bit)) continue;
             bool first = true;                      // unique str(pos): count the first duplicate only
@@ -922,6 +929,11 @@ chain_kernel(ChainArgs A) {
     for (int x = tid; x < W; x += CH_THREADS) {
         dr += evid[x] & 1;
         mr += (evid[x] >> 1) & 1;
+        er += evid[x] != 0;
+    }
+    if (A.ev_need) {
+        er = block_sum(er); es = block_sum(es);
+        if (tid == 0) { A.ev_need[d] = er; A.ev_need[(int64_t)A.n_dnms + d] = es; }
     }
     ds = block_sum(ds); ms = block_sum(ms); dr = block_sum(dr); mr = block_sum(mr);
     has_rec = block_sum(has_rec);
@@ -931,6 +943,63 @@ chain_kernel(ChainArgs A) {
         A.tally[d] = T;
     }
     CH_MARK(9);
+}
+
+// ------------------------------------------------------------------------------------------------
+// evidence lists: the (pair, parent bits) and (informative site, parent bits) entries behind the
+// tallies, compacted per DNM in slot / list order -- what snv_phaser.py:169-203 turns into the
+// record's dad_reads / mom_reads / dad_sites / mom_sites.  One warp per DNM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+evidence_lists_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_t* __restrict__ seg_pair_off,
+                      const int32_t* __restrict__ site_pos, const uint32_t* __restrict__ cand_list,
+                      const int32_t* __restrict__ n_cand, const uint8_t* __restrict__ cand_evid,
+                      const int32_t* __restrict__ win, const int64_t* __restrict__ slot_off,
+                      const uint8_t* __restrict__ slot_evid, const int64_t* __restrict__ ev_off,
+                      int32_t* __restrict__ ev_read, uint8_t* __restrict__ ev_rbits, int32_t* __restrict__ ev_pos,
+                      uint8_t* __restrict__ ev_sbits, const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
+    const int lane = threadIdx.x & 31;
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_dnms) return;
+    const unsigned below = (1u << lane) - 1u;
+    const int64_t n1 = (int64_t)n_dnms + 1;
+    const int64_t nr = ev_off[d + 1] - ev_off[d], ns = ev_off[n1 + d + 1] - ev_off[n1 + d];
+    if (nr > 0) {
+        const int64_t nd = n_dnms;
+        const int64_t a_lo = win[d], a_hi = win[nd + d], b_lo = win[2 * nd + d], b_hi = win[3 * nd + d];
+        const int na = (int)(a_hi - a_lo), W = na + (int)(b_hi - b_lo);
+        const uint8_t* ev = slot_evid + slot_off[d];
+        int64_t k = ev_off[d];
+        for (int x0 = 0; x0 < W; x0 += 32) {
+            const int x = x0 + lane;
+            const uint8_t e = x < W ? ev[x] : 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, e != 0);
+            if (e) {
+                const int64_t at = k + __popc(bal & below);
+                ev_read[at] = (int32_t)(x < na ? a_lo + x : b_lo + (x - na));
+                ev_rbits[at] = e;
+            }
+            k += __popc(bal);
+        }
+    }
+    if (ns > 0) {
+        const UnfzDnm dn = dnms[d];
+        const int64_t lbase = seg_pair_off[dn.seg_lo];
+        const int nc = n_cand[d];
+        int64_t k = ev_off[n1 + d];
+        for (int j0 = 0; j0 < nc; j0 += 32) {
+            const int j = j0 + lane;
+            const uint8_t e = j < nc ? cand_evid[lbase + j] : 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, e != 0);
+            if (e) {
+                const int64_t at = k + __popc(bal & below);
+                ev_pos[at] = __ldg(site_pos + (int64_t)(cand_list[lbase + j] & 0x3fffffffu));
+                ev_sbits[at] = e;
+            }
+            k += __popc(bal);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1216,9 +1285,10 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
                                 const int32_t* win, const int32_t* site_lo, const int32_t* site_n, const int32_t* seed_win,
                                 const int64_t* off, const int64_t* h_totals, const UnfzParams* hp, void* scratch, int64_t scratch_bytes,
                                 uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid, UnfzTally* tally,
-                                void* stream) {
+                                int64_t* ev_need, void* stream) {
     if (n_dnms <= 0) return 0;
     ChainArgs A;
+    A.ev_need = ev_need;
     A.dnms = dnms; A.n_dnms = n_dnms; A.segs = segs; A.seg_pair_off = seg_pair_off;
     A.sites = *sites; A.reads = *reads; A.rsum = rsum; A.blk_maxspan = blk_maxspan; A.hits = hits; A.mp = mark_prefix;
     A.het_list = het_list; A.n_het = n_het; A.cand_list = cand_list; A.n_cand = n_cand; A.alleles = alleles;
@@ -1226,8 +1296,6 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     A.hit_tile_base = hit_tile_base; A.hit_tile_reads = hit_tile_reads;
     A.site_lo = site_lo; A.site_n = site_n; A.seed_win = seed_win;
     A.readlen = hp->readlen;
-    const double bq = hp->min_gt_qual;
-    A.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));
     A.ext_goal = hp->ext_read_goal;
     A.no_extended = hp->no_extended;
     A.slot_label = slot_label; A.slot_evid = slot_evid; A.cand_evid = cand_evid; A.tally = tally;
@@ -1237,6 +1305,19 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     if ((int64_t)(base - (uintptr_t)scratch) + total > scratch_bytes) return unfz_fail(ctx, -20, "chain scratch too small");
     A.guard = ctx->guard;
     chain_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int unfz_evidence_lists(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms, const int64_t* seg_pair_off,
+                                   const UnfzSiteCols* sites, const uint32_t* cand_list, const int32_t* n_cand,
+                                   const uint8_t* cand_evid, const int32_t* win, const int64_t* slot_off,
+                                   const uint8_t* slot_evid, const int64_t* ev_off, int32_t* ev_read, uint8_t* ev_rbits,
+                                   int32_t* ev_pos, uint8_t* ev_sbits, void* stream) {
+    if (n_dnms <= 0) return 0;
+    evidence_lists_kernel<<<(n_dnms + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+        dnms, n_dnms, seg_pair_off, sites->pos, cand_list, n_cand, cand_evid, win, slot_off, slot_evid, ev_off,
+        ev_read, ev_rbits, ev_pos, ev_sbits, ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -2,272 +2,45 @@
 // and the read-by-site allele lookup.
 //
 // read_scan is the bandwidth kernel of the read path: per read it must see the 32 B header, the
-// CIGAR words and every quality byte.  Reads are stored in file order, so the quality bytes (and the
-// CIGAR words) of consecutive reads are one contiguous span that is staged in shared memory by
-// asynchronous copies while earlier reads are being processed; every thread then counts the
-// low-quality bases of its own read out of shared memory with 4-byte SIMD compares.
-//   read_scan_warp_kernel  one cp.async pipeline per warp, 32 reads per tile (the kernel that runs)
-//   read_scan_kernel       CTA-wide tiles with chunked TMA bulk copies (cp.async.bulk + mbarrier) for
-//                          reads too long for a warp's slice
+// CIGAR words and one low-quality bit per base.  Reads are stored in file order, so the quality bits
+// (and the CIGAR words) of consecutive reads are one contiguous span that is staged in shared memory
+// by asynchronous copies while earlier reads are being processed; every thread then counts the
+// low-quality bases of its own read out of shared memory (five or six POPCs for 150 bases).
+//   read_scan_warp_kernel  one cp.async pipeline per warp, 32 reads per tile; reads too long for a
+//                          warp's slice are counted straight out of global memory
 #include "common.cuh"
 
 namespace {
 
-// ------------------------------------------------------------------------------------------------
-// mbarrier / TMA bulk-copy wrappers (sm_90+; on sm_100a these lower to UBLKCP / SYNCS)
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: read scan
 // ------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;                 // reads per tile
-constexpr int RS_QBUF = 48 * 1024;              // staged quality bytes per round
-constexpr int RS_SPOS = 128;                    // site positions staged per tile
-
 struct ScanParams {
     int32_t min_mapq;
-    int32_t min_bq;      // clamped to [0,128]
     int32_t readlen;
 };
 
-__device__ __forceinline__ int count_low_quals(const uint8_t* __restrict__ s, int beg, int end, uint32_t minq) {
-    // number of bytes b in s[beg,end) with (b & 0x7f) < minq; minq in [0,128].
-    // Per aligned 32-bit word: t = (x | 0x80808080) - m4 never borrows across bytes (the OR also drops
-    // the escape bit), and bit 7 of a byte of t is clear exactly when (x & 0x7f) < m.  The four flag
-    // bytes (0x80 or 0) are summed with one DP4A; the first and last word are masked to the range.
-    // No POPC (quarter-rate XU pipe, it was the top pipe in the first ncu capture) and no byte loops.
-    if (end <= beg) return 0;
-    const uint32_t m4 = minq * 0x01010101u;
-    const int w0 = beg & ~3, w1 = (end + 3) & ~3;
-    const uint32_t head = 0x80808080u << (8 * (beg & 3));                 // bytes >= beg inside the first word
-    const uint32_t tail = 0x80808080u >> (8 * ((4 - (end & 3)) & 3));     // bytes <  end inside the last word
-    unsigned acc = 0;
-    // first word (masked), unmasked middle words, last word (masked): the masks stay out of the loop
-    {
-        const uint32_t x = *reinterpret_cast<const uint32_t*>(s + w0);
-        uint32_t f = ~((x | 0x80808080u) - m4) & 0x80808080u & head;
-        if (w1 - w0 == 4) f &= tail;
-        acc = __dp4a(f, 0x01010101u, acc);
-    }
-    const int wl = w1 - 4;
-#pragma unroll 8
-    for (int i = w0 + 4; i < wl; i += 4) {
-        const uint32_t x = *reinterpret_cast<const uint32_t*>(s + i);
-        acc = __dp4a(~((x | 0x80808080u) - m4) & 0x80808080u, 0x01010101u, acc);
-    }
-    if (wl > w0) {
-        const uint32_t x = *reinterpret_cast<const uint32_t*>(s + wl);
-        acc = __dp4a(~((x | 0x80808080u) - m4) & 0x80808080u & tail, 0x01010101u, acc);
-    }
-    return (int)(acc >> 7);
+// number of set bits in [b0, b1) of a little-endian bit array (bit i = bit i&31 of word i>>5): the low-quality
+// bases of one read.  A 150-base read is five or six words; the first and the last one are masked.
+template <typename Ptr>
+__device__ __forceinline__ int count_bits(Ptr w, int b0, int b1) {
+    if (b1 <= b0) return 0;
+    const int w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
+    const uint32_t head = 0xffffffffu << (b0 & 31);
+    const uint32_t tail = 0xffffffffu >> (31 - ((b1 - 1) & 31));
+    if (w0 == w1) return __popc(w[w0] & head & tail);
+    int acc = __popc(w[w0] & head);
+#pragma unroll 4
+    for (int i = w0 + 1; i < w1; ++i) acc += __popc(w[i]);
+    return acc + __popc(w[w1] & tail);
 }
-
-__global__ void __launch_bounds__(RS_THREADS)
-read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
-                 UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb, int32_t* __restrict__ blk_maxspan,
-                 uint32_t* __restrict__ tile_tot, uint2* __restrict__ tile_info, const int32_t* __restrict__ guard) {
-    UNFZ_GUARD(guard);
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* qbuf = smem;                                             // RS_QBUF + 16
-    int32_t* spos = reinterpret_cast<int32_t*>(smem + RS_QBUF + 16);  // RS_SPOS
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int64_t s_qa, s_qb, s_row_base, s_row_end;
-    __shared__ int32_t s_rb0;
-    __shared__ int32_t s_maxspan;
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    uint32_t phase = 0;
-
-    const int64_t n = reads.n_reads;
-    const int64_t n_tiles = (n + RS_THREADS - 1) / RS_THREADS;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t r0 = tile * RS_THREADS;
-        const int64_t r = r0 + threadIdx.x;
-        const bool live = r < n;
-        UnfzRead h;
-        if (live) h = load_read(reads.hdr + r);
-        const int64_t q0 = live ? read_qoff(h) : 0;
-        const int L = live ? h.l_seq : 0;
-        if (threadIdx.x == 0) {
-            s_qa = q0;
-            s_rb0 = (int32_t)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r0) - 1);
-            s_maxspan = 0;
-        }
-        const int64_t last = min(r0 + RS_THREADS, n) - 1;
-        if (r == last) s_qb = q0 + L;
-        __syncthreads();
-        const int64_t qa = s_qa, qb = s_qb;
-        const int64_t ga = qa & ~(int64_t)15;
-        // round 0 of the quality staging is issued now so it overlaps the CIGAR walk below
-        int64_t chunk_lo = qb > qa ? ga : qb;
-        if (threadIdx.x == 0 && qb > qa) {
-            const uint32_t bytes = (uint32_t)min((int64_t)RS_QBUF, ((qb - chunk_lo) + 15) & ~(int64_t)15);
-            fence_proxy_async();
-            mbar_expect_tx(&bar, bytes);
-            tma_bulk_g2s(qbuf, reads.qual + chunk_lo, bytes, &bar);
-        }
-
-        // ---- block of this read, site rows of the tile ------------------------------------
-        int rb = s_rb0;
-        if (live && r >= reads.blk_off[rb + 1])
-            rb = (int)(upper_bound_dev(reads.blk_off, (int64_t)rb, (int64_t)reads.n_blocks + 1, r) - 1);
-        const int sb = live ? reads.blk_sblk[rb] : -1;
-        if (threadIdx.x == 0) {
-            int64_t rowb = 0, rowe = 0;
-            if (sb >= 0) {
-                rowe = sites.blk_off[sb + 1];
-                rowb = lower_bound_dev(sites.pos, sites.blk_off[sb], rowe, h.start);
-            }
-            s_row_base = rowb;
-            s_row_end = rowe;
-        }
-        __syncthreads();
-        const int64_t row_base = s_row_base, row_end = s_row_end;
-        for (int i = threadIdx.x; i < RS_SPOS; i += RS_THREADS)
-            spos[i] = (row_base + i < row_end) ? __ldg(sites.pos + row_base + i) : 0x7fffffff;
-
-        // ---- header flags + CIGAR walk -----------------------------------------------------
-        int32_t end = 0;
-        uint32_t flags = 0;
-        int none_cnt = 0, non_m = 0;
-        if (live) {
-            end = h.start;
-            const uint32_t* cg = reads.cigar + h.cigar_off;
-            for (int k = 0; k < h.n_cigar; ++k) {
-                const uint32_t w = __ldg(cg + k);
-                const uint32_t op = w & 15u, ln = w >> 4;
-                if (op == 0 || op == 7 || op == 8 || op == 2 || op == 3) end += (int32_t)ln;
-                if (op == 1 || op == 4) none_cnt += (int)ln;
-                if (op != 0 && op != 7) ++non_m;
-            }
-            const uint32_t f = h.flag;
-            const bool base_ok = !(f & (0x200u | 0x4u | 0x400u | 0x100u | 0x800u | 0x8u)) &&
-                                 (int)h.mapq >= P.min_mapq && (h.aux & 1u);
-            if (base_ok) flags |= UNFZ_RS_GOOD_DISC;
-            if (none_cnt <= 5) flags |= UNFZ_RS_NONE_OK;
-            if (non_m <= 5) flags |= UNFZ_RS_EXT_OK;
-            long long ins = (long long)h.tlen - 2ll * P.readlen;
-            if (ins < 0) ins = -ins;
-            if ((double)ins <= reads.blk_cul[rb]) flags |= UNFZ_RS_INS_OK;
-            if ((f & 1u) && !(f & 8u) && h.mate >= 0) flags |= UNFZ_RS_HAS_MATE;
-            atomicMax(&s_maxspan, end - h.start);
-        }
-        __syncthreads();   // spos visible
-
-        // ---- marked-site overlap count -------------------------------------------------------
-        int32_t fmark = 0, cnt = 0;
-        int64_t lbs = 0, lbe = 0;
-        if (live && sb >= 0) {
-            if (rb == s_rb0) {
-                int lo = 0, hi = RS_SPOS;
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (spos[mid] < h.start) lo = mid + 1; else hi = mid; }
-                int lo2 = lo; hi = RS_SPOS;
-                while (lo2 < hi) { int mid = (lo2 + hi) >> 1; if (spos[mid] < end) lo2 = mid + 1; else hi = mid; }
-                lbs = row_base + lo;
-                lbe = row_base + lo2;
-                if (lo2 == RS_SPOS) {     // ran off the staged window: finish in global memory
-                    if (lo == RS_SPOS) lbs = lower_bound_dev(sites.pos, row_base + RS_SPOS - 1, row_end, h.start);
-                    lbe = lower_bound_dev(sites.pos, lbs, row_end, end);
-                }
-            } else {
-                const int64_t a = sites.blk_off[sb], b = sites.blk_off[sb + 1];
-                lbs = lower_bound_dev(sites.pos, a, b, h.start);
-                lbe = lower_bound_dev(sites.pos, lbs, b, end);
-            }
-            fmark = __ldg(mark_prefix + lbs);
-            const int32_t c = __ldg(mark_prefix + lbe) - fmark;
-            cnt = c > 0xffff ? 0xffff : c;
-        }
-
-        uint32_t hoff = 0;                       // offset inside the 32-read hit tile (see the warp-specialised kernel)
-        {
-            const int lane = threadIdx.x & 31;
-            int x = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            hoff = (uint32_t)(x - cnt);
-            const int64_t rw = r0 + (threadIdx.x & ~31);
-            if (lane == 31 && rw < n) tile_tot[rw >> 5] = (uint32_t)x;
-            const unsigned has = __ballot_sync(0xffffffffu, cnt > 0);
-            if (tile_info && lane == 0 && rw < n)                 // who has hits + the block of the tile's first read
-                tile_info[rw >> 5] = make_uint2(has, (uint32_t)(upper_bound_dev(reads.blk_off, (int64_t)s_rb0, (int64_t)reads.n_blocks + 1, rw) - 1));
-        }
-        // ---- low-quality bases out of the staged span ---------------------------------------
-        int low = 0;
-        while (chunk_lo < qb) {
-            mbar_wait(&bar, phase);
-            phase ^= 1u;
-            const int64_t chunk_hi = chunk_lo + RS_QBUF;
-            if (live && L > 0) {
-                const int64_t a = max(q0, chunk_lo), b = min(q0 + (int64_t)L, min(chunk_hi, qb));
-                if (a < b) low += count_low_quals(qbuf, (int)(a - chunk_lo), (int)(b - chunk_lo), (uint32_t)P.min_bq);
-            }
-            chunk_lo = chunk_hi;
-            __syncthreads();     // everyone is done with qbuf
-            if (threadIdx.x == 0 && chunk_lo < qb) {
-                const uint32_t bytes = (uint32_t)min((int64_t)RS_QBUF, ((qb - chunk_lo) + 15) & ~(int64_t)15);
-                fence_proxy_async();
-                mbar_expect_tx(&bar, bytes);
-                tma_bulk_g2s(qbuf, reads.qual + chunk_lo, bytes, &bar);
-            }
-        }
-        if (live) {
-            // goodread(read): <= 10 low-quality bases and (Q3) <= 10 CIGAR operations
-            if ((flags & UNFZ_RS_GOOD_DISC) && low <= 10 && h.n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
-            UnfzReadSum o;
-            o.end = end;
-            o.fmark = fmark;
-            o.flags = (uint16_t)flags;
-            o.cnt = (uint16_t)cnt;
-            o.hoff = hoff;
-            *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
-            row_lb[r] = (int32_t)lbs;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0 && s_maxspan > 0) {
-            // a tile can straddle blocks; attribute the span to every block it touches (conservative)
-            const int rb_last = (int)(upper_bound_dev(reads.blk_off, (int64_t)s_rb0, (int64_t)reads.n_blocks + 1, last) - 1);
-            for (int b = s_rb0; b <= rb_last; ++b) atomicMax(blk_maxspan + b, s_maxspan);
-        }
-        __syncthreads();
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
-// K2, streaming variant (used when the quality bytes of 32 reads fit a slice): one independent
+// K2, streaming kernel: one independent
 // software pipeline PER WARP, no CTA-wide synchronisation at all.
 //
 // Measured on B200 (profiles/README.md, round 1d): a single asynchronous copy stream -- one TMA bulk
@@ -276,7 +49,7 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
 // for the fill, the producer waits for the consumers).  What saturates HBM is MANY concurrent
 // streams, so here every warp is its own stream:
 //  * a warp owns a contiguous range of 32-read tiles ("hit tiles") and two private slices of shared
-//    memory; while it works on tile T out of one slice, the quality bytes and CIGAR words of tile
+//    memory; while it works on tile T out of one slice, the quality bits and CIGAR words of tile
 //    T+1 -- each one contiguous span, because reads are stored in file order -- are in flight into
 //    the other slice (cp.async 16-byte chunks, one commit group per tile), and the headers of tile
 //    T+2 are in flight into registers;
@@ -285,7 +58,7 @@ read_scan_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restri
 //    ahead, so the steady state issues no dependent global load for it.  When a tile runs into the
 //    next read block that block's window is opened next to it and promoted when the tiles get there;
 //  * per read: CIGAR walk out of shared memory, branch-free search of the window, two mark-prefix
-//    gathers (L2), low-quality count with 4-byte SIMD compares + DP4A out of shared memory;
+//    gathers (L2), low-quality count by POPC over the staged bit span;
 //  * hit slots are numbered per tile: one warp scan, one total per tile, no cross-warp scan.
 // ------------------------------------------------------------------------------------------------
 // 5 warps x 4 CTAs per SM: the 20 warps spread evenly over the four sub-partitions (16 K registers each),
@@ -376,7 +149,6 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
     const int t1 = min(t0 + tpw, n_tiles);
     if (t0 >= t1) return;
     const uint32_t FULL = 0xffffffffu;
-    const uint32_t minq = (uint32_t)P.min_bq;
 
     auto load_hdr = [&](int T, uint4& a, uint4& b) {
         a = make_uint4(0, 0, 0, 0);
@@ -399,22 +171,24 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
             const long long l_q = __shfl_sync(FULL, q_self + (long long)(int32_t)b.y, nl - 1);
             const uint32_t f_c = __shfl_sync(FULL, a.w, 0);
             const uint32_t l_c = __shfl_sync(FULL, a.w + (b.z >> 16), nl - 1);
-            const long long qa = f_q & ~15ll;
-            const long long qspan = l_q > qa ? ((l_q - qa + 15) & ~15ll) : 0;
+            // bytes of the bit plane that hold bases [f_q, l_q), widened to 16-byte chunks
+            const long long qa = (f_q >> 3) & ~15ll;
+            const long long qspan = l_q > f_q ? ((((l_q + 7) >> 3) - qa + 15) & ~15ll) : 0;
             const uint32_t ca = f_c & ~3u;
             const long long cspan = l_c > ca ? (((long long)l_c - ca + 3) & ~3ll) : 0;
             sp.q_ok = qspan <= qslice;
             sp.cig_ok = cspan <= WP_CIGW && (long long)ca + cspan <= reads.n_cigar;
-            sp.qa_lo = (uint32_t)qa;
+            sp.qa_lo = (uint32_t)(qa << 3);                  // first staged BIT (low 32 bits; differences stay small)
             sp.ca = ca;
             const uint32_t o = lane * 16u;
             if (sp.q_ok) {
-                // lane-strided 16-byte chunks: the first 10 (5 KB: 32 reads of up to 152 bases) are unrolled
+                // lane-strided 16-byte chunks: the first two (1 KB: 32 reads of up to 250 bases) are unrolled
                 // with immediate offsets, longer slices finish in a loop
                 const uint32_t dst = smem_u32(my + k * qslice) + o;
-                const uint8_t* src = reads.qual + qa + o;
-                CpChunks<0, 10>::run(dst, src, o, (uint32_t)qspan);
-                for (uint32_t x = o + 5120u; x < (uint32_t)qspan; x += 512u) cp_async16(my + k * qslice + x, reads.qual + qa + x);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(reads.lowq) + qa + o;
+                CpChunks<0, 2>::run(dst, src, o, (uint32_t)qspan);
+                for (uint32_t x = o + 1024u; x < (uint32_t)qspan; x += 512u)
+                    cp_async16(my + k * qslice + x, reinterpret_cast<const uint8_t*>(reads.lowq) + qa + x);
             }
             if (sp.cig_ok)                                      // <= 256 bytes: one chunk per lane
                 cp_async16_at<0>(smem_u32(cigbuf + k * WP_CIGW) + o, reinterpret_cast<const uint8_t*>(reads.cigar + ca) + o,
@@ -593,11 +367,11 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
         if (live && l_seq > 0) {
             if (spA.q_ok) {
                 const int off = (int)(hAb.x - spA.qa_lo);
-                low = count_low_quals(my + k * qslice, off, off + l_seq, minq);
+                low = count_bits(reinterpret_cast<const uint32_t*>(my + k * qslice), off, off + l_seq);
             } else {
                 const int64_t q0 = (int64_t)hAb.x | ((int64_t)((hAb.w >> 16) & 0xffu) << 32);
-                const int off = (int)(q0 & 15);
-                low = count_low_quals(reads.qual + (q0 - off), off, off + l_seq, minq);
+                const int off = (int)(q0 & 31);
+                low = count_bits(reads.lowq + (q0 >> 5), off, off + l_seq);
             }
         }
         if (live && (flags & UNFZ_RS_GOOD_DISC) && low <= 10 && n_cigar <= 10) flags |= UNFZ_RS_GOOD_CONC;
@@ -693,9 +467,10 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
         const int q = cigar_qpos(cg, h.n_cigar, h.start, p);
         if (q >= 0 && q < 0xffff) {
             const int64_t g = q0 + q;
-            const uint32_t qb = __ldg(reads.qual + g);
+            const uint32_t lq = (__ldg(reads.lowq + (g >> 5)) >> (g & 31)) & 1u;
+            const uint32_t nb = (h.aux & 4u) ? ((__ldg(reads.nmask + (g >> 5)) >> (g & 31)) & 1u) : 0u;
             const uint32_t code = (__ldg(reads.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
-            word = (uint32_t)(q + 1) | (qb << 16) | (code << 24) | ((q + 1 < h.l_seq) ? (1u << 26) : 0u);
+            word = (uint32_t)(q + 1) | (lq << 16) | (nb << 23) | (code << 24) | ((q + 1 < h.l_seq) ? (1u << 26) : 0u);
         }
         if (k >= 0 && k < s.cnt) hits[hbase + k] = word;
         ++written;
@@ -704,8 +479,8 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
 
 }  // namespace
 
-// bytes of one quality slice of the streaming kernel: 32 reads + 16-byte alignment slop on either side
-static int wp_slice_bytes(int32_t max_l_seq) { return ((32 * max_l_seq + 15) & ~15) + 32; }
+// bytes of one quality-bit slice of the streaming kernel: 32 reads + 16-byte alignment slop on either side
+static int wp_slice_bytes(int32_t max_l_seq) { return (((32 * max_l_seq + 7) / 8 + 15) & ~15) + 32; }
 
 // hit slots are numbered per tile of this many consecutive reads (tile_tot / tile_base granularity)
 extern "C" int32_t unfz_read_scan_tile_reads(int32_t max_l_seq) { (void)max_l_seq; return 32; }
@@ -716,40 +491,59 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     if (reads->n_reads <= 0) return 0;
     ScanParams P;
     P.min_mapq = hp->min_map_qual;
-    double bq = hp->min_gt_qual;
-    P.min_bq = bq <= 0 ? 0 : (bq >= 128 ? 128 : (int32_t)ceil(bq));
     P.readlen = hp->readlen;
-    const int qslice = max_l_seq > 0 ? wp_slice_bytes(max_l_seq) : 0;
+    // reads too long for a 16 KB slice (> 4000 bases) are counted out of global memory (qslice 0: nothing staged)
+    int qslice = max_l_seq > 0 ? wp_slice_bytes(max_l_seq) : 0;
+    if (qslice > 16 * 1024) qslice = 0;
     const size_t smem2 = (size_t)WP_WARPS * (2 * (size_t)qslice + WP_FIXED);
-    if (max_l_seq > 0 && smem2 <= 200 * 1024) {
-        static size_t attr2 = 0;
-        if (smem2 > attr2) {
-            UNFZ_CHECK(ctx, cudaFuncSetAttribute(read_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            attr2 = smem2;
-        }
-        int per_sm = (int)((size_t)(228 * 1024) / (smem2 + 1024));
-        if (per_sm > WP_MINB) per_sm = WP_MINB;
-        if (per_sm < 1) per_sm = 1;
-        const int64_t tiles = (reads->n_reads + 31) / 32;
-        int64_t g = (int64_t)ctx->sm_count * per_sm;
-        if (g * WP_WARPS > tiles) g = (tiles + WP_WARPS - 1) / WP_WARPS;
-        read_scan_warp_kernel<<<(unsigned)g, WP_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, qslice,
-                                                                                     out, row_lb, blk_maxspan, tile_tot,
-                                                                                     reinterpret_cast<uint2*>(tile_info), ctx->guard);
-        UNFZ_LAUNCH_CHECK(ctx);
-        return 0;
+    // the opt-in shared-memory size is an attribute of the function ON ONE DEVICE: cached per device
+    if (ctx->scan_smem_attr < smem2) {
+        UNFZ_CHECK(ctx, cudaFuncSetAttribute(read_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        ctx->scan_smem_attr = smem2;
     }
-    const size_t smem = RS_QBUF + 16 + RS_SPOS * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        UNFZ_CHECK(ctx, cudaFuncSetAttribute(read_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const int64_t n_tiles = (reads->n_reads + RS_THREADS - 1) / RS_THREADS;
-    int64_t grid = (int64_t)ctx->sm_count * 4;     // 4 x ~49 KB of staging per SM
-    if (grid > n_tiles) grid = n_tiles;
-    read_scan_kernel<<<(unsigned)grid, RS_THREADS, smem, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, out, row_lb, blk_maxspan, tile_tot,
+    int per_sm = (int)((size_t)(228 * 1024) / (smem2 + 1024));
+    if (per_sm > WP_MINB) per_sm = WP_MINB;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t tiles = (reads->n_reads + 31) / 32;
+    int64_t g = (int64_t)ctx->sm_count * per_sm;
+    if (g * WP_WARPS > tiles) g = (tiles + WP_WARPS - 1) / WP_WARPS;
+    read_scan_warp_kernel<<<(unsigned)g, WP_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, qslice,
+                                                                                 out, row_lb, blk_maxspan, tile_tot,
                                                                                  reinterpret_cast<uint2*>(tile_info), ctx->guard);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload completion: sparse list of non-ACGT bases -> bit plane + per-read flag
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void expand_nlist_kernel(UnfzReadCols reads, UnfzRead* __restrict__ hdr, uint32_t* __restrict__ nmask,
+                                    const int64_t* __restrict__ nidx, int64_t n_idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_idx) return;
+    const int64_t g = nidx[i];
+    if (g < 0 || g >= reads.n_qual) return;
+    atomicOr(nmask + (g >> 5), 1u << (g & 31));
+    // owner: the last non-empty read whose first base is at or before g (offsets never decrease with the read index)
+    int64_t lo = 0, hi = reads.n_reads;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (read_qoff(hdr[mid]) <= g) lo = mid + 1; else hi = mid;
+    }
+    int64_t r = lo - 1;
+    while (r >= 0 && hdr[r].l_seq == 0) --r;
+    if (r < 0 || read_qoff(hdr[r]) + hdr[r].l_seq <= g) return;     // a base index between two reads: nobody owns it
+    // aux is byte 29 of the 32-byte header: set bit2 with a word-wide atomic (the neighbours are mapq, qoff_hi, pad)
+    unsigned* w = reinterpret_cast<unsigned*>(hdr + r) + 7;
+    atomicOr(w, 4u << 8);
+}
+}  // namespace
+
+extern "C" int unfz_expand_nlist(UnfzCtx* ctx, const UnfzReadCols* reads, UnfzRead* hdr_rw, uint32_t* nmask_rw,
+                                 const int64_t* nidx, int64_t n_idx, void* stream) {
+    if (n_idx <= 0 || reads->n_reads <= 0) return 0;
+    expand_nlist_kernel<<<(unsigned)((n_idx + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*reads, hdr_rw, nmask_rw, nidx, n_idx);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -22,7 +22,7 @@ import torch
 
 from . import _lib as L
 from .plan import Plan
-from .schema import ReadTable, SiteTable
+from .schema import ReadTable, SiteTable, min_base_qual
 
 
 def make_params(ab_homref=(0.0, 0.2), ab_homalt=(0.8, 1.0), ab_het=(0.2, 0.8), min_gt_qual=20, min_depth=10,
@@ -79,30 +79,63 @@ def make_site_cols(n_rows, n_blocks, blk_off, pos, ref, alt, meta, rec, dep) -> 
     return c
 
 
+class PackedReads:
+    """The read columns exactly as they cross PCIe (optionally in pinned memory): 32-byte headers,
+    CIGAR words, the low-quality bit plane for ONE base-quality threshold, 2-bit bases and the sorted
+    index list of the non-ACGT bases.  A packer that decodes a BAM can fill this directly; tables that
+    carry quality bytes (synthetic data, the oracle's fixtures) are reduced here."""
+
+    def __init__(self, table: ReadTable, min_bq: int, pin: bool = False):
+        self.table, self.min_bq = table, int(min_bq)
+        conv = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()) if pin else np.ascontiguousarray
+        self.hdr = conv(table.hdr.view(np.uint8).reshape(-1))
+        self.cigar = conv(table.cigar)
+        self.lowq = conv(table.lowq_plane(self.min_bq))
+        self.seq2 = conv(table.seq2)
+        self.nidx = conv(table.n_index())
+
+    @property
+    def nbytes(self) -> int:
+        return sum(int(a.nbytes) for a in (self.hdr, self.cigar, self.lowq, self.seq2, self.nidx))
+
+
 class DeviceReads:
-    def __init__(self, table: ReadTable, device: torch.device, pin: bool = False):
-        self.table = table
+    def __init__(self, table, device: torch.device, pin: bool = False, min_bq: int = 20, engine: "Engine" = None):
+        packed = table if isinstance(table, PackedReads) else PackedReads(table, min_bq)
+        table = packed.table
+        self.table, self.min_bq = table, packed.min_bq
         self.n_reads = table.n_reads
         self.max_l_seq = table.max_l_seq()
-        up = lambda a, pad=0: _to_device(np.ascontiguousarray(a), device, pin, pad)
-        self.blk_off = up(table.blk_off.astype(np.int64))
-        self.hdr = up(table.hdr.view(np.uint8).reshape(-1))
-        self.cigar = up(table.cigar)
-        # tail padding: the scan's asynchronous copies round the staged span up to 16 B
-        self.qual = up(table.qual, 32)
-        self.seq2 = up(table.seq2, 16)
+        up = lambda a, pad=0: _to_device(a, device, pin, pad)
+        self.blk_off = up(np.ascontiguousarray(table.blk_off.astype(np.int64)))
+        self.hdr = up(packed.hdr)
+        self.cigar = up(packed.cigar)
+        # tail padding: the scan's asynchronous copies round the staged span up to 16 B; planes are read as words
+        nq = int(table.qual.shape[0])
+        plane_bytes = (nq + 7) // 8
+        self.lowq = up(packed.lowq, 48 + (-plane_bytes) % 4)
+        self.seq2 = up(packed.seq2, 16)
+        self.nidx = up(packed.nidx)
+        self.nmask = torch.zeros(self.lowq.shape[0], dtype=torch.uint8, device=device)
+        self.h2d_bytes = packed.nbytes
         self.blk_sblk = torch.full((max(table.n_blocks, 1),), -1, dtype=torch.int32, device=device)
         self.blk_cul = torch.zeros((max(table.n_blocks, 1),), dtype=torch.float64, device=device)
         c = L.ReadCols()
         c.n_reads, c.n_blocks = table.n_reads, table.n_blocks
         c.blk_off, c.blk_sblk, c.blk_cul = self.blk_off.data_ptr(), self.blk_sblk.data_ptr(), self.blk_cul.data_ptr()
-        c.hdr, c.cigar, c.qual, c.seq2 = self.hdr.data_ptr(), self.cigar.data_ptr(), self.qual.data_ptr(), self.seq2.data_ptr()
-        c.n_qual, c.n_cigar = int(table.qual.shape[0]), int(table.cigar.shape[0])
+        c.hdr, c.cigar, c.seq2 = self.hdr.data_ptr(), self.cigar.data_ptr(), self.seq2.data_ptr()
+        c.lowq, c.nmask = self.lowq.data_ptr(), self.nmask.data_ptr()
+        c.n_qual, c.n_cigar = nq, int(table.cigar.shape[0])
         self.cols = c
+        if engine is not None and packed.nidx.shape[0]:
+            st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            engine._check(engine.lib.unfz_expand_nlist(engine.ctx, C.byref(c), self.hdr.data_ptr(), self.nmask.data_ptr(),
+                                                       self.nidx.data_ptr(), int(packed.nidx.shape[0]), st), "expand_nlist")
 
     @property
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.hdr, self.cigar, self.qual, self.seq2))
+        """Bytes that crossed PCIe for these columns."""
+        return self.h2d_bytes
 
 
 def _to_device(a: np.ndarray, device, pin: bool, pad: int = 0) -> torch.Tensor:
@@ -258,8 +291,13 @@ class Engine:
     def upload_sites(self, table: SiteTable, pin: bool = False) -> DeviceSites:
         return DeviceSites(table, self.device, pin)
 
-    def upload_reads(self, table: ReadTable, pin: bool = False) -> DeviceReads:
-        return DeviceReads(table, self.device, pin)
+    def upload_reads(self, table, pin: bool = False, min_gt_qual=20) -> DeviceReads:
+        """Read columns -> device.  ``table`` is a ReadTable (reduced to the low-quality plane of
+        ``min_gt_qual`` first) or a PackedReads (copied as it is)."""
+        return DeviceReads(table, self.device, pin, min_base_qual(min_gt_qual), self)
+
+    def pack_reads(self, table: ReadTable, min_gt_qual=20, pin: bool = True) -> PackedReads:
+        return PackedReads(table, min_base_qual(min_gt_qual), pin)
 
     def _check(self, rc: int, what: str):
         if rc != 0:
@@ -355,6 +393,10 @@ class Engine:
         p_all = p_seg + plan.seg.nbytes
         sc = C.byref(dsites.cols)
         has_reads = dreads is not None and N > 0 and bool((plan.dnm["rblk"] >= 0).any())
+        if has_reads and dreads.min_bq != min_base_qual(params.min_gt_qual):
+            raise ValueError("the read columns on the device hold the low-quality plane of base quality < %d, the call "
+                             "asks for < %d: upload them again with upload_reads(table, min_gt_qual=...)"
+                             % (dreads.min_bq, min_base_qual(params.min_gt_qual)))
 
         # ---- arena 1: everything whose size is known up front -------------------------------------
         z1, e1 = Arena(True), Arena(False)

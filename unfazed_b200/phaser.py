@@ -15,7 +15,7 @@ from . import _lib as L
 from .engine import BatchResult, DeviceReads, DeviceSites, Engine, make_params
 from .plan import (SNV_TYPES, SV_TYPES, Plan, SiteIndex, concat_plans, concordant_upper_lens,
                    plan_find_fast)
-from .schema import ReadTable, SiteTable
+from .schema import ReadTable, SiteTable, min_base_qual
 
 
 def dnm_key(dn: dict) -> str:
@@ -30,10 +30,24 @@ class BatchPhaser:
         self.sites, self.reads, self.ped = sites, reads, pedigrees
         self.sidx = SiteIndex(sites)
         self.dsites = dsites if dsites is not None else engine.upload_sites(sites)
-        self.dreads = dreads if dreads is not None else (engine.upload_reads(reads) if reads is not None else None)
+        # the read columns go up with the low-quality plane of one --min-gt-qual: uploaded at first use
+        self._dreads = dreads
         self._cul_cache: Dict[tuple, np.ndarray] = {}
 
     # -------------------------------------------------------------------------------------
+    def dreads_for(self, min_gt_qual=20) -> Optional[DeviceReads]:
+        if self.reads is None:
+            return None
+        mb = min_base_qual(min_gt_qual)
+        if self._dreads is None or self._dreads.min_bq != mb:
+            self._dreads = None                      # release the old planes first
+            self._dreads = self.engine.upload_reads(self.reads, min_gt_qual=min_gt_qual)
+        return self._dreads
+
+    @property
+    def dreads(self) -> Optional[DeviceReads]:
+        return self._dreads if self._dreads is not None else self.dreads_for(20)
+
     def cul(self, readlen, insert_size_max_sample, stdevs) -> Optional[np.ndarray]:
         if self.reads is None:
             return None
@@ -95,7 +109,7 @@ class BatchPhaser:
         plan = concat_plans(plans)
         params = make_params(ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, min_map_qual, readlen,
                              insert_size_max_sample, no_extended, evidence_min_ratio, split_error_margin)
-        res = self.engine.run(self.dsites, self.dreads, plan, params,
+        res = self.engine.run(self.dsites, self.dreads_for(min_gt_qual), plan, params,
                               blk_cul=self.cul(readlen, insert_size_max_sample, stdevs), time_stages=time_stages)
         return res, layout
 

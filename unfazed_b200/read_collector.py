@@ -85,7 +85,14 @@ def _collect(bam_name, region, het_sites, ref, alt, cram_ref, no_extended, conco
     # min_gt_qual is also the genotype-quality gate of the synthetic rows (GQ 99): keep them passing.
     # Base qualities never exceed 93, so clamping at 99 does not change any base-quality decision.
     params.min_gt_qual = min(float(min_gt_qual), 99.0)
-    res = eng.run(eng.upload_sites(sites), eng.upload_reads(reads), plan, params, blk_cul=cul)
+    # the device copy of a registered table is kept with the table (one upload per base-quality threshold)
+    from .schema import min_base_qual
+    key = (id(eng), min_base_qual(params.min_gt_qual))
+    cache = reads.__dict__.setdefault("_device_reads", {})
+    if key not in cache:
+        cache.clear()
+        cache[key] = eng.upload_reads(reads, min_gt_qual=params.min_gt_qual)
+    res = eng.run(eng.upload_sites(sites), cache[key], plan, params, blk_cul=cul)
     lab = res.slot_labels(0)
     out = {"alt": [], "ref": []} if no_extended else {"ref": [], "alt": []}
     xs = np.nonzero(lab)[0]

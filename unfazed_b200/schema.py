@@ -54,6 +54,18 @@ assert READ_HDR.itemsize == 32
 
 AUX_SAME_REF = 1
 AUX_HAS_SA = 2
+AUX_HAS_N = 4      # device copies only: some base of the read is not A/C/G/T (set by unfz_expand_nlist)
+
+
+def min_base_qual(min_gt_qual) -> int:
+    """--min-gt-qual as the integer base-quality threshold (read_collector.py:361-362): a phred
+    value q is an integer, so ``q < t`` is ``q < ceil(t)``; clamped to the 7 bits a quality has."""
+    t = float(min_gt_qual)
+    if t <= 0:
+        return 0
+    if t >= 128:
+        return 128
+    return int(np.ceil(t))
 
 # BAM CIGAR op codes (pysam cigartuples; reference utils.py:13-24)
 CIG_M, CIG_I, CIG_D, CIG_N, CIG_S, CIG_H, CIG_P, CIG_EQ, CIG_X, CIG_B = range(10)
@@ -180,6 +192,23 @@ class ReadTable:
             return self.names[r]
         m = int(self.hdr["mate"][r])
         return "q%d" % (min(r, m) if m >= 0 else r)
+
+    def lowq_plane(self, min_bq: int, chunk: int = 1 << 26) -> np.ndarray:
+        """One bit per query base, bit i&7 of byte i>>3: ``(qual & 0x7f) < min_bq``.  This is what the
+        device gets instead of the quality bytes -- every base-quality test of the path is this one
+        comparison (reference read_collector.py:44-46, :123, :281-284)."""
+        Q = int(self.qual.shape[0])
+        out = np.zeros((Q + 7) // 8, dtype=np.uint8)
+        for a in range(0, Q, chunk):
+            b = min(Q, a + chunk)                          # chunk is a multiple of 8
+            out[a >> 3: (b + 7) >> 3] = np.packbits((self.qual[a:b] & 0x7F) < min_bq, bitorder="little")
+        return out
+
+    def n_index(self, chunk: int = 1 << 26) -> np.ndarray:
+        """Sorted base indices of the non-ACGT bases (quality bit7)."""
+        Q = int(self.qual.shape[0])
+        parts = [np.flatnonzero(self.qual[a: a + chunk] & QUAL_ESCAPE) + a for a in range(0, Q, chunk)]
+        return np.concatenate(parts).astype(np.int64) if parts else np.zeros(0, dtype=np.int64)
 
     def ref_ends(self) -> np.ndarray:
         """reference_end (exclusive) of every read: start + lengths of M/D/N/=/X ops. Cached."""

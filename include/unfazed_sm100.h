@@ -307,19 +307,19 @@ int unfz_chain_tally(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const UnfzSe
                      const UnfzParams* h_params, void* scratch, int64_t scratch_bytes,
                      uint8_t* slot_label, uint8_t* slot_evid, uint8_t* cand_evid,
                      UnfzTally* tally,
-                     int64_t* ev_need /* [2][n_dnms] or NULL: pairs / candidate entries with evidence, for unfz_evidence_lists */,
+                     int64_t* ev_need /* [4][n_dnms] or NULL: list lengths for unfz_evidence_lists */,
                      void* stream);
 
-/* The entries behind the tallies, per DNM and in order: what snv_phaser.py:169-203 puts into the record's
- * dad_reads / mom_reads (ev_read = read index of the pair's window slot, ev_rbits bit0 dad / bit1 mom) and
- * dad_sites / mom_sites (ev_pos = 0-based position of the informative site, ev_sbits likewise; duplicates of a
- * site are kept, the reference builds a set).  ev_off[2][n_dnms+1] = exclusive scans of ev_need
- * (unfz_exclusive_scan_rows_i64); slot_off = row 0 of unfz_chain_tally's `off`. */
+/* The entries behind the tallies, per DNM, per parent and in order: what snv_phaser.py:169-203 puts into the record's
+ * dad_reads / mom_reads (read index of the pair's window slot) and dad_sites / mom_sites (0-based position of the
+ * informative site; duplicates of a site are kept, the reference builds a set).  ev_off[4][n_dnms+1] = exclusive
+ * scans of ev_need (unfz_exclusive_scan_rows_i64), rows: dad pairs, mom pairs, dad sites, mom sites;
+ * slot_off = row 0 of unfz_chain_tally's `off`. */
 int unfz_evidence_lists(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const int64_t* seg_pair_off,
                         const UnfzSiteCols* sites, const uint32_t* cand_list, const int32_t* n_cand,
                         const uint8_t* cand_evid, const int32_t* win, const int64_t* slot_off,
-                        const uint8_t* slot_evid, const int64_t* ev_off, int32_t* ev_read, uint8_t* ev_rbits,
-                        int32_t* ev_pos, uint8_t* ev_sbits, void* stream);
+                        const uint8_t* slot_evid, const int64_t* ev_off, int32_t* ev_read_dad, int32_t* ev_read_mom,
+                        int32_t* ev_pos_dad, int32_t* ev_pos_mom, void* stream);
 int64_t unfz_chain_scratch_bytes(int64_t slots, int64_t incs, int64_t seeds, int64_t seed_incs,
                                  int64_t het_sites, int64_t cand_sites, int64_t n_dnms);
 
@@ -370,9 +370,9 @@ typedef struct {
     uint8_t* cand_evid;
     /* sized by cap_hits / cap_chain */
     uint32_t* hits;  void* scratch;  int64_t scratch_bytes;  uint8_t* slot_label;  uint8_t* slot_evid;
-    /* evidence lists (all NULL: not wanted).  ev_need 2*n_dnms, ev_off 2*(n_dnms+1); ev_read / ev_rbits hold
-     * cap_chain[0] entries, ev_pos / ev_sbits cap_pairs entries (upper bounds of what can carry evidence) */
-    int64_t* ev_need;  int64_t* ev_off;  int32_t* ev_read;  uint8_t* ev_rbits;  int32_t* ev_pos;  uint8_t* ev_sbits;
+    /* evidence lists (all NULL: not wanted).  ev_need 4*n_dnms, ev_off 4*(n_dnms+1); ev_read_* hold cap_chain[0]
+     * entries each, ev_pos_* cap_pairs entries each (upper bounds of what can carry evidence) */
+    int64_t* ev_need;  int64_t* ev_off;  int32_t* ev_read_dad;  int32_t* ev_read_mom;  int32_t* ev_pos_dad;  int32_t* ev_pos_mom;
 } UnfzBatch;
 int unfz_run_batch(UnfzCtx*, const UnfzBatch* h_batch, void* stream);
 int unfz_batch_struct_bytes(void);      /* sizeof(UnfzBatch), for bindings to check their mirror */

@@ -63,6 +63,8 @@ class Batch(C.Structure):
         ("cls", c_void_p), ("het_list", c_void_p), ("cand_list", c_void_p), ("site_lo", c_void_p), ("site_n", c_void_p),
         ("seed_win", c_void_p), ("cand_evid", c_void_p),
         ("hits", c_void_p), ("scratch", c_void_p), ("scratch_bytes", c_int64), ("slot_label", c_void_p), ("slot_evid", c_void_p),
+        ("ev_need", c_void_p), ("ev_off", c_void_p), ("ev_read_dad", c_void_p), ("ev_read_mom", c_void_p),
+        ("ev_pos_dad", c_void_p), ("ev_pos_mom", c_void_p),
     ]
 
 
@@ -121,7 +123,8 @@ SYMBOLS = {
     "unfz_chain_scratch_bytes": (c_int64, [c_int64] * 7),
     "unfz_chain_tally": (C.c_int, [_P, _P, c_int32, _P, _P, C.POINTER(SiteCols), C.POINTER(ReadCols), _P, _P, _P, _P, c_int32, _P,
                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(Params), _P, c_int64,
-                                   _P, _P, _P, _P, _P]),
+                                   _P, _P, _P, _P, _P, _P]),
+    "unfz_evidence_lists": (C.c_int, [_P, _P, c_int32, _P, C.POINTER(SiteCols), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "unfz_insert_size_work_bytes": (c_int64, []),
     "unfz_insert_size_order_stats": (C.c_int, [_P, C.POINTER(ReadCols), _P, _P, c_int32, c_int32, _P, _P, _P, _P]),
     "unfz_summarize": (C.c_int, [_P, _P, c_int32, _P, _P, _P, _P, C.POINTER(Params), _P, _P, _P]),

@@ -114,10 +114,10 @@ extern "C" int unfz_run_batch(UnfzCtx* ctx, const UnfzBatch* b, void* s) {
                                  b->h_params, b->scratch, b->scratch_bytes, b->slot_label, b->slot_evid, b->cand_evid,
                                  b->tally, b->ev_need, s));
         if (b->ev_need != nullptr) {
-            UNFZ_RC(unfz_exclusive_scan_rows_i64(ctx, b->ev_need, b->ev_off, 2, n, s));
+            UNFZ_RC(unfz_exclusive_scan_rows_i64(ctx, b->ev_need, b->ev_off, 4, n, s));
             UNFZ_RC(unfz_evidence_lists(ctx, b->dnms, n, b->seg_pair_off, b->sites, b->cand_list, b->n_cand, b->cand_evid,
-                                        b->win, b->off, b->slot_evid, b->ev_off, b->ev_read, b->ev_rbits, b->ev_pos,
-                                        b->ev_sbits, s));
+                                        b->win, b->off, b->slot_evid, b->ev_off, b->ev_read_dad, b->ev_read_mom, b->ev_pos_dad,
+                                        b->ev_pos_mom, s));
         }
     }
     UNFZ_RC(unfz_summarize(ctx, b->dnms, n, b->tally, b->cnv_dad, b->cnv_mom, b->n_cand, b->h_params, b->calls_strict,

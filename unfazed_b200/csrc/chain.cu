@@ -59,7 +59,7 @@ struct ChainArgs {
     const int32_t* site_lo; const int32_t* site_n; const int32_t* seed_win;   // fetch ranges found by chain_size
     int32_t readlen, ext_goal, no_extended;
     uint8_t* slot_label; uint8_t* slot_evid; uint8_t* cand_evid; UnfzTally* tally;
-    int64_t* ev_need;             // [2][n_dnms] or null: pairs / candidate entries that carry evidence
+    int64_t* ev_need;             // [4][n_dnms] or null: dad pairs, mom pairs, dad site entries, mom site entries
     const int32_t* guard;
     Scratch S;
 };
@@ -385,7 +385,7 @@ chain_kernel(ChainArgs A) {
     if (dn.kind == UNFZ_KIND_SKIP || dn.rblk < 0 || nc <= 0 || dn.seg_hi <= dn.seg_lo) {
         if (tid == 0) {
             A.tally[d] = T;
-            if (A.ev_need) { A.ev_need[d] = 0; A.ev_need[(int64_t)A.n_dnms + d] = 0; }
+            if (A.ev_need) for (int q = 0; q < 4; ++q) A.ev_need[(int64_t)q * A.n_dnms + d] = 0;
         }
         return;
     }
@@ -914,10 +914,11 @@ chain_kernel(ChainArgs A) {
 
     CH_MARK(8);
     // ---------------------------------------------------------------- phase 6: tally
-    int ds = 0, ms = 0, dr = 0, mr = 0, er = 0, es = 0;
+    int ds = 0, ms = 0, dr = 0, mr = 0, esd = 0, esm = 0;
     for (int j = tid; j < nc; j += CH_THREADS) {
         const uint8_t b = cev[j];
-        es += b != 0;
+        esd += b & 1;
+        esm += (b >> 1) & 1;
         for (int bit = 1; bit <= 2; ++bit) {
             if (!(b & bit)) continue;
             bool first = true;                      // unique str(pos): count the first duplicate only
@@ -929,11 +930,9 @@ chain_kernel(ChainArgs A) {
     for (int x = tid; x < W; x += CH_THREADS) {
         dr += evid[x] & 1;
         mr += (evid[x] >> 1) & 1;
-        er += evid[x] != 0;
     }
     if (A.ev_need) {
-        er = block_sum(er); es = block_sum(es);
-        if (tid == 0) { A.ev_need[d] = er; A.ev_need[(int64_t)A.n_dnms + d] = es; }
+        esd = block_sum(esd); esm = block_sum(esm);
     }
     ds = block_sum(ds); ms = block_sum(ms); dr = block_sum(dr); mr = block_sum(mr);
     has_rec = block_sum(has_rec);
@@ -941,14 +940,18 @@ chain_kernel(ChainArgs A) {
         T.n_dad_sites = ds; T.n_mom_sites = ms; T.n_dad_reads = dr; T.n_mom_reads = mr;
         T.has_record = has_rec > 0;
         A.tally[d] = T;
+        if (A.ev_need) {                        // list lengths of unfz_evidence_lists (site entries keep duplicates)
+            const int64_t n = A.n_dnms;
+            A.ev_need[d] = dr; A.ev_need[n + d] = mr; A.ev_need[2 * n + d] = esd; A.ev_need[3 * n + d] = esm;
+        }
     }
     CH_MARK(9);
 }
 
 // ------------------------------------------------------------------------------------------------
-// evidence lists: the (pair, parent bits) and (informative site, parent bits) entries behind the
-// tallies, compacted per DNM in slot / list order -- what snv_phaser.py:169-203 turns into the
-// record's dad_reads / mom_reads / dad_sites / mom_sites.  One warp per DNM.
+// evidence lists: the pairs and informative sites behind the tallies, per DNM and per parent, in
+// slot / list order -- what snv_phaser.py:169-203 turns into the record's dad_reads / mom_reads /
+// dad_sites / mom_sites.  One warp per DNM; ev_off[4][n+1] = dad pairs, mom pairs, dad sites, mom sites.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 evidence_lists_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_t* __restrict__ seg_pair_off,
@@ -956,48 +959,47 @@ evidence_lists_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const in
                       const int32_t* __restrict__ n_cand, const uint8_t* __restrict__ cand_evid,
                       const int32_t* __restrict__ win, const int64_t* __restrict__ slot_off,
                       const uint8_t* __restrict__ slot_evid, const int64_t* __restrict__ ev_off,
-                      int32_t* __restrict__ ev_read, uint8_t* __restrict__ ev_rbits, int32_t* __restrict__ ev_pos,
-                      uint8_t* __restrict__ ev_sbits, const int32_t* __restrict__ guard) {
+                      int32_t* __restrict__ ev_read_dad, int32_t* __restrict__ ev_read_mom,
+                      int32_t* __restrict__ ev_pos_dad, int32_t* __restrict__ ev_pos_mom,
+                      const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
     const int lane = threadIdx.x & 31;
     const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_dnms) return;
     const unsigned below = (1u << lane) - 1u;
     const int64_t n1 = (int64_t)n_dnms + 1;
-    const int64_t nr = ev_off[d + 1] - ev_off[d], ns = ev_off[n1 + d + 1] - ev_off[n1 + d];
-    if (nr > 0) {
+    int64_t kd = ev_off[d], km = ev_off[n1 + d];
+    if (ev_off[d + 1] > kd || ev_off[n1 + d + 1] > km) {
         const int64_t nd = n_dnms;
         const int64_t a_lo = win[d], a_hi = win[nd + d], b_lo = win[2 * nd + d], b_hi = win[3 * nd + d];
         const int na = (int)(a_hi - a_lo), W = na + (int)(b_hi - b_lo);
         const uint8_t* ev = slot_evid + slot_off[d];
-        int64_t k = ev_off[d];
         for (int x0 = 0; x0 < W; x0 += 32) {
             const int x = x0 + lane;
             const uint8_t e = x < W ? ev[x] : 0;
-            const unsigned bal = __ballot_sync(0xffffffffu, e != 0);
-            if (e) {
-                const int64_t at = k + __popc(bal & below);
-                ev_read[at] = (int32_t)(x < na ? a_lo + x : b_lo + (x - na));
-                ev_rbits[at] = e;
-            }
-            k += __popc(bal);
+            const int32_t r = (int32_t)(x < na ? a_lo + x : b_lo + (x - na));
+            const unsigned bd = __ballot_sync(0xffffffffu, e & 1), bm = __ballot_sync(0xffffffffu, e & 2);
+            if (e & 1) ev_read_dad[kd + __popc(bd & below)] = r;
+            if (e & 2) ev_read_mom[km + __popc(bm & below)] = r;
+            kd += __popc(bd);
+            km += __popc(bm);
         }
     }
-    if (ns > 0) {
+    kd = ev_off[2 * n1 + d];
+    km = ev_off[3 * n1 + d];
+    if (ev_off[2 * n1 + d + 1] > kd || ev_off[3 * n1 + d + 1] > km) {
         const UnfzDnm dn = dnms[d];
         const int64_t lbase = seg_pair_off[dn.seg_lo];
         const int nc = n_cand[d];
-        int64_t k = ev_off[n1 + d];
         for (int j0 = 0; j0 < nc; j0 += 32) {
             const int j = j0 + lane;
             const uint8_t e = j < nc ? cand_evid[lbase + j] : 0;
-            const unsigned bal = __ballot_sync(0xffffffffu, e != 0);
-            if (e) {
-                const int64_t at = k + __popc(bal & below);
-                ev_pos[at] = __ldg(site_pos + (int64_t)(cand_list[lbase + j] & 0x3fffffffu));
-                ev_sbits[at] = e;
-            }
-            k += __popc(bal);
+            const int32_t p = e ? __ldg(site_pos + (int64_t)(cand_list[lbase + j] & 0x3fffffffu)) : 0;
+            const unsigned bd = __ballot_sync(0xffffffffu, e & 1), bm = __ballot_sync(0xffffffffu, e & 2);
+            if (e & 1) ev_pos_dad[kd + __popc(bd & below)] = p;
+            if (e & 2) ev_pos_mom[km + __popc(bm & below)] = p;
+            kd += __popc(bd);
+            km += __popc(bm);
         }
     }
 }
@@ -1312,12 +1314,12 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
 extern "C" int unfz_evidence_lists(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnms, const int64_t* seg_pair_off,
                                    const UnfzSiteCols* sites, const uint32_t* cand_list, const int32_t* n_cand,
                                    const uint8_t* cand_evid, const int32_t* win, const int64_t* slot_off,
-                                   const uint8_t* slot_evid, const int64_t* ev_off, int32_t* ev_read, uint8_t* ev_rbits,
-                                   int32_t* ev_pos, uint8_t* ev_sbits, void* stream) {
+                                   const uint8_t* slot_evid, const int64_t* ev_off, int32_t* ev_read_dad, int32_t* ev_read_mom,
+                                   int32_t* ev_pos_dad, int32_t* ev_pos_mom, void* stream) {
     if (n_dnms <= 0) return 0;
     evidence_lists_kernel<<<(n_dnms + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         dnms, n_dnms, seg_pair_off, sites->pos, cand_list, n_cand, cand_evid, win, slot_off, slot_evid, ev_off,
-        ev_read, ev_rbits, ev_pos, ev_sbits, ctx->guard);
+        ev_read_dad, ev_read_mom, ev_pos_dad, ev_pos_mom, ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

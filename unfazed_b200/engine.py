@@ -169,6 +169,9 @@ class BatchResult:
     calls_ambiguous: Optional[np.ndarray] = None
     win: Optional[np.ndarray] = None          # [4, n]: read-index ranges [a_lo,a_hi) U [b_lo,b_hi) of every entry
     slot_off: Optional[np.ndarray] = None
+    # evidence lists (Engine.run(evidence=True)): off int64[4][n+1] (dad pairs, mom pairs, dad sites, mom sites) and the
+    # four int32 lists read_dad / read_mom (read indices) / pos_dad / pos_mom (site positions)
+    ev: Optional[dict] = None
     timings_ms: Dict[str, float] = field(default_factory=dict)
     launches: int = 0
     _dev: dict = field(default_factory=dict)
@@ -324,7 +327,7 @@ class Engine:
 
     def run(self, dsites: DeviceSites, dreads: Optional[DeviceReads], plan: Plan, params: L.Params,
             blk_cul: Optional[np.ndarray] = None, time_stages: bool = False, download: bool = True,
-            keep_device: bool = True, speculative: bool = True) -> BatchResult:
+            keep_device: bool = True, speculative: bool = True, evidence: bool = False) -> BatchResult:
         """One batch through the pipeline.  The sizes of the variable outputs (pairs; hits + chain
         scratch) are only known on the device.  The first batch reads them back (two host syncs); later
         batches allocate from the capacities the engine has seen (+25 %), have the device check them
@@ -411,6 +414,9 @@ class Engine:
         z1.add("result", 4 * acc)
         z1.add("guard", 256)                      # int32 flag + int64 actual[8] at +64
         z1.add("seg_pair_off", 8 * (S + 1))
+        want_ev = bool(evidence and has_reads and download)
+        if want_ev:
+            z1.add("ev_off", 8 * 4 * (n + 1))
         dl_end = z1.size
         if has_reads:
             z1.add("off", 8 * (6 * (n + 1) + 1))
@@ -422,6 +428,8 @@ class Engine:
         if has_reads:
             z1.add("blk_maxspan", 4 * max(dreads.table.n_blocks, 1))
             z1.add("need", 8 * 6 * n)
+            if want_ev:
+                z1.add("ev_need", 8 * 4 * n)
             e1.add("rsum", 16 * N)
             e1.add("row_lb", 4 * N)
             tile_reads = int(lib.unfz_read_scan_tile_reads(dreads.max_l_seq))
@@ -445,6 +453,9 @@ class Engine:
                 e.add("site_n", 4 * n_pairs_)
                 e.add("seed_win", 16 * n)
             z.add("cand_evid", n_pairs_ + 8)
+            if want_ev:
+                e.add("ev_pos_dad", 4 * n_pairs_ + 16)
+                e.add("ev_pos_mom", 4 * n_pairs_ + 16)
             z.alloc()
             e.alloc()
             return z, e
@@ -456,6 +467,9 @@ class Engine:
             e.add("scratch", nb)
             z.add("slot_label", int(totals_[0]) + 4)
             z.add("slot_evid", int(totals_[0]) + 4)
+            if want_ev:
+                e.add("ev_read_dad", 4 * int(totals_[0]) + 16)
+                e.add("ev_read_mom", 4 * int(totals_[0]) + 16)
             z.alloc()
             e.alloc()
             return z, e, nb
@@ -517,8 +531,12 @@ class Engine:
                 b.site_lo, b.site_n, b.seed_win = e2.ptr["site_lo"], e2.ptr["site_n"], e2.ptr["seed_win"]
                 b.hits, b.scratch, b.scratch_bytes = e3.ptr["hits"], e3.ptr["scratch"], nbytes
                 b.slot_label, b.slot_evid = z3.ptr["slot_label"], z3.ptr["slot_evid"]
+                if want_ev:
+                    b.ev_need, b.ev_off = z1.ptr["ev_need"], z1.ptr["ev_off"]
+                    b.ev_read_dad, b.ev_read_mom = e3.ptr["ev_read_dad"], e3.ptr["ev_read_mom"]
+                    b.ev_pos_dad, b.ev_pos_mom = e2.ptr["ev_pos_dad"], e2.ptr["ev_pos_mom"]
             self._check(lib.unfz_run_batch(ctx, C.byref(b), s), "run_batch")
-            launches += 20 if has_reads else 11
+            launches += (20 if has_reads else 11) + (2 if want_ev else 0)
             h_pair_off, h_off = None, None
             res = BatchResult(plan=plan, n_pairs=int(caps["pairs"]), n_hits=int(caps["hits"]) if has_reads else 0,
                               seg_row_lo=None, seg_pair_off=None, n_het=None, n_cand=None, cnv_dad=None, cnv_mom=None)
@@ -628,10 +646,20 @@ class Engine:
                                                  rp["n_het"], e2.ptr["cand_list"], rp["n_cand"], p_all, rp["win"], e2.ptr["site_lo"], e2.ptr["site_n"],
                                                  e2.ptr["seed_win"], off_ptr,
                                                  totals.ctypes.data, C.byref(params), e3.ptr["scratch"], nbytes,
-                                                 z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"], s),
+                                                 z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"],
+                                                 z1.ptr["ev_need"] if want_ev else None, s),
                             "chain_tally")
                 launches += 1
                 mark("chain_tally")
+                if want_ev:
+                    self._check(lib.unfz_exclusive_scan_rows_i64(ctx, z1.ptr["ev_need"], z1.ptr["ev_off"], 4, n, s), "scan(ev)")
+                    self._check(lib.unfz_evidence_lists(ctx, p_dnm, n, z1.ptr["seg_pair_off"], sc, e2.ptr["cand_list"], rp["n_cand"],
+                                                        z2.ptr["cand_evid"], rp["win"], off_ptr, z3.ptr["slot_evid"], z1.ptr["ev_off"],
+                                                        e3.ptr["ev_read_dad"], e3.ptr["ev_read_mom"], e2.ptr["ev_pos_dad"],
+                                                        e2.ptr["ev_pos_mom"], s),
+                                "evidence_lists")
+                    launches += 2
+                    mark("evidence_lists")
                 dv.update(rsum=e1.view["rsum"], hits=e3.view["hits"].view(torch.int32),
                           tile_base=e1.view["tile_base"].view(torch.int32), tile_reads=tile_reads, slot_label=z3.view["slot_label"],
                           slot_evid=z3.view["slot_evid"], row_mark=z1.view["row_mark"],
@@ -647,6 +675,7 @@ class Engine:
             lib.unfz_ctx_set_guard(ctx, None)
         if download:
             front = self._download(z1.buf[:dl_end])
+            self.last_d2h_bytes = int(dl_end)
             item = {nm: (off, nb) for nm, off, nb in z1.items}
             sect = lambda nm: front[item[nm][0]: item[nm][0] + item[nm][1]]
             hr = sect("result").view(np.int32)
@@ -658,7 +687,7 @@ class Engine:
                     self._caps = None
                     dv.clear()
                     return self.run(dsites, dreads, plan, params, blk_cul=blk_cul, time_stages=time_stages,
-                                    download=download, keep_device=keep_device, speculative=False)
+                                    download=download, keep_device=keep_device, speculative=False, evidence=evidence)
                 h_pair_off = sect("seg_pair_off").view(np.int64)[: S + 1].copy()
                 res.seg_pair_off = h_pair_off
                 res.n_pairs = int(actual[0])
@@ -687,6 +716,21 @@ class Engine:
             res.calls_strict = g("calls_s", 4 * n).view(L.CALL_DTYPE)
             res.calls_ambiguous = g("calls_a", 4 * n).view(L.CALL_DTYPE)
             res.win = g("win", 4 * n).reshape(4, n)
+            if want_ev:
+                # second, small download: the evidence lists, now that their lengths are on the host
+                eo = sect("ev_off").view(np.int64).reshape(4, n + 1).copy()
+                tot = [int(eo[q, n]) for q in range(4)]
+                parts = [(e3.view["ev_read_dad"], 4 * tot[0]), (e3.view["ev_read_mom"], 4 * tot[1]),
+                         (e2.view["ev_pos_dad"], 4 * tot[2]), (e2.view["ev_pos_mom"], 4 * tot[3])]
+                bufs = []
+                for t_, nb_ in parts:
+                    hb = torch.empty((max(nb_, 4),), dtype=torch.uint8, pin_memory=True)
+                    if nb_:
+                        hb[:nb_].copy_(t_[:nb_], non_blocking=True)
+                    bufs.append(hb.numpy()[:nb_].view(np.int32))
+                torch.cuda.current_stream(dev).synchronize()
+                res.ev = {"off": eo, "read_dad": bufs[0], "read_mom": bufs[1], "pos_dad": bufs[2], "pos_mom": bufs[3]}
+                self.last_d2h_bytes += 4 * sum(tot)
         mark("download")
         res.launches = launches
         if time_stages:

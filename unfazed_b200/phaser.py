@@ -12,7 +12,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import _lib as L
-from .engine import BatchResult, DeviceReads, DeviceSites, Engine, make_params
+from .engine import BatchResult, DeviceReads, DeviceSites, Engine, PackedReads, make_params
 from .plan import (SNV_TYPES, SV_TYPES, Plan, SiteIndex, concat_plans, concordant_upper_lens,
                    plan_find_fast)
 from .schema import ReadTable, SiteTable, min_base_qual
@@ -24,29 +24,48 @@ def dnm_key(dn: dict) -> str:
 
 
 class BatchPhaser:
-    def __init__(self, engine: Engine, sites: SiteTable, reads: Optional[ReadTable], pedigrees: dict,
-                 dsites: Optional[DeviceSites] = None, dreads: Optional[DeviceReads] = None):
+    """``resident=True`` (default): the site and read columns are uploaded once and stay in HBM across
+    calls.  ``resident=False``: every call copies them from the host arrays it was given (pinned
+    arrays copy asynchronously) and releases them afterwards -- the end-to-end mode of ``bench.py``.
+    ``reads`` is a ReadTable or an engine.PackedReads (the columns as they cross PCIe)."""
+
+    def __init__(self, engine: Engine, sites: SiteTable, reads, pedigrees: dict,
+                 dsites: Optional[DeviceSites] = None, dreads: Optional[DeviceReads] = None, resident: bool = True):
         self.engine = engine
-        self.sites, self.reads, self.ped = sites, reads, pedigrees
+        self.packed = reads if isinstance(reads, PackedReads) else None
+        self.sites, self.reads, self.ped = sites, (reads.table if self.packed is not None else reads), pedigrees
         self.sidx = SiteIndex(sites)
-        self.dsites = dsites if dsites is not None else engine.upload_sites(sites)
+        self.resident = resident
+        self._dsites = dsites
         # the read columns go up with the low-quality plane of one --min-gt-qual: uploaded at first use
         self._dreads = dreads
         self._cul_cache: Dict[tuple, np.ndarray] = {}
+        self.last_timing: Dict[str, float] = {}
 
     # -------------------------------------------------------------------------------------
+    @property
+    def dsites(self) -> DeviceSites:
+        if self._dsites is None:
+            self._dsites = self.engine.upload_sites(self.sites)
+        return self._dsites
+
     def dreads_for(self, min_gt_qual=20) -> Optional[DeviceReads]:
         if self.reads is None:
             return None
         mb = min_base_qual(min_gt_qual)
         if self._dreads is None or self._dreads.min_bq != mb:
             self._dreads = None                      # release the old planes first
-            self._dreads = self.engine.upload_reads(self.reads, min_gt_qual=min_gt_qual)
+            src = self.packed if (self.packed is not None and self.packed.min_bq == mb) else self.reads
+            self._dreads = self.engine.upload_reads(src, min_gt_qual=min_gt_qual)
         return self._dreads
 
     @property
     def dreads(self) -> Optional[DeviceReads]:
         return self._dreads if self._dreads is not None else self.dreads_for(20)
+
+    def release_device(self):
+        self._dsites = None
+        self._dreads = None
 
     def cul(self, readlen, insert_size_max_sample, stdevs) -> Optional[np.ndarray]:
         if self.reads is None:
@@ -76,13 +95,11 @@ class BatchPhaser:
         return cands, hets
 
     # -------------------------------------------------------------------------------------
-    def run(self, snvs: List[dict], svs: List[dict], *, threads=2, build="38", no_extended=False,
-            multiread_proc_min=1000, ab_homref=(0.0, 0.2), ab_homalt=(0.8, 1.0), ab_het=(0.2, 0.8),
-            min_gt_qual=20, min_depth=10, search_dist=5000, insert_size_max_sample=1000000, stdevs=3,
-            min_map_qual=1, readlen=151, split_error_margin=5, evidence_min_ratio=10,
-            time_stages=False):
-        """Plan + run all entries of one call.  Returns (result, layout) where layout gives the
-        entry ranges: cnv entries of the SVs, read entries of the SVs, read entries of the SNVs."""
+    def plan_batch(self, snvs: List[dict], svs: List[dict], *, threads=2, build="38", multiread_proc_min=1000,
+                   search_dist=5000):
+        """Window plan of one call: the CNV entries of the SVs (find with search_dist 0, whole region:
+        sv_phaser.py:375-389), the read entries of the SVs, the read entries of the SNVs.  Returns
+        (plan, layout) where layout gives the three entry ranges."""
         common = dict(build=build, multiread_proc_min=multiread_proc_min, threads=threads)
         plans: List[Plan] = []
         n0 = 0
@@ -106,11 +123,36 @@ class BatchPhaser:
         if snvs:
             add(snvs, search_dist=search_dist, whole_region=False, with_reads=True)
             layout["snv"] = (n0 - len(snvs), n0)
-        plan = concat_plans(plans)
+        return concat_plans(plans), layout
+
+    def run(self, snvs: List[dict], svs: List[dict], *, threads=2, build="38", no_extended=False,
+            multiread_proc_min=1000, ab_homref=(0.0, 0.2), ab_homalt=(0.8, 1.0), ab_het=(0.2, 0.8),
+            min_gt_qual=20, min_depth=10, search_dist=5000, insert_size_max_sample=1000000, stdevs=3,
+            min_map_qual=1, readlen=151, split_error_margin=5, evidence_min_ratio=10,
+            time_stages=False, evidence=True):
+        """Plan + run all entries of one call.  Returns (result, layout)."""
+        import time as _t
+        t0 = _t.perf_counter()
+        if not self.resident:
+            # the copies are asynchronous when the host arrays are pinned: the windows are planned while they fly
+            self.release_device()
+            _ = self.dsites
+            self.dreads_for(min_gt_qual)
+        t1 = _t.perf_counter()
+        plan, layout = self.plan_batch(snvs, svs, threads=threads, build=build, multiread_proc_min=multiread_proc_min,
+                                       search_dist=search_dist)
+        t2 = _t.perf_counter()
         params = make_params(ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, min_map_qual, readlen,
                              insert_size_max_sample, no_extended, evidence_min_ratio, split_error_margin)
-        res = self.engine.run(self.dsites, self.dreads_for(min_gt_qual), plan, params,
-                              blk_cul=self.cul(readlen, insert_size_max_sample, stdevs), time_stages=time_stages)
+        dreads = self.dreads_for(min_gt_qual)
+        res = self.engine.run(self.dsites, dreads, plan, params,
+                              blk_cul=self.cul(readlen, insert_size_max_sample, stdevs), time_stages=time_stages,
+                              evidence=evidence)
+        t3 = _t.perf_counter()
+        if not self.resident:
+            self.release_device()
+        self.last_timing = {"issue_uploads_ms": (t1 - t0) * 1e3, "plan_ms": (t2 - t1) * 1e3,
+                            "run_until_results_ms": (t3 - t2) * 1e3}
         return res, layout
 
     # -------------------------------------------------------------------------------------
@@ -171,16 +213,39 @@ class BatchPhaser:
                 "cnv_dad_sites": vd, "cnv_mom_sites": vm, "cnv_evidence_type": "ALLELE-BALANCE",
                 "dad_sites": "", "mom_sites": "", "evidence_type": "", "dad_reads": [], "mom_reads": [],
             }
+        ev = res.ev
+        if ev is not None:
+            # evidence lists compacted per DNM and per parent on the device: every string of the batch is made in
+            # four flat passes, a record is then slices of those lists (no per-read work in the loop below)
+            nm_d, nm_m = self.reads.names_of(ev["read_dad"]), self.reads.names_of(ev["read_mom"])
+            sp_d, sp_m = list(map(str, ev["pos_dad"].tolist())), list(map(str, ev["pos_mom"].tolist()))
+            o_rd, o_rm, o_sd, o_sm = (ev["off"][q].tolist() for q in range(4))
+        flags = plan.dnm["flags"].tolist()
+        has = res.tally["has_record"].tolist() if res.tally is not None else None
+        ped = self.ped
         for name, out in (("sv_read", out_sv), ("snv", out_snv)):
             a, b = layout[name]
             for d in range(a, b):
                 dn = plan.entries[d]
-                dad, mom = self.ped[dn["kid"]]["dad"], self.ped[dn["kid"]]["mom"]
-                if plan.dnm["flags"][d] & L.DNM_AUTOPHASE:
-                    out[dnm_key(dn)] = self._auto_record(dn, dad, mom)
+                if flags[d] & L.DNM_AUTOPHASE:
+                    out[dnm_key(dn)] = self._auto_record(dn, ped[dn["kid"]]["dad"], ped[dn["kid"]]["mom"])
                     continue
-                if res.tally is not None and res.tally["has_record"][d]:
+                if has is None or not has[d]:
+                    continue
+                if ev is None:
                     out[dnm_key(dn)] = self._read_record(res, d, dn)
+                    continue
+                kid = dn["kid"]
+                # one pair = one window slot = one name, so the read lists are unique as they come (slot order); a site
+                # seen through two overlapping windows (Q9) appears twice, the reference keeps a set of str(pos)
+                out[dnm_key(dn)] = {
+                    "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
+                    "vartype": dn["vartype"], "kid": kid, "dad": ped[kid]["dad"], "mom": ped[kid]["mom"],
+                    "dad_sites": sorted(set(sp_d[o_sd[d]:o_sd[d + 1]])),
+                    "mom_sites": sorted(set(sp_m[o_sm[d]:o_sm[d + 1]])), "evidence_type": "readbacked",
+                    "dad_reads": nm_d[o_rd[d]:o_rd[d + 1]], "mom_reads": nm_m[o_rm[d]:o_rm[d + 1]],
+                    "cnv_dad_sites": "", "cnv_mom_sites": "", "cnv_evidence_type": "",
+                }
         for k, c in cnv.items():                                  # sv_phaser.py:484-492
             if k not in out_sv:
                 out_sv[k] = c
@@ -202,5 +267,9 @@ class BatchPhaser:
         kids = set(self.ped)
         svs = [d for d in dnms if d["vartype"].upper() in SV_TYPES and d["kid"] in kids]
         snvs = [d for d in dnms if d["vartype"].upper() in SNV_TYPES and d["kid"] in kids]
+        import time as _t
         res, layout = self.run(snvs, svs, **params)
-        return self.records(res, layout)
+        t0 = _t.perf_counter()
+        out = self.records(res, layout)
+        self.last_timing["records_ms"] = (_t.perf_counter() - t0) * 1e3
+        return out

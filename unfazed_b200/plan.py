@@ -292,15 +292,8 @@ def plan_find_fast(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Op
     end = np.fromiter((d["end"] for d in dnms), dtype=np.int64, count=n)
     # ---- per (kid, chrom) group facts -------------------------------------------------------
     gid_of: Dict[tuple, int] = {}
-    gids = np.empty(n, dtype=np.int64)
-    groups: List[tuple] = []
-    for i, d in enumerate(dnms):
-        key = (d["kid"], d["chrom"])
-        g = gid_of.get(key)
-        if g is None:
-            g = gid_of[key] = len(groups)
-            groups.append(key)
-        gids[i] = g
+    gids = np.fromiter((gid_of.setdefault((d["kid"], d["chrom"]), len(gid_of)) for d in dnms), dtype=np.int64, count=n)
+    groups: List[tuple] = list(gid_of)
     G = len(groups)
     g_trio = np.full(G, -1, dtype=np.int32)
     g_sblk = np.full(G, -1, dtype=np.int32)
@@ -396,12 +389,13 @@ def plan_find_fast(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Op
         alt_off = np.zeros(n, dtype=np.int32); alt_len = np.zeros(n, dtype=np.int32)
         fast_blob = np.zeros(2 * n, dtype=np.uint8)           # [ref, alt] of entry i at 2i, 2i+1
         slow: List[int] = []
-        by_contig: Dict[str, List[int]] = {}
-        for i in need:
-            by_contig.setdefault(g_contig[gids[i]], []).append(int(i))
+        # group the DNMs that need REF/ALT by contig (a handful of contigs: one vectorised pass each)
+        cid_of: Dict[str, int] = {}
+        g_cid = np.array([cid_of.setdefault(c, len(cid_of)) for c in g_contig], dtype=np.int64)
+        need_cid = g_cid[gids[need]]
+        by_contig = {c: need[need_cid == k] for c, k in cid_of.items() if np.any(need_cid == k)}
         rid_all = sites.record_ids()
         for contig, idxs in by_contig.items():
-            idxs = np.array(idxs, dtype=np.int64)
             pos, rid, rows, ext = sidx.contig_rows(contig)
             s0 = start[idxs]
             a = np.searchsorted(pos, s0 - 1, "left")
@@ -412,11 +406,15 @@ def plan_find_fast(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Op
             row1 = rows[np.minimum(a, max(len(rows) - 1, 0))] if len(rows) else np.zeros(len(idxs), dtype=np.int64)
             ok &= (sites.flag[row1] & SITE_FLAG_SIMPLE) != 0 if len(rows) else False
             if ext:
-                ep = np.array([e[0] for e in ext], dtype=np.int64)
-                ee = ep + np.array([e[1] for e in ext], dtype=np.int64)
-                # any extra record with p < start-1 < p+len  -> generic path
-                for p_, e_ in zip(ep, ee):
-                    ok &= ~((p_ < s0 - 1) & (e_ > s0 - 1))
+                # any extra record with p < start-1 < p+len -> generic path (ext is sorted by p: the furthest end of
+                # the records before start-1 is a running maximum)
+                cache = sidx.__dict__.setdefault("_ext_cache", {})
+                if contig not in cache:
+                    ep = np.array([e[0] for e in ext], dtype=np.int64)
+                    cache[contig] = (ep, np.maximum.accumulate(ep + np.array([e[1] for e in ext], dtype=np.int64)))
+                ep, reach = cache[contig]
+                k = np.searchsorted(ep, s0 - 1, "left")
+                ok &= ~((k > 0) & (reach[np.maximum(k - 1, 0)] > s0 - 1))
             # two rows that are the same record seen through two trio blocks also go the generic way
             fi = idxs[ok]
             fast_blob[2 * fi] = sites.ref[row1[ok]]

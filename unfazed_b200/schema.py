@@ -193,6 +193,16 @@ class ReadTable:
         m = int(self.hdr["mate"][r])
         return "q%d" % (min(r, m) if m >= 0 else r)
 
+    def names_of(self, idx: np.ndarray) -> List[str]:
+        """query_name of many reads at once (both mates of a pair share it)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        if self.names is not None:
+            nm = self.names
+            return [nm[i] for i in idx.tolist()]
+        m = self.hdr["mate"][idx].astype(np.int64)
+        ids = np.where(m >= 0, np.minimum(idx, m), idx)
+        return ["q%d" % i for i in ids.tolist()]
+
     def lowq_plane(self, min_bq: int, chunk: int = 1 << 26) -> np.ndarray:
         """One bit per query base, bit i&7 of byte i>>3: ``(qual & 0x7f) < min_bq``.  This is what the
         device gets instead of the quality bytes -- every base-quality test of the path is this one

@@ -45,6 +45,10 @@ class SynthConfig:
     chr_prefix: str = ""          # prefix of VCF/BAM contig names
     dnm_chr_prefix: Optional[str] = None   # prefix used in the DNM list (default: same)
     read_margin: int = 700        # reads are simulated this far beyond the site window
+    # cohort mode: the GLOBAL indices of the trios to generate.  Every trio then draws from its own
+    # generator seeded (seed, trio id), so any subset of a cohort -- one rank's shard -- is made of
+    # exactly the trios the whole cohort would contain.  None: trios 0..n_trios-1 off one generator.
+    trio_ids: Optional[Tuple[int, ...]] = None
     chunk_frags: int = 200_000
 
 
@@ -235,12 +239,14 @@ def make_dataset(cfg: SynthConfig) -> Dataset:
     n_cig_tot = 0
     n_q_tot = 0
 
-    for t in range(cfg.n_trios):
-        kid, dad, mom = "kid%d" % t, "dad%d" % t, "mom%d" % t
+    for t, gid in enumerate(cfg.trio_ids if cfg.trio_ids is not None else range(cfg.n_trios)):
+        if cfg.trio_ids is not None:
+            rng = np.random.default_rng([cfg.seed, int(gid)])
+        kid, dad, mom = "kid%d" % gid, "dad%d" % gid, "mom%d" % gid
         trios.append((kid, dad, mom))
         sex = "1" if rng.random() < cfg.male_frac else "2"
         pedigrees[kid] = {"kid": kid, "dad": dad, "mom": mom, "sex": sex}
-        d_contig, d_start, d_end, d_kind = _place_dnms(cfg, rng, t)
+        d_contig, d_start, d_end, d_kind = _place_dnms(cfg, rng, int(gid))
         d_hap = rng.integers(0, 2, size=len(d_start))     # 0: paternal haplotype, 1: maternal
 
         for c in np.unique(d_contig):

@@ -11,3 +11,17 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs the reference checkout at /root/reference")
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU-marked tests are skipped (not errored) where no CUDA device or no built library is present, so a
+    plain `pytest` works on a CPU box; `-m gpu` on the B200 box runs them all."""
+    import torch
+    lib = os.path.join(ROOT, "unfazed_b200", "libunfazed_sm100.so")
+    if torch.cuda.is_available() and os.path.exists(lib):
+        return
+    why = "no CUDA device visible" if not torch.cuda.is_available() else "libunfazed_sm100.so is not built"
+    skip = pytest.mark.skip(reason=why + ": GPU parity tests run on the B200 box (pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

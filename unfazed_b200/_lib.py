@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunfazed_sm100.so")
+# UNFZ_LIB selects another build of the same library (profiling variants, e.g. -DCH_DEBUG)
+LIB_PATH = os.environ.get("UNFZ_LIB") or os.path.join(_HERE, "libunfazed_sm100.so")
 
 c_void_p, c_int32, c_int64, c_double = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 

@@ -17,6 +17,7 @@ extern "C" int unfz_ctx_create(int device, UnfzCtx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->guard = nullptr;
     c->scan_smem_attr = 0;
+    c->chain_carveout_set = false;
     c->err[0] = 0;
     *out = c;
     return 0;

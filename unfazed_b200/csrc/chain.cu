@@ -11,6 +11,8 @@
 //   claim[pair] = min best[site] over the sites where the pair is an eligible target
 // The order of the next level's lists is (claiming key, position in the site's read list), which is
 // recovered with per-site ballot ranks and a rank of the sites by key -- no global sort.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -18,33 +20,32 @@ namespace {
 constexpr int CH_THREADS = 128;
 constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr unsigned long long KEY_NONE = ~0ull;
-constexpr int CH_SMEM_SITES = 256;         // per-site state lives in shared memory up to this many het sites
+constexpr int CH_SMEM_SITES = 128;         // per-site state lives in shared memory up to this many het sites
 
-struct Scratch {
-    // per window slot: one 32-byte record (a single DRAM sector) per read pair, see SlotField
-    char* slot;
-    // per het-site incidence
-    int32_t* inc_r; int32_t* inc_x; int32_t* inc_site; int32_t* inc_sidx; uint8_t* inc_al;
-    // seeds
-    int32_t* seed_e; uint8_t* seed_hap;
-    // seed incidences
-    int32_t* sinc_x; int32_t* sinc_site; int32_t* sinc_sidx; uint8_t* sinc_al;
-    // per het site (site_off has one extra entry per DNM)
-    int32_t* spos; uint8_t* sref; uint8_t* salt; int32_t* site_off; int32_t* cand_off;
-    unsigned long long* bestkey; int32_t* site_cnt; int32_t* site_base;
-    // per candidate site
-    int32_t* cpos;
+// what a window slot carries: the key that elects a pair's last writer and the pair's dense id
+struct __align__(16) SlotRec {
+    unsigned long long key;
+    int32_t dense;
+    int32_t pad;
 };
 
-// The per-pair state used to be six arrays; a touched pair then cost six sectors.  Packed as
-//   minkey u64 @0 | prim i32 @8 | ord u32 @12 | lvl i32 @16 | fpos i32 @20 | tmp i32 @24 | pad
-// it costs one.  SlotField keeps the array syntax (f[x], f + x) over the strided records.
-constexpr int SLOT_BYTES = 32;
-template <typename T, int OFF>
-struct SlotField {
-    char* base;
-    __device__ __forceinline__ T& operator[](int x) const { return *reinterpret_cast<T*>(base + (size_t)x * SLOT_BYTES + OFF); }
-    __device__ __forceinline__ T* operator+(int x) const { return reinterpret_cast<T*>(base + (size_t)x * SLOT_BYTES + OFF); }
+struct Scratch {
+    SlotRec* slot;                                                  // per window slot
+    // per het-site incidence (site-major); inc_x holds the window slot during set-up, then the dense pair
+    int32_t* inc_r; int32_t* inc_x; int32_t* inc_site; uint8_t* inc_al;
+    // seed entries
+    int32_t* seed_e; uint8_t* seed_hap; uint32_t* seed_reg;
+    // seed incidences
+    int32_t* sinc_px; int32_t* sinc_site; uint32_t* sinc_sidx; uint8_t* sinc_al;
+    // per dense pair (at most one per incidence + one per seed entry): slot, primary read, chaining state
+    int32_t* x_of; int32_t* prim;
+    uint32_t* p_ord; int32_t* p_fpos; int32_t* p_tmp; unsigned long long* p_minkey; uint8_t* p_label;
+    int32_t* adj; int32_t* adj_off; int32_t* front0; int32_t* front1;
+    // per het site (site_off has one extra entry per DNM)
+    int32_t* spos; uint8_t* sref; uint8_t* salt; int32_t* site_off; int32_t* cand_off;
+    unsigned long long* bestkey; int32_t* site_cnt; int32_t* site_base; int32_t* active;
+    // per candidate site
+    int32_t* cpos;
 };
 
 struct ChainArgs {
@@ -360,10 +361,158 @@ __device__ unsigned long long g_ch_dbg[16];
 #define CH_MARK(i)
 #endif
 
-// 16 CTAs per SM (32 registers, ~150 B of spills): the kernel is a chain of dependent gathers, so resident
-// warps matter more than registers (measured at 4000 DNMs: 8 CTAs 0.348 ms, 12 CTAs 0.310 ms, 16 CTAs 0.292 ms)
+// ------------------------------------------------------------------------------------------------
+// The breadth-first 2-colouring over DENSE pair ids, one instantiation per storage class:
+//   <uint16_t, uint8_t>  everything in shared memory (the common case: a 5 kb window at 30x has a few
+//                        hundred pairs and incidences) -- a level is a handful of shared-memory passes
+//   <int32_t, int32_t>   everything in global scratch (deep / wide windows)
+// A level touches only its FRONTIER (the pairs labelled by the previous level, through a pair-major
+// adjacency of the incidences where the pair can read an allele) and the ACTIVE sites (those some
+// frontier pair reaches), so a level costs what it does, not a rescan of every incidence.
+// ------------------------------------------------------------------------------------------------
+template <typename PT, typename ST>
+struct BfsView {
+    // per dense pair
+    uint32_t* ord; int32_t* fpos; int32_t* tmp; unsigned long long* minkey; uint8_t* label;
+    // per het-site incidence (site-major): pair, site, allele codes (bits0-1 finder, bits2-3 target)
+    PT* inc_px; ST* inc_site; uint8_t* inc_al;
+    // per seed incidence: pair, site, position in the pair's site list, allele codes
+    PT* sinc_px; ST* sinc_site; uint32_t* sinc_sidx; uint8_t* sinc_al;
+    // pair-major adjacency over finder-capable entries (entry e < n_inc: incidence e, else seed incidence e - n_inc)
+    PT* adj; PT* adj_off;
+    PT* front[2];
+    // per het site
+    const int32_t* spos; const int32_t* site_off; unsigned long long* bestkey; int32_t* site_cnt; int32_t* site_base;
+    ST* active;
+};
+
+template <typename PT, typename ST>
+__device__ void bfs_levels(const BfsView<PT, ST>& V, int nh, int n_inc, int n_front0) {
+    __shared__ int s_nact, s_nnext;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n_front = n_front0;
+    PT* fcur = V.front[0];
+    PT* fnext = V.front[1];
+    for (;;) {
+        for (int i = tid; i < nh; i += CH_THREADS) V.bestkey[i] = KEY_NONE;
+        if (tid == 0) { s_nact = 0; s_nnext = 0; }
+        __syncthreads();
+        // a. best finder per site, over the frontier only; the finder's haplotype and allele ride in the low key bits
+        for (int f = tid; f < n_front; f += CH_THREADS) {
+            const int p = (int)fcur[f];
+            const uint8_t fh = (V.label[p] & 2) ? 2 : 1;            // level 0: the "alt" visit comes first
+            const unsigned long long okey = (unsigned long long)V.ord[p] << 36;
+            const int32_t fp = V.fpos[p];
+            const int q1 = (int)V.adj_off[p + 1];
+            for (int q = (int)V.adj_off[p]; q < q1; ++q) {
+                const int e = (int)V.adj[q];
+                const bool sd = e >= n_inc;
+                const int kk = sd ? e - n_inc : e;
+                const int i = sd ? (int)V.sinc_site[kk] : (int)V.inc_site[kk];
+                if (V.spos[i] == fp) continue;
+                const uint8_t al = sd ? V.sinc_al[kk] : V.inc_al[kk];
+                const uint32_t sidx = sd ? V.sinc_sidx[kk] : (uint32_t)i;   // registered sites come in site order
+                atomicMin(V.bestkey + i, okey | ((unsigned long long)sidx << 4) | (unsigned long long)((fh << 2) | (al & 3)));
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nh; i += CH_THREADS)
+            if (V.bestkey[i] != KEY_NONE) V.active[atomicAdd(&s_nact, 1)] = (ST)i;
+        __syncthreads();
+        const int n_act = s_nact;
+        if (n_act == 0) break;
+        // b. earliest claiming key per unlabelled pair, over the active sites' incidences
+        for (int a = warp; a < n_act; a += CH_WARPS) {
+            const int i = (int)V.active[a];
+            const unsigned long long bk = V.bestkey[i];
+            const int k1 = V.site_off[i + 1];
+            for (int k = V.site_off[i] + lane; k < k1; k += 32) {
+                const int p = (int)V.inc_px[k];
+                if (V.label[p] == 0 && (V.inc_al[k] >> 2)) atomicMin(V.minkey + p, bk);
+            }
+        }
+        __syncthreads();
+        // c. claim, one warp per active site, in the order of the site's read list
+        for (int a = warp; a < n_act; a += CH_WARPS) {
+            const int i = (int)V.active[a];
+            const unsigned long long bk = V.bestkey[i];
+            const int k0 = V.site_off[i], k1 = V.site_off[i + 1];
+            int cnt = 0;
+            for (int kb = k0; kb < k1; kb += 32) {
+                const int k = kb + lane;
+                bool claim = false;
+                int p = 0;
+                uint8_t ta = 0;
+                if (k < k1) {
+                    p = (int)V.inc_px[k];
+                    ta = V.inc_al[k] >> 2;
+                    claim = V.label[p] == 0 && ta && V.minkey[p] == bk;
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, claim);
+                if (claim) {
+                    const uint8_t fh = (uint8_t)((bk >> 2) & 3), fa = (uint8_t)(bk & 3);
+                    const uint8_t nh_ = (ta == fa) ? fh : (uint8_t)(3 - fh);
+                    V.tmp[p] = (i << 8) | (nh_ << 4) | 1;
+                    V.ord[p] = (uint32_t)(cnt + __popc(b & ((1u << lane) - 1u)));   // rank inside the site
+                }
+                cnt += __popc(b);
+            }
+            if (lane == 0) V.site_cnt[i] = cnt;
+        }
+        __syncthreads();
+        // d. order of the active sites by key -> base offsets
+        int assigned = 0;
+        for (int a = tid; a < n_act; a += CH_THREADS) {
+            const int i = (int)V.active[a];
+            const int c = V.site_cnt[i];
+            int base = 0;
+            if (c > 0) {
+                const unsigned long long bk = V.bestkey[i];
+                for (int b = 0; b < n_act; ++b) {
+                    const int j = (int)V.active[b];
+                    if (V.site_cnt[j] > 0 && V.bestkey[j] < bk) base += V.site_cnt[j];
+                }
+            }
+            V.site_base[i] = base;
+            assigned += c;
+        }
+        assigned = block_sum(assigned);
+        if (assigned == 0) break;
+        // e. commit the new level; the newly labelled pairs are the next frontier
+        for (int a = warp; a < n_act; a += CH_WARPS) {
+            const int i = (int)V.active[a];
+            const unsigned long long bk = V.bestkey[i];
+            const int k1 = V.site_off[i + 1];
+            for (int k = V.site_off[i] + lane; k < k1; k += 32) {
+                const int p = (int)V.inc_px[k];
+                if (V.label[p] != 0) continue;
+                const int t = V.tmp[p];
+                if (!(t & 1)) { V.minkey[p] = KEY_NONE; continue; }      // still unlabelled: re-arm for the next level
+                if ((t >> 8) != i || V.minkey[p] != bk || !(V.inc_al[k] >> 2)) continue;
+                const uint8_t nhap = (t >> 4) & 3;
+                V.ord[p] = ((nhap == 1 ? 0u : 1u) << 24) | ((uint32_t)V.site_base[i] + V.ord[p]);   // deeper levels: "ref" list first
+                V.fpos[p] = V.spos[i];
+                V.tmp[p] = 0;
+                V.label[p] = nhap;
+                fnext[atomicAdd(&s_nnext, 1)] = (PT)p;
+            }
+        }
+        __syncthreads();
+        n_front = s_nnext;
+        { PT* t_ = fcur; fcur = fnext; fnext = t_; }
+        __syncthreads();                                   // s_nnext is cleared at the top of the next level
+    }
+    __syncthreads();
+}
+
+// per-pair state, incidence views and adjacency of the shared-memory mode
+constexpr int SM_P = 512;                 // dense pairs
+constexpr int SM_I = 768;                 // het-site incidences
+constexpr int SM_SI = 256;                // seed incidences
+
+// 8 CTAs per SM: ~27 KB of shared memory each
 #ifndef CH_MINB
-#define CH_MINB 16
+#define CH_MINB 8
 #endif
 __global__ void __launch_bounds__(CH_THREADS, CH_MINB)
 chain_kernel(ChainArgs A) {
@@ -398,25 +547,18 @@ chain_kernel(ChainArgs A) {
     const int64_t o_sinc = off[3 * n1 + d], o_het = off[4 * n1 + d], o_cand = off[5 * n1 + d];
     const int64_t cap_inc = off[1 * n1 + d + 1] - o_inc, cap_seed = off[2 * n1 + d + 1] - o_seed;
     const int64_t cap_sinc = off[3 * n1 + d + 1] - o_sinc;
+    const int64_t o_pair = o_inc + o_seed, o_adj = o_inc + o_sinc;      // pairs <= incidences + seed entries
 
-    // per-DNM views
-    char* slot_base = S0.slot + o_slot * SLOT_BYTES;
-    const SlotField<unsigned long long, 0> minkey{slot_base};
-    const SlotField<int32_t, 8> prim{slot_base};
-    const SlotField<uint32_t, 12> ord{slot_base};
-    const SlotField<int32_t, 16> lvl{slot_base};
-    const SlotField<int32_t, 20> fpos{slot_base};
-    const SlotField<int32_t, 24> tmp{slot_base};
-    uint8_t* label = A.slot_label + o_slot; uint8_t* evid = A.slot_evid + o_slot;
+    // per-DNM views of the global scratch
+    SlotRec* rec = S0.slot + o_slot;
+    uint8_t* label_out = A.slot_label + o_slot; uint8_t* evid_out = A.slot_evid + o_slot;
     int32_t* inc_r = S0.inc_r + o_inc; int32_t* inc_x = S0.inc_x + o_inc; int32_t* inc_site = S0.inc_site + o_inc;
-    int32_t* inc_sidx = S0.inc_sidx + o_inc; uint8_t* inc_al = S0.inc_al + o_inc;
-    int32_t* seed_e = S0.seed_e + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed;
-    int32_t* sinc_x = S0.sinc_x + o_sinc; int32_t* sinc_site = S0.sinc_site + o_sinc;
-    int32_t* sinc_sidx = S0.sinc_sidx + o_sinc; uint8_t* sinc_al = S0.sinc_al + o_sinc;
+    int32_t* seed_e = S0.seed_e + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed; uint32_t* seed_reg = S0.seed_reg + o_seed;
+    int32_t* x_of = S0.x_of + o_pair; int32_t* prim = S0.prim + o_pair;
     __shared__ int32_t sh_spos[CH_SMEM_SITES], sh_site_off[CH_SMEM_SITES + 1], sh_cand_off[CH_SMEM_SITES + 1];
     __shared__ int32_t sh_site_cnt[CH_SMEM_SITES], sh_site_base[CH_SMEM_SITES];
     __shared__ unsigned long long sh_bestkey[CH_SMEM_SITES];
-    __shared__ uint8_t sh_sref[CH_SMEM_SITES], sh_salt[CH_SMEM_SITES];
+    __shared__ uint8_t sh_sref[CH_SMEM_SITES], sh_salt[CH_SMEM_SITES], sh_active[CH_SMEM_SITES];
     const bool small_sites = nh <= CH_SMEM_SITES;
     int32_t* spos = small_sites ? sh_spos : S0.spos + o_het;
     uint8_t* sref = small_sites ? sh_sref : S0.sref + o_het;
@@ -434,7 +576,6 @@ chain_kernel(ChainArgs A) {
     // the read window is the union of two index ranges (second one only for far-apart SV breakpoints)
     const int64_t nd_ = A.n_dnms;
     const int64_t a_lo = A.win[d], a_hi = A.win[nd_ + d], b_lo = A.win[2 * nd_ + d], b_hi = A.win[3 * nd_ + d];
-    const int W = (int)((a_hi - a_lo) + (b_hi - b_lo));
     auto slot_of = [&](int64_t r) -> int {
         if (r >= a_lo && r < a_hi) return (int)(r - a_lo);
         if (r >= b_lo && r < b_hi) return (int)((a_hi - a_lo) + (r - b_lo));
@@ -450,13 +591,9 @@ chain_kernel(ChainArgs A) {
     };
     const double cul = R.blk_cul[dn.rblk];
 
-    // per-slot state is initialised lazily, only for the pairs that get touched (seeds + registered
-    // reads); slot_label / slot_evid are zero-filled by the caller
-    auto init_slot = [&](int x) {                                 // two 16-byte stores
-        int4* rec = reinterpret_cast<int4*>(slot_base + (size_t)x * SLOT_BYTES);
-        rec[0] = make_int4(0, 0, -1, -1);                          // minkey = 0, prim = -1, ord = 0xffffffff
-        rec[1] = make_int4(-1, -1, 0, 0);                          // lvl = -1, fpos = -1, tmp = 0
-    };
+    // a window slot only carries what maps a pair to its DENSE id (16 bytes, initialised lazily for the pairs
+    // that get touched: seeds + registered reads); all chaining state is indexed by the dense id
+    auto init_slot = [&](int x) { *reinterpret_cast<int4*>(rec + x) = make_int4(0, 0, -1, 0); };   // key 0, dense -1
     for (int i = tid; i < nh; i += CH_THREADS) {
         const int64_t row = H[i];
         spos[i] = __ldg(A.sites.pos + row);
@@ -550,6 +687,7 @@ chain_kernel(ChainArgs A) {
     for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) init_slot(x); }
     __syncthreads();
     int n_inc = 0, n_sinc = 0;
+    int P = 0;                                     // dense pairs
     const int nh_reg = A.no_extended ? 0 : nh;     // --no-extended: seeds are the haplotype lists
     if (!A.no_extended) {
         // ------------------------------------------------------------ phase 2: het-site incidences
@@ -640,7 +778,6 @@ chain_kernel(ChainArgs A) {
                         inc_r[k] = (int32_t)r;
                         inc_x[k] = canon(r);
                         inc_site[k] = i;
-                        inc_sidx[k] = i;      // order key inside read_sites[x]: registered sites come in site order
                     }
                 }
             }
@@ -657,10 +794,22 @@ chain_kernel(ChainArgs A) {
         __syncthreads();
         // fetched_reads[name] = [read, mate]: the last writer (highest site) wins (Q18)
         for (int k = tid; k < n_inc; k += CH_THREADS)
-            atomicMax(minkey + inc_x[k], ((unsigned long long)(uint32_t)(inc_site[k] + 1) << 32) | (uint32_t)inc_r[k]);
+            atomicMax(&rec[inc_x[k]].key, ((unsigned long long)(uint32_t)(inc_site[k] + 1) << 32) | (uint32_t)inc_r[k]);
         __syncthreads();
-        for (int k = tid; k < n_inc; k += CH_THREADS) prim[inc_x[k]] = (int32_t)(uint32_t)minkey[inc_x[k]];
-        __syncthreads();
+        // the winning incidence of a pair gives it its dense id (ids in incidence order) and its primary read
+        for (int base = 0; base < n_inc; base += CH_THREADS) {
+            const int k = base + tid;
+            bool rep = false;
+            int x = 0;
+            if (k < n_inc) {
+                x = inc_x[k];
+                rep = rec[x].key == (((unsigned long long)(uint32_t)(inc_site[k] + 1) << 32) | (uint32_t)inc_r[k]);
+            }
+            int tot;
+            const int id = P + block_prefix(rep, &tot);
+            if (rep) { rec[x].dense = id; x_of[id] = x; prim[id] = inc_r[k]; }
+            P += tot;
+        }
         if (tid == 0) {                                             // empty sites inherit the next offset
             int nxt = n_inc;
             site_off[nh] = n_inc;
@@ -668,26 +817,26 @@ chain_kernel(ChainArgs A) {
         }
         __syncthreads();
     }
-    {
     CH_MARK(4);
-        // ------------------------------------------------------------ phase 3: seed registration
-        // Entries register in the order "ref" list then "alt" list (:226-249); the level-0 visit order
-        // is "alt" list first (Q19).  Everything is resolved with order keys instead of a serial loop:
-        //   reg(k)   = position of entry k in the registration order
-        //   prim[x]  = entry with the largest reg  (last writer wins)
-        //   ord[x]   = smallest visit position of the pair
-        int n_ref_entries = 0;
-        for (int base = 0; base < n_seed; base += CH_THREADS) {
-            const int k = base + tid;
-            int tot;
-            block_prefix(k < n_seed && seed_hap[k] == 1, &tot);
-            n_ref_entries += tot;
-        }
-        for (int k = tid; k < n_inc; k += CH_THREADS) minkey[inc_x[k]] = 0ull;
-        for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) minkey[x] = 0ull; }
-        __syncthreads();
+    // ------------------------------------------------------------ phase 3: seed registration
+    // Entries register in the order "ref" list then "alt" list (:226-249); the level-0 visit order
+    // is "alt" list first (Q19).  Everything is resolved with order keys instead of a serial loop:
+    //   reg(k)   = position of entry k in the registration order
+    //   prim[p]  = entry with the largest reg  (last writer wins)
+    //   ord[p]   = smallest visit position of the pair
+    int n_ref_entries = 0;
+    for (int base = 0; base < n_seed; base += CH_THREADS) {
+        const int k = base + tid;
+        int tot;
+        block_prefix(k < n_seed && seed_hap[k] == 1, &tot);
+        n_ref_entries += tot;
+    }
+    for (int k = tid; k < n_inc; k += CH_THREADS) rec[inc_x[k]].key = 0ull;
+    for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) rec[x].key = 0ull; }
+    __syncthreads();
+    {
+        // pass A: registration keys; the entry with the largest one is the pair's last writer
         int ref_seen = 0, alt_seen = 0;
-        int ns_total = 0;
         for (int base = 0; base < n_seed; base += CH_THREADS) {
             const int k = base + tid;
             const bool live = k < n_seed;
@@ -695,31 +844,98 @@ chain_kernel(ChainArgs A) {
             int tot_ref, tot_alt;
             const int pr = block_prefix(hap == 1, &tot_ref);
             const int pa = block_prefix(hap == 2, &tot_alt);
-            int n_match = 0, piv = -1, x = -1;
-            int32_t st = 0, en = 0;
-            int64_t e = 0;
-            unsigned reg = 0;
             if (live) {
-                e = seed_e[k];
+                const int32_t e = seed_e[k];
+                const int x = canon(e);
+                const unsigned reg = hap == 1 ? (unsigned)(ref_seen + pr) : (unsigned)(n_ref_entries + alt_seen + pa);
+                // visit order at level 0: alt entries first, then ref entries
+                const unsigned visit = hap == 2 ? (unsigned)(alt_seen + pa) : (unsigned)(ref_seen + pr);
+                seed_reg[k] = reg;
+                seed_e[k] = x >= 0 ? e : -1 - e;                       // entries outside the window are inert
+                if (x >= 0) atomicMax(&rec[x].key, ((unsigned long long)(reg + 1u) << 32) | (uint32_t)e);
+                (void)visit;
+            }
+            ref_seen += tot_ref;
+            alt_seen += tot_alt;
+        }
+        __syncthreads();
+        // pass B: dense ids of the pairs only seeds touch; the last writer's read becomes the primary read
+        for (int base = 0; base < n_seed; base += CH_THREADS) {
+            const int k = base + tid;
+            bool rep = false, fresh = false;
+            int x = -1;
+            int32_t e = -1;
+            if (k < n_seed && (e = seed_e[k]) >= 0) {
                 x = canon(e);
-                reg = hap == 1 ? (unsigned)(ref_seen + pr) : (unsigned)(n_ref_entries + alt_seen + pa);
-                if (x >= 0) {
-                    // visit order at level 0: alt entries first, then ref entries
-                    const unsigned visit = hap == 2 ? (unsigned)(alt_seen + pa) : (unsigned)(ref_seen + pr);
-                    atomicMin(ord + x, (hap == 2 ? 0u : (1u << 24)) | (visit & 0xffffffu));
-                    atomicMax(minkey + x, ((unsigned long long)(reg + 1u) << 32) | (uint32_t)e);
-                    unsigned* lw = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(label + x) & ~(uintptr_t)3);
-                    atomicOr(lw, (unsigned)hap << (8 * (reinterpret_cast<uintptr_t>(label + x) & 3)));
-                    lvl[x] = 0;
-                    if (nh_reg > 0) {
-                        st = rd_start(R, e);
-                        en = A.rsum[e].end;
-                        piv = bisect_pivot(spos, nh_reg, st, en);
-                        if (piv >= 0) {
-                            n_match = 1;
-                            for (int j = piv + 1; j < nh_reg && st <= spos[j] && spos[j] <= en; ++j) ++n_match;
-                            for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) ++n_match;
-                        }
+                rep = rec[x].key == (((unsigned long long)(seed_reg[k] + 1u) << 32) | (uint32_t)e);
+                fresh = rep && rec[x].dense < 0;
+            }
+            int tot;
+            const int id = P + block_prefix(fresh, &tot);
+            if (fresh) { rec[x].dense = id; x_of[id] = x; }
+            if (rep) prim[fresh ? id : rec[x].dense] = e;
+            P += tot;
+        }
+        __syncthreads();
+    }
+    if ((int64_t)P > cap_inc + cap_seed) { P = (int)(cap_inc + cap_seed); T.status |= 8; }     // cannot happen: one id per entry at most
+
+    // ---- storage class of the chaining state ---------------------------------------------------------------------
+    __shared__ __align__(8) unsigned long long sm_minkey[SM_P];
+    __shared__ uint32_t sm_ord[SM_P];
+    __shared__ int32_t sm_fpos[SM_P], sm_tmp[SM_P];
+    __shared__ uint32_t sm_sinc_sidx[SM_SI];
+    __shared__ uint16_t sm_inc_px[SM_I], sm_sinc_px[SM_SI], sm_adj[SM_I + SM_SI], sm_adj_off[SM_P + 2], sm_front[2][SM_P];
+    __shared__ uint8_t sm_label[SM_P], sm_inc_site[SM_I], sm_inc_al[SM_I], sm_sinc_site[SM_SI], sm_sinc_al[SM_SI];
+    const bool in_smem = small_sites && P <= SM_P && n_inc <= SM_I && cap_sinc <= SM_SI;
+    // the rest of the set-up is the same code over either view
+    int n_front0 = 0;
+    auto setup = [&](auto& V) {
+        using PT = typename std::remove_reference<decltype(V.inc_px[0])>::type;
+        using ST = typename std::remove_reference<decltype(V.inc_site[0])>::type;
+        __shared__ int s_front;
+        for (int p = tid; p < P; p += CH_THREADS) {
+            V.ord[p] = 0xffffffffu; V.fpos[p] = -1; V.tmp[p] = 0; V.minkey[p] = KEY_NONE; V.label[p] = 0;
+        }
+        if (tid == 0) s_front = 0;
+        // incidences: window slot -> dense pair (in global mode the column is rewritten in place)
+        for (int k = tid; k < n_inc; k += CH_THREADS) {
+            const int px = rec[inc_x[k]].dense;
+            const int st = inc_site[k];
+            V.inc_px[k] = (PT)px;
+            V.inc_site[k] = (ST)st;
+        }
+        __syncthreads();
+        // pass C over the seed entries: labels, visit order, level-0 frontier, seed incidences
+        int ref_seen = 0, alt_seen = 0, ns_total = 0;
+        for (int base = 0; base < n_seed; base += CH_THREADS) {
+            const int k = base + tid;
+            const bool live = k < n_seed;
+            const int hap = live ? seed_hap[k] : 0;
+            int tot_ref, tot_alt;
+            const int pr = block_prefix(hap == 1, &tot_ref);
+            const int pa = block_prefix(hap == 2, &tot_alt);
+            int n_match = 0, piv = -1, px = -1;
+            int32_t st = 0, en = 0;
+            unsigned reg = 0;
+            if (live && seed_e[k] >= 0) {
+                const int32_t e = seed_e[k];
+                const int x = canon(e);
+                px = rec[x].dense;
+                reg = seed_reg[k];
+                const unsigned visit = hap == 2 ? (unsigned)(alt_seen + pa) : (unsigned)(ref_seen + pr);
+                atomicMin(V.ord + px, (hap == 2 ? 0u : (1u << 24)) | (visit & 0xffffffu));
+                atomicOr(V.tmp + px, hap);                          // haplotype bits gather in tmp (word atomics), see below
+                if (rec[x].key == (((unsigned long long)(reg + 1u) << 32) | (uint32_t)e))     // once per pair
+                    V.front[0][atomicAdd(&s_front, 1)] = (PT)px;
+                if (nh_reg > 0) {
+                    st = rd_start(R, e);
+                    en = A.rsum[e].end;
+                    piv = bisect_pivot(spos, nh_reg, st, en);
+                    if (piv >= 0) {
+                        n_match = 1;
+                        for (int j = piv + 1; j < nh_reg && st <= spos[j] && spos[j] <= en; ++j) ++n_match;
+                        for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) ++n_match;
                     }
                 }
             }
@@ -728,13 +944,13 @@ chain_kernel(ChainArgs A) {
             // pivot / right / left order of binary_search, Q16)
             int tm;
             const int off_m = block_prefix_sum(n_match, &tm);
-            if (live && n_match > 0) {
+            if (n_match > 0) {
                 int w = 0;
                 const unsigned keybase = (unsigned)nh + reg * (unsigned)(nh + 1);
                 const int dst0 = ns_total + off_m;
                 auto push = [&](int i) {
                     const int dst = dst0 + w;
-                    if (dst < cap_sinc) { sinc_x[dst] = x; sinc_site[dst] = i; sinc_sidx[dst] = (int32_t)(keybase + (unsigned)w); }
+                    if (dst < cap_sinc) { V.sinc_px[dst] = (PT)px; V.sinc_site[dst] = (ST)i; V.sinc_sidx[dst] = keybase + (unsigned)w; }
                     ++w;
                 };
                 push(piv);
@@ -745,131 +961,84 @@ chain_kernel(ChainArgs A) {
             alt_seen += tot_alt;
             ns_total += tm;
         }
-        __syncthreads();
-        for (int k = tid; k < n_seed; k += CH_THREADS) {
-            const int x = canon(seed_e[k]);
-            if (x >= 0 && minkey[x] != 0ull) prim[x] = (int32_t)(uint32_t)minkey[x];
-        }
         n_sinc = ns_total;
         if (n_sinc > cap_sinc) { n_sinc = (int)cap_sinc; T.status |= 4; }
         __syncthreads();
-    }
-    if (!A.no_extended) {
+        n_front0 = s_front;
+        for (int p = tid; p < P; p += CH_THREADS) { V.label[p] = (uint8_t)V.tmp[p]; V.tmp[p] = 0; }
+        __syncthreads();
+        if (A.no_extended) return;
     CH_MARK(5);
-        // ------------------------------------------------------------ phase 3.5: allele codes
+        // -------------------------------------------------------- phase 3.5: allele codes + pair-major adjacency
+        // tmp[p] counts the entries where pair p can read an allele (finder role), then serves as the fill cursor
         for (int k = tid; k < n_inc; k += CH_THREADS) {
-            const int i = inc_site[k];
-            inc_al[k] = allele_info(A, S0, (int64_t)prim[inc_x[k]], (int64_t)H[i], (char)sref[i], (char)salt[i]);
+            const int i = (int)V.inc_site[k], px = (int)V.inc_px[k];
+            const uint8_t al = allele_info(A, S0, (int64_t)prim[px], (int64_t)H[i], (char)sref[i], (char)salt[i]);
+            V.inc_al[k] = al;
+            if (al & 3) atomicAdd(V.tmp + px, 1);
         }
         for (int k = tid; k < n_sinc; k += CH_THREADS) {
-            const int i = sinc_site[k];
-            sinc_al[k] = allele_info(A, S0, (int64_t)prim[sinc_x[k]], (int64_t)H[i], (char)sref[i], (char)salt[i]);
+            const int i = (int)V.sinc_site[k], px = (int)V.sinc_px[k];
+            const uint8_t al = allele_info(A, S0, (int64_t)prim[px], (int64_t)H[i], (char)sref[i], (char)salt[i]);
+            V.sinc_al[k] = al;
+            if (al & 3) atomicAdd(V.tmp + px, 1);
         }
         __syncthreads();
-
+        int run = 0;
+        for (int base = 0; base < P; base += CH_THREADS) {
+            const int p = base + tid;
+            const int c = p < P ? V.tmp[p] : 0;
+            int tot;
+            const int o = run + block_prefix_sum(c, &tot);
+            if (p < P) { V.adj_off[p] = (PT)o; V.tmp[p] = 0; }
+            run += tot;
+        }
+        if (tid == 0) V.adj_off[P] = (PT)run;
+        __syncthreads();
+        for (int k = tid; k < n_inc; k += CH_THREADS)
+            if (V.inc_al[k] & 3) { const int px = (int)V.inc_px[k]; V.adj[(int)V.adj_off[px] + atomicAdd(V.tmp + px, 1)] = (PT)k; }
+        for (int k = tid; k < n_sinc; k += CH_THREADS)
+            if (V.sinc_al[k] & 3) { const int px = (int)V.sinc_px[k]; V.adj[(int)V.adj_off[px] + atomicAdd(V.tmp + px, 1)] = (PT)(n_inc + k); }
+        __syncthreads();
+        for (int p = tid; p < P; p += CH_THREADS) V.tmp[p] = 0;
+        __syncthreads();
     CH_MARK(6);
-        // ------------------------------------------------------------ phase 4: level-synchronous BFS
-        for (int k = tid; k < n_inc; k += CH_THREADS) minkey[inc_x[k]] = KEY_NONE;
-        __syncthreads();
-        for (int level = 0;; ++level) {
-            for (int i = tid; i < nh; i += CH_THREADS) { bestkey[i] = KEY_NONE; site_cnt[i] = 0; }
-            __syncthreads();
-            // a. best finder per site; the finder's haplotype and allele ride in the low key bits
-            for (int k = tid; k < n_inc + n_sinc; k += CH_THREADS) {
-                const bool sd = k >= n_inc;
-                const int kk = sd ? k - n_inc : k;
-                const int x = sd ? sinc_x[kk] : inc_x[kk];
-                if (lvl[x] != level) continue;
-                const uint8_t al = sd ? sinc_al[kk] : inc_al[kk];
-                if (!(al & 3)) continue;
-                const int i = sd ? sinc_site[kk] : inc_site[kk];
-                if (spos[i] == fpos[x]) continue;
-                const uint8_t fh = (label[x] & 2) ? 2 : 1;          // level 0: the "alt" visit comes first
-                const unsigned long long key = ((unsigned long long)ord[x] << 36) |
-                                               ((unsigned long long)(uint32_t)(sd ? sinc_sidx[kk] : inc_sidx[kk]) << 4) |
-                                               (unsigned long long)((fh << 2) | (al & 3));
-                atomicMin(bestkey + i, key);
-            }
-            __syncthreads();
-            // b. earliest claiming key per unlabelled pair
-            for (int k = tid; k < n_inc; k += CH_THREADS) {
-                const unsigned long long bk = bestkey[inc_site[k]];
-                if (bk == KEY_NONE) continue;                        // no finder at this site: no gathers
-                const int x = inc_x[k];
-                if (label[x] != 0 || !(inc_al[k] >> 2)) continue;
-                atomicMin(minkey + x, bk);
-            }
-            __syncthreads();
-            // c. claim, one warp per site, in the order of the site's read list
-            for (int i = warp; i < nh; i += CH_WARPS) {
-                const unsigned long long bk = bestkey[i];
-                if (bk == KEY_NONE) continue;
-                const int k0 = site_off[i], k1 = site_off[i + 1];
-                int cnt = 0;
-                for (int kb = k0; kb < k1; kb += 32) {
-                    const int k = kb + lane;
-                    bool claim = false;
-                    int x = 0;
-                    if (k < k1) {
-                        x = inc_x[k];
-                        claim = label[x] == 0 && (inc_al[k] >> 2) && minkey[x] == bk;
-                    }
-                    const unsigned b = __ballot_sync(0xffffffffu, claim);
-                    if (claim) {
-                        const uint8_t fh = (uint8_t)((bk >> 2) & 3), fa = (uint8_t)(bk & 3), ta = inc_al[k] >> 2;
-                        const uint8_t nh_ = (ta == fa) ? fh : (uint8_t)(3 - fh);
-                        tmp[x] = (i << 8) | (nh_ << 4) | 1;
-                        ord[x] = (uint32_t)(cnt + __popc(b & ((1u << lane) - 1u)));   // rank inside the site
-                    }
-                    cnt += __popc(b);
-                }
-                if (lane == 0) site_cnt[i] = cnt;
-            }
-            __syncthreads();
-            // d. order of the sites by key -> base offsets
-            int assigned = 0;
-            for (int i = tid; i < nh; i += CH_THREADS) {
-                int base = 0;
-                const unsigned long long bk = bestkey[i];
-                if (site_cnt[i] > 0)
-                    for (int j = 0; j < nh; ++j)
-                        if (site_cnt[j] > 0 && bestkey[j] < bk) base += site_cnt[j];
-                site_base[i] = base;
-                assigned += site_cnt[i];
-            }
-            assigned = block_sum(assigned);
-            if (assigned == 0) break;
-            // e. commit the new level
-            for (int k = tid; k < n_inc; k += CH_THREADS) {
-                // an incidence at a site without a finder neither claimed nor touched minkey in (b): if its pair
-                // was touched through another site, that incidence re-arms / commits it
-                if (bestkey[inc_site[k]] == KEY_NONE) continue;
-                const int x = inc_x[k];
-                if (label[x] != 0) continue;
-                const int t = tmp[x];
-                if (!(t & 1)) { minkey[x] = KEY_NONE; continue; }        // still unlabelled: re-arm for the next level
-                if ((t >> 8) != inc_site[k] || minkey[x] != bestkey[inc_site[k]] || !(inc_al[k] >> 2)) continue;
-                const int i = t >> 8;
-                const uint8_t nhap = (t >> 4) & 3;
-                const uint32_t seq = (uint32_t)site_base[i] + ord[x];
-                ord[x] = ((nhap == 1 ? 0u : 1u) << 24) | seq;       // deeper levels: "ref" list first
-                lvl[x] = level + 1;
-                fpos[x] = spos[i];
-                tmp[x] = 0;
-                label[x] = nhap;
-            }
-            __syncthreads();
-        }
-        __syncthreads();
+        // -------------------------------------------------------- phase 4: level-synchronous BFS
+        bfs_levels(V, nh, n_inc, n_front0);
+    };
+    if (in_smem) {
+        BfsView<uint16_t, uint8_t> VS;
+        VS.ord = sm_ord; VS.fpos = sm_fpos; VS.tmp = sm_tmp; VS.minkey = sm_minkey; VS.label = sm_label;
+        VS.inc_px = sm_inc_px; VS.inc_site = sm_inc_site; VS.inc_al = sm_inc_al;
+        VS.sinc_px = sm_sinc_px; VS.sinc_site = sm_sinc_site; VS.sinc_sidx = sm_sinc_sidx; VS.sinc_al = sm_sinc_al;
+        VS.adj = sm_adj; VS.adj_off = sm_adj_off; VS.front[0] = sm_front[0]; VS.front[1] = sm_front[1];
+        VS.spos = spos; VS.site_off = site_off; VS.bestkey = bestkey; VS.site_cnt = site_cnt; VS.site_base = site_base;
+        VS.active = sh_active;
+        setup(VS);
+    } else {
+        BfsView<int32_t, int32_t> VG;
+        VG.ord = S0.p_ord + o_pair; VG.fpos = S0.p_fpos + o_pair; VG.tmp = S0.p_tmp + o_pair; VG.minkey = S0.p_minkey + o_pair;
+        VG.label = S0.p_label + o_pair;
+        VG.inc_px = inc_x; VG.inc_site = inc_site; VG.inc_al = S0.inc_al + o_inc;          // the slot column becomes the pair column
+        VG.sinc_px = S0.sinc_px + o_sinc; VG.sinc_site = S0.sinc_site + o_sinc;
+        VG.sinc_sidx = S0.sinc_sidx + o_sinc; VG.sinc_al = S0.sinc_al + o_sinc;
+        VG.adj = S0.adj + o_adj; VG.adj_off = S0.adj_off + o_pair + 2 * (int64_t)d;
+        VG.front[0] = S0.front0 + o_pair; VG.front[1] = S0.front1 + o_pair;
+        VG.spos = spos; VG.site_off = site_off; VG.bestkey = bestkey; VG.site_cnt = site_cnt; VG.site_base = site_base;
+        VG.active = S0.active + o_het;
+
+        setup(VG);
     }
+    __syncthreads();
 
     CH_MARK(7);
     // ---------------------------------------------------------------- phase 5: matching + evidence
-    int has_rec = 0;
-    for (int x = tid; x < W; x += CH_THREADS) {
-        const uint8_t lab = label[x];
-        if (!lab || prim[x] < 0) continue;
-        const int64_t e0 = prim[x];
+    int has_rec = 0, dr = 0, mr = 0;
+    const uint8_t* final_label = in_smem ? sm_label : S0.p_label + o_pair;
+    for (int p = tid; p < P; p += CH_THREADS) {
+        const uint8_t lab = final_label[p];
+        if (!lab) continue;
+        const int64_t e0 = prim[p];
         const int64_t ents[2] = {e0, (int64_t)rd_mate(R, e0)};
         uint8_t ev = 0;
         for (int t = 0; t < 2; ++t) {
@@ -908,13 +1077,17 @@ chain_kernel(ChainArgs A) {
                 atomicOr(wp, (unsigned)bits << (8 * (reinterpret_cast<uintptr_t>(cev + j) & 3)));
             }
         }
-        evid[x] = ev;
+        const int x = x_of[p];
+        label_out[x] = lab;                                      // zero-filled by the caller: only labelled pairs are written
+        evid_out[x] = ev;
+        dr += ev & 1;
+        mr += (ev >> 1) & 1;
     }
     __syncthreads();
 
     CH_MARK(8);
     // ---------------------------------------------------------------- phase 6: tally
-    int ds = 0, ms = 0, dr = 0, mr = 0, esd = 0, esm = 0;
+    int ds = 0, ms = 0, esd = 0, esm = 0;
     for (int j = tid; j < nc; j += CH_THREADS) {
         const uint8_t b = cev[j];
         esd += b & 1;
@@ -927,13 +1100,7 @@ chain_kernel(ChainArgs A) {
             if (first) { if (bit == 1) ++ds; else ++ms; }
         }
     }
-    for (int x = tid; x < W; x += CH_THREADS) {
-        dr += evid[x] & 1;
-        mr += (evid[x] >> 1) & 1;
-    }
-    if (A.ev_need) {
-        esd = block_sum(esd); esm = block_sum(esm);
-    }
+    if (A.ev_need) { esd = block_sum(esd); esm = block_sum(esm); }
     ds = block_sum(ds); ms = block_sum(ms); dr = block_sum(dr); mr = block_sum(mr);
     has_rec = block_sum(has_rec);
     if (tid == 0) {
@@ -1228,18 +1395,26 @@ Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_
                   int64_t n_dnms, int64_t* total) {
     Scratch S;
     char* p = base;
-    S.slot = carve<char>(p, slots * SLOT_BYTES);                  // first: the base is 256-byte aligned
+    const int64_t pairs = incs + seeds, adjs = incs + sincs;
+    S.slot = (SlotRec*)carve<SlotRec>(p, slots);                  // first: the base is 256-byte aligned
+    S.p_minkey = (unsigned long long*)carve<unsigned long long>(p, pairs);
     S.inc_r = (int32_t*)carve<int32_t>(p, incs); S.inc_x = (int32_t*)carve<int32_t>(p, incs);
-    S.inc_site = (int32_t*)carve<int32_t>(p, incs); S.inc_sidx = (int32_t*)carve<int32_t>(p, incs);
-    S.inc_al = (uint8_t*)carve<uint8_t>(p, incs);
+    S.inc_site = (int32_t*)carve<int32_t>(p, incs); S.inc_al = (uint8_t*)carve<uint8_t>(p, incs);
     S.seed_e = (int32_t*)carve<int32_t>(p, seeds); S.seed_hap = (uint8_t*)carve<uint8_t>(p, seeds);
-    S.sinc_x = (int32_t*)carve<int32_t>(p, sincs); S.sinc_site = (int32_t*)carve<int32_t>(p, sincs);
-    S.sinc_sidx = (int32_t*)carve<int32_t>(p, sincs); S.sinc_al = (uint8_t*)carve<uint8_t>(p, sincs);
+    S.seed_reg = (uint32_t*)carve<uint32_t>(p, seeds);
+    S.sinc_px = (int32_t*)carve<int32_t>(p, sincs); S.sinc_site = (int32_t*)carve<int32_t>(p, sincs);
+    S.sinc_sidx = (uint32_t*)carve<uint32_t>(p, sincs); S.sinc_al = (uint8_t*)carve<uint8_t>(p, sincs);
+    S.x_of = (int32_t*)carve<int32_t>(p, pairs); S.prim = (int32_t*)carve<int32_t>(p, pairs);
+    S.p_ord = (uint32_t*)carve<uint32_t>(p, pairs); S.p_fpos = (int32_t*)carve<int32_t>(p, pairs);
+    S.p_tmp = (int32_t*)carve<int32_t>(p, pairs); S.p_label = (uint8_t*)carve<uint8_t>(p, pairs);
+    S.adj = (int32_t*)carve<int32_t>(p, adjs); S.adj_off = (int32_t*)carve<int32_t>(p, pairs + 2 * n_dnms + 2);
+    S.front0 = (int32_t*)carve<int32_t>(p, pairs); S.front1 = (int32_t*)carve<int32_t>(p, pairs);
     S.spos = (int32_t*)carve<int32_t>(p, hets); S.sref = (uint8_t*)carve<uint8_t>(p, hets);
     S.salt = (uint8_t*)carve<uint8_t>(p, hets); S.site_off = (int32_t*)carve<int32_t>(p, hets + n_dnms + 1);
     S.cand_off = (int32_t*)carve<int32_t>(p, hets + n_dnms + 1);
     S.bestkey = (unsigned long long*)carve<unsigned long long>(p, hets);
     S.site_cnt = (int32_t*)carve<int32_t>(p, hets); S.site_base = (int32_t*)carve<int32_t>(p, hets);
+    S.active = (int32_t*)carve<int32_t>(p, hets);
     S.cpos = (int32_t*)carve<int32_t>(p, cands);
     *total = (int64_t)(p - base);
     return S;
@@ -1306,6 +1481,10 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     A.S = carve_all((char*)base, h_totals[0], h_totals[1], h_totals[2], h_totals[3], h_totals[4], h_totals[5], n_dnms, &total);
     if ((int64_t)(base - (uintptr_t)scratch) + total > scratch_bytes) return unfz_fail(ctx, -20, "chain scratch too small");
     A.guard = ctx->guard;
+    if (!ctx->chain_carveout_set) {           // 8 CTAs x 26 KB of static shared memory per SM need the large carve-out
+        UNFZ_CHECK(ctx, cudaFuncSetAttribute(chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->chain_carveout_set = true;
+    }
     chain_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;

@@ -11,6 +11,7 @@ struct UnfzCtx {
     int device;
     int sm_count;
     const int32_t* guard;     // device flag of the speculative-sizing mode (unfz_ctx_set_guard), or null
+    bool chain_carveout_set;  // shared-memory carve-out preference of the chaining kernel set on THIS device
     size_t scan_smem_attr;    // opt-in dynamic shared memory already granted to the read scan on THIS device
     char err[512];
 };

@@ -292,6 +292,9 @@ class Engine:
         return out
 
     def upload_sites(self, table: SiteTable, pin: bool = False) -> DeviceSites:
+        if table.n_rows >= 2 ** 30:
+            # candidate words carry two flags above a 30-bit row index (include/unfazed_sm100.h, unfz_compact_sites)
+            raise ValueError("a SiteTable holds %d rows; one upload is limited to 2^30 - 1 (split the cohort)" % table.n_rows)
         return DeviceSites(table, self.device, pin)
 
     def upload_reads(self, table, pin: bool = False, min_gt_qual=20) -> DeviceReads:

@@ -111,14 +111,18 @@ def cross_kid_coupling(svs: Sequence[dict], pedigrees: dict, build, multiread_pr
 
 def phase_sharded(phase_fn: Callable[[List[dict]], Dict[str, dict]], dnms: Sequence[dict],
                   reads_per_kid: Optional[Dict[str, int]] = None,
-                  split_heavy: bool = True) -> Optional[Dict[str, dict]]:
+                  split_heavy: bool = True, all_on_rank0: bool = False) -> Optional[Dict[str, dict]]:
     """Run ``phase_fn`` on this rank's shard and gather the record dicts on rank 0 (None elsewhere).
-    Works without an initialised process group (single process)."""
+    Works without an initialised process group (single process).  ``all_on_rank0`` keeps the whole list
+    on rank 0 (runs whose kids are coupled) while every rank still takes part in the gather."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return phase_fn(list(dnms))
     rank, world = dist.get_rank(), dist.get_world_size()
-    mine = shard_dnms(dnms, world, reads_per_kid, split_heavy)[rank]
+    if all_on_rank0:
+        mine = list(dnms) if rank == 0 else []
+    else:
+        mine = shard_dnms(dnms, world, reads_per_kid, split_heavy)[rank]
     try:
         local = (True, phase_fn(mine) if mine else {})
     except BaseException as exc:                    # every rank must reach the gather

@@ -267,13 +267,10 @@ def _phase_multi_gpu(snvs, svs, common):
         return out
 
     if cross_kid_coupling(svs, pedigrees, build, mpm):
-        # one kid's events change another kid's windows (Q12): keep the run on one GPU to stay exact
-        if dist.get_rank() != 0:
-            dist.barrier()
-            return None
-        out = phase_fn(svs + snvs)
-        dist.barrier()
-        return out
+        # one kid's events change another kid's windows (Q12): the run stays on rank 0 to be exact.  It still goes
+        # through the gather protocol of phase_sharded (every rank reaches the collective, an exception on rank 0
+        # is re-raised after it), so a failure cannot leave the other ranks waiting
+        return phase_sharded(phase_fn, svs + snvs, split_heavy=False, all_on_rank0=True)
     # a family is only cut into slices when its DNMs cannot interact (per-DNM `find` windows)
     return phase_sharded(phase_fn, svs + snvs, split_heavy=len(snvs) < mpm and len(svs) < mpm)
 

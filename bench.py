@@ -341,6 +341,19 @@ def run_b200(args):
     t_gen = time.perf_counter() - t_gen
     eng = Engine(local_rank)
     dev = eng.device
+    with eng.on_stream():           # CUDA events below are recorded on the stream the kernels are launched on
+        _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_rank, world)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from unfazed_b200.engine import make_params
+    from unfazed_b200.phaser import BatchPhaser
+    from unfazed_b200.plan import SNV_TYPES, SV_TYPES
+    dev = eng.device
     kids = set(ds.pedigrees)
     svs = [d for d in ds.dnms if d["vartype"].upper() in SV_TYPES and d["kid"] in kids]
     snvs = [d for d in ds.dnms if d["vartype"].upper() in SNV_TYPES and d["kid"] in kids]
@@ -552,8 +565,6 @@ def run_b200(args):
             line["parity"] = len(bad) == 0
             line["parity_detail"] = {"dnms_compared": len(sample), "records_compared": len(want), "mismatches": bad[:5]}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def _k(d):

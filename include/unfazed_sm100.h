@@ -245,6 +245,13 @@ int unfz_compact_sites(UnfzCtx*, const UnfzDnm* dnms, int32_t n_dnms, const Unfz
                        int32_t* het_list, int32_t* n_het, uint32_t* cand_list, int32_t* n_cand,
                        int32_t* cnv_dad, int32_t* cnv_mom, uint8_t* row_mark, void* stream);
 
+/* Device-side completion of the site columns after an upload: the host table is plain SoA (gt / gq / rd / ad as
+ * [3][n_rows] member planes, kid dad mom); this writes the packed rows of UnfzSiteCols (meta, rec, dep).  No
+ * reference counterpart (cyvcf2 hands out per-record arrays, informative_site_finder.py:240-265). */
+int unfz_pack_site_rows(UnfzCtx*, int64_t n_rows, const int32_t* pos, const uint8_t* flag, const uint8_t* gt,
+                        const float* gq, const int32_t* rd, const int32_t* ad, uint32_t* meta, float* rec,
+                        int32_t* dep, void* stream);
+
 /* Device-side completion of the read columns after an upload: the host ships the positions of the (rare)
  * non-ACGT bases as a sorted list of base indices; this sets their bits in `nmask` (zeroed by the caller,
  * ceil(n_qual/32)+12 words) and bit2 of hdr[].aux of the reads that own them.  No reference counterpart
@@ -375,6 +382,15 @@ typedef struct {
     int64_t* ev_need;  int64_t* ev_off;  int32_t* ev_read_dad;  int32_t* ev_read_mom;  int32_t* ev_pos_dad;  int32_t* ev_pos_mom;
 } UnfzBatch;
 int unfz_run_batch(UnfzCtx*, const UnfzBatch* h_batch, void* stream);
+
+/* The same batch replayed as one CUDA graph: clears `n_zero` spans (the caller's zero-initialised buffers), runs the
+ * sequence of unfz_run_batch and copies `d2h_bytes` from d_src to the (pinned) host address h_dst.  Captured once per
+ * distinct set of arguments -- every pointer, capacity and parameter is part of the key -- and cached in the context
+ * (8 graphs, least recently used evicted).  `stream` must be a non-default stream.  Asynchronous like everything else:
+ * synchronise the stream before reading h_dst. */
+typedef struct { void* ptr; int64_t bytes; } UnfzSpan;
+int unfz_run_batch_graph(UnfzCtx*, const UnfzBatch* h_batch, const UnfzSpan* h_zero, int32_t n_zero,
+                         void* h_dst, const void* d_src, int64_t d2h_bytes, void* stream);
 int unfz_batch_struct_bytes(void);      /* sizeof(UnfzBatch), for bindings to check their mirror */
 
 #ifdef __cplusplus

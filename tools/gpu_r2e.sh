@@ -1,0 +1,9 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/r2e_pytest.log
+cat gpurun_out/r2e_pytest.log
+(
+python tools/dbg_chain.py 4000
+python tools/dbg_chain.py 10000
+python tools/dbg_chain.py 150 50000 60
+) 2>&1 | grep -v Warning | tee gpurun_out/r2e_chain.log

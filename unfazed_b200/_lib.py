@@ -69,6 +69,10 @@ class Batch(C.Structure):
     ]
 
 
+class Span(C.Structure):
+    _fields_ = [("ptr", c_void_p), ("bytes", c_int64)]
+
+
 SEG_DTYPE = np.dtype([
     ("sblk", "<i4"), ("lo_pos", "<i4"), ("hi_pos", "<i4"), ("mult", "<i4"),
     ("dnm", "<i4"), ("excl_lo", "<i4"), ("excl_hi", "<i4"), ("mode", "<i4"),
@@ -106,6 +110,7 @@ SYMBOLS = {
     "unfz_ctx_set_guard": (C.c_int, [_P, _P]),
     "unfz_check_caps": (C.c_int, [_P, c_int32, _P, _P, _P, _P, _P]),
     "unfz_run_batch": (C.c_int, [_P, C.POINTER(Batch), _P]),
+    "unfz_run_batch_graph": (C.c_int, [_P, C.POINTER(Batch), _P, c_int32, _P, _P, c_int64, _P]),
     "unfz_batch_struct_bytes": (C.c_int, []),
     "unfz_scan_work_bytes": (c_int64, [c_int64]),
     "unfz_exclusive_scan_i64": (C.c_int, [_P, _P, _P, c_int64, _P, _P]),
@@ -115,6 +120,7 @@ SYMBOLS = {
     "unfz_window_search": (C.c_int, [_P, C.POINTER(SiteCols), _P, c_int32, _P, _P, _P]),
     "unfz_classify_sites": (C.c_int, [_P, C.POINTER(SiteCols), _P, _P, _P, c_int32, c_int64, C.POINTER(Params), _P, _P]),
     "unfz_compact_sites": (C.c_int, [_P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "unfz_pack_site_rows": (C.c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "unfz_expand_nlist": (C.c_int, [_P, C.POINTER(ReadCols), _P, _P, _P, c_int64, _P]),
     "unfz_read_scan_tile_reads": (c_int32, [c_int32]),
     "unfz_read_scan": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, C.POINTER(Params), c_int32, _P, _P, _P, _P, _P, _P]),

@@ -18,12 +18,19 @@ extern "C" int unfz_ctx_create(int device, UnfzCtx** out) {
     c->guard = nullptr;
     c->scan_smem_attr = 0;
     c->chain_carveout_set = false;
+    memset(c->graphs, 0, sizeof(c->graphs));
+    c->graph_tick = 0;
     c->err[0] = 0;
     *out = c;
     return 0;
 }
 
-extern "C" void unfz_ctx_destroy(UnfzCtx* ctx) { delete ctx; }
+extern "C" void unfz_ctx_destroy(UnfzCtx* ctx) {
+    if (!ctx) return;
+    for (auto& g : ctx->graphs)
+        if (g.key) cudaGraphExecDestroy(g.exec);
+    delete ctx;
+}
 
 extern "C" const char* unfz_last_error(UnfzCtx* ctx) { return ctx ? ctx->err : "null context"; }
 
@@ -124,5 +131,69 @@ extern "C" int unfz_run_batch(UnfzCtx* ctx, const UnfzBatch* b, void* s) {
     UNFZ_RC(unfz_summarize(ctx, b->dnms, n, b->tally, b->cnv_dad, b->cnv_mom, b->n_cand, b->h_params, b->calls_strict,
                            b->calls_ambiguous, s));
     ctx->guard = nullptr;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same batch as ONE CUDA graph: the zero-fills of the caller's arenas, the ~25 launches of
+// unfz_run_batch and the device-to-host copy of the result block are captured once per buffer layout
+// and replayed with a single cudaGraphLaunch -- the per-launch gaps of the ten small kernels in front
+// of the read scan disappear, and nothing but this library's kernels runs on the stream.
+// The graph is keyed by a hash of every value the captured launches depend on (the batch struct, the
+// column structs and parameters behind its host pointers, the spans to clear, the copy); a caller that
+// recycles its buffers -- Engine.run does -- hits the cache from the third batch on.
+// `stream` must not be the legacy default stream (CUDA cannot capture it).
+// ------------------------------------------------------------------------------------------------
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+extern "C" int unfz_run_batch_graph(UnfzCtx* ctx, const UnfzBatch* b, const UnfzSpan* zero, int32_t n_zero,
+                                    void* h_dst, const void* d_src, int64_t d2h_bytes, void* stream) {
+    if (!ctx || !b) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint64_t key = 1469598103934665603ull;
+    key = fnv1a(key, b, sizeof(*b));
+    key = fnv1a(key, b->sites, sizeof(*b->sites));
+    if (b->reads) key = fnv1a(key, b->reads, sizeof(*b->reads));
+    key = fnv1a(key, b->h_params, sizeof(*b->h_params));
+    key = fnv1a(key, zero, sizeof(UnfzSpan) * (size_t)(n_zero > 0 ? n_zero : 0));
+    key = fnv1a(key, &h_dst, sizeof(h_dst));
+    key = fnv1a(key, &d_src, sizeof(d_src));
+    key = fnv1a(key, &d2h_bytes, sizeof(d2h_bytes));
+    if (key == 0) key = 1;
+    UnfzGraphSlot* slot = nullptr;
+    UnfzGraphSlot* victim = nullptr;                  // an empty slot if there is one, else the least recently used
+    for (auto& g : ctx->graphs) {
+        if (g.key == key) { slot = &g; break; }
+        if (!victim || (victim->key != 0 && (g.key == 0 || g.tick < victim->tick))) victim = &g;
+    }
+    if (!slot) {
+        cudaGraph_t graph = nullptr;
+        UNFZ_CHECK(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (int i = 0; i < n_zero && rc == 0; ++i)
+            if (zero[i].bytes > 0 && cudaMemsetAsync(zero[i].ptr, 0, (size_t)zero[i].bytes, s) != cudaSuccess) rc = -40;
+        if (rc == 0) rc = unfz_run_batch(ctx, b, s);
+        if (rc == 0 && d2h_bytes > 0 && cudaMemcpyAsync(h_dst, d_src, (size_t)d2h_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = -41;
+        const cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (rc != 0 || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc != 0 ? rc : unfz_fail(ctx, -42, "unfz_run_batch_graph: stream capture failed (legacy default stream?)");
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return unfz_fail(ctx, -43, cudaGetErrorString(ei));
+        if (victim->key) cudaGraphExecDestroy(victim->exec);
+        victim->key = key;
+        victim->exec = exec;
+        slot = victim;
+    }
+    slot->tick = ++ctx->graph_tick;
+    UNFZ_CHECK(ctx, cudaGraphLaunch(slot->exec, s));
     return 0;
 }

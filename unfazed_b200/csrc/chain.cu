@@ -17,7 +17,10 @@
 
 namespace {
 
-constexpr int CH_THREADS = 128;
+#ifndef CH_THREADS_N
+#define CH_THREADS_N 128
+#endif
+constexpr int CH_THREADS = CH_THREADS_N;
 constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr unsigned long long KEY_NONE = ~0ull;
 constexpr int CH_SMEM_SITES = 128;         // per-site state lives in shared memory up to this many het sites
@@ -46,6 +49,8 @@ struct Scratch {
     unsigned long long* bestkey; int32_t* site_cnt; int32_t* site_base; int32_t* active;
     // per candidate site
     int32_t* cpos;
+    // per DNM: hand-over between the three chaining kernels
+    int32_t* meta;
 };
 
 struct ChainArgs {
@@ -505,17 +510,20 @@ __device__ void bfs_levels(const BfsView<PT, ST>& V, int nh, int n_inc, int n_fr
     __syncthreads();
 }
 
-// per-pair state, incidence views and adjacency of the shared-memory mode
-constexpr int SM_P = 512;                 // dense pairs
-constexpr int SM_I = 768;                 // het-site incidences
-constexpr int SM_SI = 256;                // seed incidences
-
-// 8 CTAs per SM: ~27 KB of shared memory each
+// The chaining of one DNM runs as three kernels, one CTA per DNM each, because its parts want opposite things:
+//   chain_setup_kernel     seeds, het-site incidences, dense pair ids, allele codes, adjacency: chains of dependent
+//                          gathers -> as many resident CTAs as possible (16 per SM, almost no shared memory)
+//   chain_bfs_kernel       the level-synchronous colouring: no gathers at all once its few KB of state sit in shared
+//                          memory -> few CTAs per SM, each fast
+//   chain_evidence_kernel  matching against the informative sites + tallies: gathers again
+// The hand-over between them is the per-DNM global scratch the wide-window mode uses anyway.
 #ifndef CH_MINB
-#define CH_MINB 8
+#define CH_MINB 16
 #endif
+constexpr int META_INTS = 8;              // per DNM: pairs (-1: nothing to do), incidences, seed incidences, level-0 frontier, status
+
 __global__ void __launch_bounds__(CH_THREADS, CH_MINB)
-chain_kernel(ChainArgs A) {
+chain_setup_kernel(ChainArgs A) {
     UNFZ_GUARD(A.guard);
 #ifdef CH_DEBUG
     long long ch_t0 = clock64();
@@ -535,6 +543,7 @@ chain_kernel(ChainArgs A) {
         if (tid == 0) {
             A.tally[d] = T;
             if (A.ev_need) for (int q = 0; q < 4; ++q) A.ev_need[(int64_t)q * A.n_dnms + d] = 0;
+            S0.meta[(int64_t)d * META_INTS] = -1;
         }
         return;
     }
@@ -551,25 +560,21 @@ chain_kernel(ChainArgs A) {
 
     // per-DNM views of the global scratch
     SlotRec* rec = S0.slot + o_slot;
-    uint8_t* label_out = A.slot_label + o_slot; uint8_t* evid_out = A.slot_evid + o_slot;
     int32_t* inc_r = S0.inc_r + o_inc; int32_t* inc_x = S0.inc_x + o_inc; int32_t* inc_site = S0.inc_site + o_inc;
     int32_t* seed_e = S0.seed_e + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed; uint32_t* seed_reg = S0.seed_reg + o_seed;
     int32_t* x_of = S0.x_of + o_pair; int32_t* prim = S0.prim + o_pair;
     __shared__ int32_t sh_spos[CH_SMEM_SITES], sh_site_off[CH_SMEM_SITES + 1], sh_cand_off[CH_SMEM_SITES + 1];
     __shared__ int32_t sh_site_cnt[CH_SMEM_SITES], sh_site_base[CH_SMEM_SITES];
-    __shared__ unsigned long long sh_bestkey[CH_SMEM_SITES];
-    __shared__ uint8_t sh_sref[CH_SMEM_SITES], sh_salt[CH_SMEM_SITES], sh_active[CH_SMEM_SITES];
+    __shared__ uint8_t sh_sref[CH_SMEM_SITES], sh_salt[CH_SMEM_SITES];
     const bool small_sites = nh <= CH_SMEM_SITES;
     int32_t* spos = small_sites ? sh_spos : S0.spos + o_het;
     uint8_t* sref = small_sites ? sh_sref : S0.sref + o_het;
     uint8_t* salt = small_sites ? sh_salt : S0.salt + o_het;
     int32_t* site_off = small_sites ? sh_site_off : S0.site_off + o_het + d;
     int32_t* cand_off = small_sites ? sh_cand_off : S0.cand_off + o_het + d;
-    unsigned long long* bestkey = small_sites ? sh_bestkey : S0.bestkey + o_het;
     int32_t* site_cnt = small_sites ? sh_site_cnt : S0.site_cnt + o_het;
     int32_t* site_base = small_sites ? sh_site_base : S0.site_base + o_het;
     int32_t* cpos = S0.cpos + o_cand;
-    uint8_t* cev = A.cand_evid + lbase;
 
     const UnfzReadCols& R = A.reads;
     const int64_t blk_lo = R.blk_off[dn.rblk];
@@ -880,14 +885,6 @@ chain_kernel(ChainArgs A) {
     }
     if ((int64_t)P > cap_inc + cap_seed) { P = (int)(cap_inc + cap_seed); T.status |= 8; }     // cannot happen: one id per entry at most
 
-    // ---- storage class of the chaining state ---------------------------------------------------------------------
-    __shared__ __align__(8) unsigned long long sm_minkey[SM_P];
-    __shared__ uint32_t sm_ord[SM_P];
-    __shared__ int32_t sm_fpos[SM_P], sm_tmp[SM_P];
-    __shared__ uint32_t sm_sinc_sidx[SM_SI];
-    __shared__ uint16_t sm_inc_px[SM_I], sm_sinc_px[SM_SI], sm_adj[SM_I + SM_SI], sm_adj_off[SM_P + 2], sm_front[2][SM_P];
-    __shared__ uint8_t sm_label[SM_P], sm_inc_site[SM_I], sm_inc_al[SM_I], sm_sinc_site[SM_SI], sm_sinc_al[SM_SI];
-    const bool in_smem = small_sites && P <= SM_P && n_inc <= SM_I && cap_sinc <= SM_SI;
     // the rest of the set-up is the same code over either view
     int n_front0 = 0;
     auto setup = [&](auto& V) {
@@ -1002,39 +999,142 @@ chain_kernel(ChainArgs A) {
         __syncthreads();
         for (int p = tid; p < P; p += CH_THREADS) V.tmp[p] = 0;
         __syncthreads();
-    CH_MARK(6);
-        // -------------------------------------------------------- phase 4: level-synchronous BFS
-        bfs_levels(V, nh, n_inc, n_front0);
     };
-    if (in_smem) {
-        BfsView<uint16_t, uint8_t> VS;
-        VS.ord = sm_ord; VS.fpos = sm_fpos; VS.tmp = sm_tmp; VS.minkey = sm_minkey; VS.label = sm_label;
-        VS.inc_px = sm_inc_px; VS.inc_site = sm_inc_site; VS.inc_al = sm_inc_al;
-        VS.sinc_px = sm_sinc_px; VS.sinc_site = sm_sinc_site; VS.sinc_sidx = sm_sinc_sidx; VS.sinc_al = sm_sinc_al;
-        VS.adj = sm_adj; VS.adj_off = sm_adj_off; VS.front[0] = sm_front[0]; VS.front[1] = sm_front[1];
-        VS.spos = spos; VS.site_off = site_off; VS.bestkey = bestkey; VS.site_cnt = site_cnt; VS.site_base = site_base;
-        VS.active = sh_active;
-        setup(VS);
-    } else {
-        BfsView<int32_t, int32_t> VG;
-        VG.ord = S0.p_ord + o_pair; VG.fpos = S0.p_fpos + o_pair; VG.tmp = S0.p_tmp + o_pair; VG.minkey = S0.p_minkey + o_pair;
-        VG.label = S0.p_label + o_pair;
-        VG.inc_px = inc_x; VG.inc_site = inc_site; VG.inc_al = S0.inc_al + o_inc;          // the slot column becomes the pair column
-        VG.sinc_px = S0.sinc_px + o_sinc; VG.sinc_site = S0.sinc_site + o_sinc;
-        VG.sinc_sidx = S0.sinc_sidx + o_sinc; VG.sinc_al = S0.sinc_al + o_sinc;
-        VG.adj = S0.adj + o_adj; VG.adj_off = S0.adj_off + o_pair + 2 * (int64_t)d;
-        VG.front[0] = S0.front0 + o_pair; VG.front[1] = S0.front1 + o_pair;
-        VG.spos = spos; VG.site_off = site_off; VG.bestkey = bestkey; VG.site_cnt = site_cnt; VG.site_base = site_base;
-        VG.active = S0.active + o_het;
+    BfsView<int32_t, int32_t> VG;
+    VG.ord = S0.p_ord + o_pair; VG.fpos = S0.p_fpos + o_pair; VG.tmp = S0.p_tmp + o_pair; VG.minkey = S0.p_minkey + o_pair;
+    VG.label = S0.p_label + o_pair;
+    VG.inc_px = inc_x; VG.inc_site = inc_site; VG.inc_al = S0.inc_al + o_inc;          // the slot column becomes the pair column
+    VG.sinc_px = S0.sinc_px + o_sinc; VG.sinc_site = S0.sinc_site + o_sinc;
+    VG.sinc_sidx = S0.sinc_sidx + o_sinc; VG.sinc_al = S0.sinc_al + o_sinc;
+    VG.adj = S0.adj + o_adj; VG.adj_off = S0.adj_off + o_pair + 2 * (int64_t)d;
+    VG.front[0] = S0.front0 + o_pair; VG.front[1] = S0.front1 + o_pair;
+    VG.spos = spos; VG.site_off = site_off; VG.bestkey = nullptr; VG.site_cnt = site_cnt; VG.site_base = site_base;
+    VG.active = S0.active + o_het;
 
-        setup(VG);
-    }
+    setup(VG);
     __syncthreads();
+    // hand-over: what the next two kernels need and only shared memory holds
+    if (small_sites) {
+        int32_t* g_spos = S0.spos + o_het;
+        int32_t* g_off = S0.site_off + o_het + d;
+        for (int i = tid; i < nh; i += CH_THREADS) g_spos[i] = spos[i];
+        for (int i = tid; i <= nh; i += CH_THREADS) g_off[i] = A.no_extended ? 0 : site_off[i];
+    }
+    if (tid == 0) {
+        int32_t* m = S0.meta + (int64_t)d * META_INTS;
+        m[0] = P; m[1] = n_inc; m[2] = n_sinc; m[3] = n_front0; m[4] = T.status;
+    }
+    CH_MARK(6);
+}
+
+// per-pair state, incidence views and adjacency of the shared-memory mode
+constexpr int SM_P = 512;                 // dense pairs
+constexpr int SM_I = 768;                 // het-site incidences
+constexpr int SM_SI = 256;                // seed incidences
+#ifndef CH_BFS_MINB
+#define CH_BFS_MINB 8
+#endif
+
+__global__ void __launch_bounds__(CH_THREADS, CH_BFS_MINB)
+chain_bfs_kernel(ChainArgs A) {
+    UNFZ_GUARD(A.guard);
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x;
+    const Scratch& S0 = A.S;
+    const int32_t* meta = S0.meta + (int64_t)d * META_INTS;
+    const int P = meta[0], n_inc = meta[1], n_sinc = meta[2], n_front0 = meta[3];
+    if (P <= 0 || n_front0 <= 0 || A.no_extended) return;          // nothing can spread (labels of the seeds are final)
+    const int nh = A.n_het[d];
+    const int64_t* off = A.off;
+    const int64_t n1 = (int64_t)A.n_dnms + 1;
+    const int64_t o_inc = off[1 * n1 + d], o_seed = off[2 * n1 + d], o_sinc = off[3 * n1 + d], o_het = off[4 * n1 + d];
+    const int64_t o_pair = o_inc + o_seed, o_adj = o_inc + o_sinc;
+    BfsView<int32_t, int32_t> G;
+    G.ord = S0.p_ord + o_pair; G.fpos = S0.p_fpos + o_pair; G.tmp = S0.p_tmp + o_pair; G.minkey = S0.p_minkey + o_pair;
+    G.label = S0.p_label + o_pair;
+    G.inc_px = S0.inc_x + o_inc; G.inc_site = S0.inc_site + o_inc; G.inc_al = S0.inc_al + o_inc;
+    G.sinc_px = S0.sinc_px + o_sinc; G.sinc_site = S0.sinc_site + o_sinc;
+    G.sinc_sidx = S0.sinc_sidx + o_sinc; G.sinc_al = S0.sinc_al + o_sinc;
+    G.adj = S0.adj + o_adj; G.adj_off = S0.adj_off + o_pair + 2 * (int64_t)d;
+    G.front[0] = S0.front0 + o_pair; G.front[1] = S0.front1 + o_pair;
+    G.spos = S0.spos + o_het; G.site_off = S0.site_off + o_het + d; G.bestkey = S0.bestkey + o_het;
+    G.site_cnt = S0.site_cnt + o_het; G.site_base = S0.site_base + o_het; G.active = S0.active + o_het;
+    const int n_adj = G.adj_off[P];
+    if (!(nh <= CH_SMEM_SITES && P <= SM_P && n_inc <= SM_I && n_sinc <= SM_SI)) {
+        bfs_levels(G, nh, n_inc, n_front0);                        // wide window: the state stays in global scratch
+        return;
+    }
+    // stage the DNM's chaining state (a few KB, contiguous arrays) into shared memory, colour there, write the labels back
+    __shared__ __align__(8) unsigned long long sm_minkey[SM_P], sm_bestkey[CH_SMEM_SITES];
+    __shared__ uint32_t sm_ord[SM_P], sm_sinc_sidx[SM_SI];
+    __shared__ int32_t sm_fpos[SM_P], sm_tmp[SM_P], sm_spos[CH_SMEM_SITES], sm_site_off[CH_SMEM_SITES + 1];
+    __shared__ int32_t sm_site_cnt[CH_SMEM_SITES], sm_site_base[CH_SMEM_SITES];
+    __shared__ uint16_t sm_inc_px[SM_I], sm_sinc_px[SM_SI], sm_adj[SM_I + SM_SI], sm_adj_off[SM_P + 2], sm_front[2][SM_P];
+    __shared__ uint8_t sm_label[SM_P], sm_inc_site[SM_I], sm_inc_al[SM_I], sm_sinc_site[SM_SI], sm_sinc_al[SM_SI];
+    __shared__ uint8_t sm_active[CH_SMEM_SITES];
+    for (int p = tid; p < P; p += CH_THREADS) {
+        sm_ord[p] = G.ord[p]; sm_label[p] = G.label[p]; sm_adj_off[p] = (uint16_t)G.adj_off[p];
+        sm_fpos[p] = -1; sm_tmp[p] = 0; sm_minkey[p] = KEY_NONE;
+    }
+    if (tid == 0) sm_adj_off[P] = (uint16_t)n_adj;
+    for (int k = tid; k < n_inc; k += CH_THREADS) {
+        sm_inc_px[k] = (uint16_t)G.inc_px[k]; sm_inc_site[k] = (uint8_t)G.inc_site[k]; sm_inc_al[k] = G.inc_al[k];
+    }
+    for (int k = tid; k < n_sinc; k += CH_THREADS) {
+        sm_sinc_px[k] = (uint16_t)G.sinc_px[k]; sm_sinc_site[k] = (uint8_t)G.sinc_site[k];
+        sm_sinc_sidx[k] = G.sinc_sidx[k]; sm_sinc_al[k] = G.sinc_al[k];
+    }
+    for (int q = tid; q < n_adj; q += CH_THREADS) sm_adj[q] = (uint16_t)G.adj[q];
+    for (int f = tid; f < n_front0; f += CH_THREADS) sm_front[0][f] = (uint16_t)G.front[0][f];
+    for (int i = tid; i < nh; i += CH_THREADS) sm_spos[i] = G.spos[i];
+    for (int i = tid; i <= nh; i += CH_THREADS) sm_site_off[i] = G.site_off[i];
+    __syncthreads();
+    BfsView<uint16_t, uint8_t> V;
+    V.ord = sm_ord; V.fpos = sm_fpos; V.tmp = sm_tmp; V.minkey = sm_minkey; V.label = sm_label;
+    V.inc_px = sm_inc_px; V.inc_site = sm_inc_site; V.inc_al = sm_inc_al;
+    V.sinc_px = sm_sinc_px; V.sinc_site = sm_sinc_site; V.sinc_sidx = sm_sinc_sidx; V.sinc_al = sm_sinc_al;
+    V.adj = sm_adj; V.adj_off = sm_adj_off; V.front[0] = sm_front[0]; V.front[1] = sm_front[1];
+    V.spos = sm_spos; V.site_off = sm_site_off; V.bestkey = sm_bestkey; V.site_cnt = sm_site_cnt; V.site_base = sm_site_base;
+    V.active = sm_active;
+    bfs_levels(V, nh, n_inc, n_front0);
+    for (int p = tid; p < P; p += CH_THREADS) G.label[p] = sm_label[p];
+}
+
+__global__ void __launch_bounds__(CH_THREADS, CH_MINB)
+chain_evidence_kernel(ChainArgs A) {
+    UNFZ_GUARD(A.guard);
+#ifdef CH_DEBUG
+    long long ch_t0 = clock64();
+#endif
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x;
+    const Scratch& S0 = A.S;
+    const int32_t* meta = S0.meta + (int64_t)d * META_INTS;
+    const int P = meta[0];
+    if (P < 0) return;                                 // skipped by the set-up kernel (tally already written)
+    const UnfzDnm dn = A.dnms[d];
+    UnfzTally T;
+    T.n_dad_sites = T.n_mom_sites = T.n_dad_reads = T.n_mom_reads = 0;
+    T.cnv_dad = T.cnv_mom = 0;
+    T.has_record = 0;
+    T.status = meta[4];
+    const int nc = A.n_cand[d];
+    const int64_t lbase = A.seg_pair_off[dn.seg_lo];
+    const uint32_t* C = A.cand_list + lbase;
+    const int64_t* off = A.off;
+    const int64_t n1 = (int64_t)A.n_dnms + 1;
+    const int64_t o_slot = off[0 * n1 + d], o_inc = off[1 * n1 + d], o_seed = off[2 * n1 + d], o_cand = off[5 * n1 + d];
+    const int64_t o_pair = o_inc + o_seed;
+    uint8_t* label_out = A.slot_label + o_slot; uint8_t* evid_out = A.slot_evid + o_slot;
+    const int32_t* x_of = S0.x_of + o_pair; const int32_t* prim = S0.prim + o_pair;
+    const int32_t* cpos = S0.cpos + o_cand;
+    uint8_t* cev = A.cand_evid + lbase;
+    const UnfzReadCols& R = A.reads;
 
     CH_MARK(7);
     // ---------------------------------------------------------------- phase 5: matching + evidence
     int has_rec = 0, dr = 0, mr = 0;
-    const uint8_t* final_label = in_smem ? sm_label : S0.p_label + o_pair;
+    const uint8_t* final_label = S0.p_label + o_pair;
     for (int p = tid; p < P; p += CH_THREADS) {
         const uint8_t lab = final_label[p];
         if (!lab) continue;
@@ -1416,6 +1516,7 @@ Scratch carve_all(char* base, int64_t slots, int64_t incs, int64_t seeds, int64_
     S.site_cnt = (int32_t*)carve<int32_t>(p, hets); S.site_base = (int32_t*)carve<int32_t>(p, hets);
     S.active = (int32_t*)carve<int32_t>(p, hets);
     S.cpos = (int32_t*)carve<int32_t>(p, cands);
+    S.meta = (int32_t*)carve<int32_t>(p, n_dnms * 8);
     *total = (int64_t)(p - base);
     return S;
 }
@@ -1481,11 +1582,15 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     A.S = carve_all((char*)base, h_totals[0], h_totals[1], h_totals[2], h_totals[3], h_totals[4], h_totals[5], n_dnms, &total);
     if ((int64_t)(base - (uintptr_t)scratch) + total > scratch_bytes) return unfz_fail(ctx, -20, "chain scratch too small");
     A.guard = ctx->guard;
-    if (!ctx->chain_carveout_set) {           // 8 CTAs x 26 KB of static shared memory per SM need the large carve-out
-        UNFZ_CHECK(ctx, cudaFuncSetAttribute(chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (!ctx->chain_carveout_set) {           // 8 CTAs x 25 KB of static shared memory per SM need the large carve-out
+        UNFZ_CHECK(ctx, cudaFuncSetAttribute(chain_bfs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         ctx->chain_carveout_set = true;
     }
-    chain_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    chain_setup_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    UNFZ_LAUNCH_CHECK(ctx);
+    chain_bfs_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    UNFZ_LAUNCH_CHECK(ctx);
+    chain_evidence_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -7,12 +7,20 @@
 
 #include "../../include/unfazed_sm100.h"
 
+struct UnfzGraphSlot {
+    uint64_t key;             // hash of everything the captured launches depend on; 0 = empty
+    cudaGraphExec_t exec;
+    uint64_t tick;            // last use, for eviction
+};
+
 struct UnfzCtx {
     int device;
     int sm_count;
     const int32_t* guard;     // device flag of the speculative-sizing mode (unfz_ctx_set_guard), or null
     bool chain_carveout_set;  // shared-memory carve-out preference of the chaining kernel set on THIS device
     size_t scan_smem_attr;    // opt-in dynamic shared memory already granted to the read scan on THIS device
+    UnfzGraphSlot graphs[8];  // instantiated batch graphs (unfz_run_batch_graph)
+    uint64_t graph_tick;
     char err[512];
 };
 

@@ -342,7 +342,33 @@ compact_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const UnfzSegIn
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// upload completion: SoA genotype columns -> the classifier's 44-byte row layout
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_site_rows_kernel(int64_t n, const int32_t* __restrict__ pos, const uint8_t* __restrict__ flag,
+                                      const uint8_t* __restrict__ gt, const float* __restrict__ gq,
+                                      const int32_t* __restrict__ rd, const int32_t* __restrict__ ad,
+                                      uint32_t* __restrict__ meta, float4* __restrict__ rec, int2* __restrict__ dep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    meta[i] = (uint32_t)flag[i] | ((uint32_t)gt[i] << 8) | ((uint32_t)gt[n + i] << 16) | ((uint32_t)gt[2 * n + i] << 24);
+    rec[i] = make_float4(__int_as_float(pos[i]), gq[i], gq[n + i], gq[2 * n + i]);
+    dep[3 * i] = make_int2(rd[i], ad[i]);
+    dep[3 * i + 1] = make_int2(rd[n + i], ad[n + i]);
+    dep[3 * i + 2] = make_int2(rd[2 * n + i], ad[2 * n + i]);
+}
+
 }  // namespace
+
+extern "C" int unfz_pack_site_rows(UnfzCtx* ctx, int64_t n_rows, const int32_t* pos, const uint8_t* flag, const uint8_t* gt,
+                                   const float* gq, const int32_t* rd, const int32_t* ad, uint32_t* meta, float* rec,
+                                   int32_t* dep, void* stream) {
+    if (n_rows <= 0) return 0;
+    pack_site_rows_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n_rows, pos, flag, gt, gq, rd, ad, meta, reinterpret_cast<float4*>(rec), reinterpret_cast<int2*>(dep));
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
 
 extern "C" int unfz_window_search(UnfzCtx* ctx, const UnfzSiteCols* sites, const UnfzSegIn* segs, int32_t n_segs,
                                   int32_t* seg_row_lo, int64_t* seg_count, void* stream) {

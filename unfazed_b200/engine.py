@@ -12,6 +12,7 @@ Pipeline (one stream, in order):
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from dataclasses import dataclass, field
@@ -54,7 +55,7 @@ def pack_site_rows(pos, flag, gt, gq, rd, ad):
 
 
 class DeviceSites:
-    def __init__(self, table: SiteTable, device: torch.device, pin: bool = False):
+    def __init__(self, table: SiteTable, device: torch.device, pin: bool = False, engine: "Engine" = None):
         self.table = table
         self.n_rows = table.n_rows
         up = lambda a: _to_device(np.ascontiguousarray(a), device, pin)
@@ -62,7 +63,17 @@ class DeviceSites:
         self.pos, self.ref, self.alt = up(table.pos), up(table.ref), up(table.alt)
         flag, gt, gq, rd, ad = up(table.flag), up(table.gt), up(table.gq), up(table.rd), up(table.ad)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.pos, self.ref, self.alt, flag, gt, gq, rd, ad))
-        self.meta, self.rec, self.dep = pack_site_rows(self.pos, flag, gt, gq, rd, ad)
+        if engine is not None:
+            V = max(self.n_rows, 1)
+            self.meta = torch.empty((V,), dtype=torch.int32, device=device)
+            self.rec = torch.empty((V, 4), dtype=torch.float32, device=device)
+            self.dep = torch.empty((V, 6), dtype=torch.int32, device=device)
+            st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            engine._check(engine.lib.unfz_pack_site_rows(engine.ctx, self.n_rows, self.pos.data_ptr(), flag.data_ptr(), gt.data_ptr(),
+                                                         gq.data_ptr(), rd.data_ptr(), ad.data_ptr(), self.meta.data_ptr(),
+                                                         self.rec.data_ptr(), self.dep.data_ptr(), st), "pack_site_rows")
+        else:
+            self.meta, self.rec, self.dep = pack_site_rows(self.pos, flag, gt, gq, rd, ad)
         self.cols = make_site_cols(table.n_rows, table.n_blocks, self.blk_off, self.pos, self.ref, self.alt,
                                    self.meta, self.rec, self.dep)
 
@@ -231,6 +242,18 @@ class Engine:
         if rc != 0:
             raise RuntimeError("unfz_ctx_create failed (%d): libunfazed_sm100.so targets sm_100a only" % rc)
         self.ctx = ctx
+        # everything the engine does runs on its own stream: CUDA cannot capture the legacy default stream, and the
+        # batch is replayed as a CUDA graph (unfz_run_batch_graph)
+        self.stream = torch.cuda.Stream(self.device)
+        self.use_graph = not os.environ.get("UNFZ_NO_GRAPH")
+
+    def on_stream(self):
+        """Context: torch's current stream is the engine's (uploads, runs, events recorded by callers)."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur == self.stream:
+            return contextlib.nullcontext()
+        self.stream.wait_stream(cur)
+        return torch.cuda.stream(self.stream)
 
     def __del__(self):
         try:
@@ -245,6 +268,10 @@ class Engine:
         """Per read block: the reference's estimate_concordant_insert_len of the block's kid
         (read_collector.py:11-25), with the order statistics selected on the GPU
         (unfz_insert_size_order_stats) and numpy's own interpolation applied to them."""
+        with self.on_stream():
+            return self._concordant_upper_lens(dreads, readlen, insert_size_max_sample, stdevs)
+
+    def _concordant_upper_lens(self, dreads, readlen, insert_size_max_sample, stdevs):
         t = dreads.table
         lib, dev = self.lib, self.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -295,12 +322,14 @@ class Engine:
         if table.n_rows >= 2 ** 30:
             # candidate words carry two flags above a 30-bit row index (include/unfazed_sm100.h, unfz_compact_sites)
             raise ValueError("a SiteTable holds %d rows; one upload is limited to 2^30 - 1 (split the cohort)" % table.n_rows)
-        return DeviceSites(table, self.device, pin)
+        with self.on_stream():
+            return DeviceSites(table, self.device, pin, self)
 
     def upload_reads(self, table, pin: bool = False, min_gt_qual=20) -> DeviceReads:
         """Read columns -> device.  ``table`` is a ReadTable (reduced to the low-quality plane of
         ``min_gt_qual`` first) or a PackedReads (copied as it is)."""
-        return DeviceReads(table, self.device, pin, min_base_qual(min_gt_qual), self)
+        with self.on_stream():
+            return DeviceReads(table, self.device, pin, min_base_qual(min_gt_qual), self)
 
     def pack_reads(self, table: ReadTable, min_gt_qual=20, pin: bool = True) -> PackedReads:
         return PackedReads(table, min_base_qual(min_gt_qual), pin)
@@ -328,9 +357,13 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         return buf.numpy()
 
-    def run(self, dsites: DeviceSites, dreads: Optional[DeviceReads], plan: Plan, params: L.Params,
-            blk_cul: Optional[np.ndarray] = None, time_stages: bool = False, download: bool = True,
-            keep_device: bool = True, speculative: bool = True, evidence: bool = False) -> BatchResult:
+    def run(self, *args, **kw) -> BatchResult:
+        with self.on_stream():
+            return self._run(*args, **kw)
+
+    def _run(self, dsites: DeviceSites, dreads: Optional[DeviceReads], plan: Plan, params: L.Params,
+             blk_cul: Optional[np.ndarray] = None, time_stages: bool = False, download: bool = True,
+             keep_device: bool = True, speculative: bool = True, evidence: bool = False) -> BatchResult:
         """One batch through the pipeline.  The sizes of the variable outputs (pairs; hits + chain
         scratch) are only known on the device.  The first batch reads them back (two host syncs); later
         batches allocate from the capacities the engine has seen (+25 %), have the device check them
@@ -348,6 +381,9 @@ class Engine:
         caps = getattr(self, "_caps", None)
         spec = bool(speculative and download and caps is not None)
         reuse = not keep_device and not os.environ.get("UNFZ_NO_ARENA_REUSE")
+        # recycled buffers at stable addresses + sizes known up front: the batch is one CUDA graph, which also clears
+        # the zero-initialised arenas (no torch fill kernels on the stream)
+        graph = bool(spec and not time_stages and reuse and self.use_graph)
         pool = self.__dict__.setdefault("_arena_pool", {})
         arenas: List = []
 
@@ -365,7 +401,7 @@ class Engine:
                 self.items.append((name, self.size, int(nbytes)))
                 self.size += (int(nbytes) + 255) & ~255
 
-            def alloc(self_):
+            def alloc(self_, clear=True):
                 # a run that keeps nothing on the device hands its buffers back (see the end of run());
                 # the next run with the same layout reuses them and only clears the zero-initialised ones
                 self_.key = (self_.zero, tuple(self_.items))
@@ -373,7 +409,7 @@ class Engine:
                 if buf is None:
                     fn = torch.zeros if self_.zero else torch.empty
                     buf = fn((max(self_.size, 256),), dtype=torch.uint8, device=dev)
-                elif self_.zero:
+                elif self_.zero and clear:
                     buf.zero_()
                 self_.buf = buf
                 arenas.append(self_)
@@ -440,7 +476,7 @@ class Engine:
             e1.add("tile_tot", 4 * n_tiles)
             e1.add("tile_base", 4 * (n_tiles + 1))
             e1.add("tile_info", 8 * n_tiles)
-        z1.alloc()
+        z1.alloc(clear=not graph)
         e1.alloc()
         R = z1.ptr["result"]
         rp = {nm: R + 4 * o for nm, o in r_off.items()}
@@ -459,7 +495,7 @@ class Engine:
             if want_ev:
                 e.add("ev_pos_dad", 4 * n_pairs_ + 16)
                 e.add("ev_pos_mom", 4 * n_pairs_ + 16)
-            z.alloc()
+            z.alloc(clear=not graph)
             e.alloc()
             return z, e
 
@@ -473,7 +509,7 @@ class Engine:
             if want_ev:
                 e.add("ev_read_dad", 4 * int(totals_[0]) + 16)
                 e.add("ev_read_mom", 4 * int(totals_[0]) + 16)
-            z.alloc()
+            z.alloc(clear=not graph)
             e.alloc()
             return z, e, nb
 
@@ -538,8 +574,13 @@ class Engine:
                     b.ev_need, b.ev_off = z1.ptr["ev_need"], z1.ptr["ev_off"]
                     b.ev_read_dad, b.ev_read_mom = e3.ptr["ev_read_dad"], e3.ptr["ev_read_mom"]
                     b.ev_pos_dad, b.ev_pos_mom = e2.ptr["ev_pos_dad"], e2.ptr["ev_pos_mom"]
-            self._check(lib.unfz_run_batch(ctx, C.byref(b), s), "run_batch")
-            launches += (20 if has_reads else 11) + (2 if want_ev else 0)
+            if graph:
+                zs = [z1, z2] + ([z3] if has_reads else [])
+                spans = (L.Span * len(zs))(*[L.Span(z_.buf.data_ptr(), z_.buf.numel()) for z_ in zs])
+                self._check(lib.unfz_run_batch_graph(ctx, C.byref(b), spans, len(zs), None, None, 0, s), "run_batch_graph")
+            else:
+                self._check(lib.unfz_run_batch(ctx, C.byref(b), s), "run_batch")
+            launches += (22 if has_reads else 11) + (2 if want_ev else 0)
             h_pair_off, h_off = None, None
             res = BatchResult(plan=plan, n_pairs=int(caps["pairs"]), n_hits=int(caps["hits"]) if has_reads else 0,
                               seg_row_lo=None, seg_pair_off=None, n_het=None, n_cand=None, cnv_dad=None, cnv_mom=None)
@@ -652,7 +693,7 @@ class Engine:
                                                  z3.ptr["slot_label"], z3.ptr["slot_evid"], z2.ptr["cand_evid"], rp["tally"],
                                                  z1.ptr["ev_need"] if want_ev else None, s),
                             "chain_tally")
-                launches += 1
+                launches += 3
                 mark("chain_tally")
                 if want_ev:
                     self._check(lib.unfz_exclusive_scan_rows_i64(ctx, z1.ptr["ev_need"], z1.ptr["ev_off"], 4, n, s), "scan(ev)")
@@ -689,7 +730,7 @@ class Engine:
                     # a capacity was exceeded: nothing was written out of bounds, run again with exact sizes
                     self._caps = None
                     dv.clear()
-                    return self.run(dsites, dreads, plan, params, blk_cul=blk_cul, time_stages=time_stages,
+                    return self._run(dsites, dreads, plan, params, blk_cul=blk_cul, time_stages=time_stages,
                                     download=download, keep_device=keep_device, speculative=False, evidence=evidence)
                 h_pair_off = sect("seg_pair_off").view(np.int64)[: S + 1].copy()
                 res.seg_pair_off = h_pair_off

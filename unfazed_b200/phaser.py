@@ -195,24 +195,42 @@ class BatchPhaser:
         s = self.sites
         a, b = layout["sv_cnv"]
         cnv: Dict[str, dict] = {}
-        for d in range(a, b):
-            dn = plan.entries[d]
-            dad, mom = self.ped[dn["kid"]]["dad"], self.ped[dn["kid"]]["mom"]
-            if plan.dnm["flags"][d] & L.DNM_AUTOPHASE:
-                cnv[dnm_key(dn)] = self._auto_record(dn, dad, mom)
-                continue
-            if dn["vartype"] not in ("DEL", "DUP") or res.n_cand[d] == 0:
-                continue
-            vd, vm = [], []
-            for w in res.cand_words(d).view(np.uint32).tolist():
-                votes_dad = bool(w & 0x80000000) == bool(w & 0x40000000)
-                (vd if votes_dad else vm).append(str(int(s.pos[w & 0x3FFFFFFF])))
-            cnv[dnm_key(dn)] = {
-                "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
-                "vartype": dn["vartype"], "kid": dn["kid"], "dad": dad, "mom": mom,
-                "cnv_dad_sites": vd, "cnv_mom_sites": vm, "cnv_evidence_type": "ALLELE-BALANCE",
-                "dad_sites": "", "mom_sites": "", "evidence_type": "", "dad_reads": [], "mom_reads": [],
-            }
+        if b > a:
+            # phase_by_snvs (sv_phaser.py:71-85) for all CNV entries at once: every candidate votes for
+            # site[site["kid_allele"]]; the per-parent str(pos) lists are cut out of two flat lists
+            n_c = np.asarray(res.n_cand[a:b], dtype=np.int64)
+            seg_lo, seg_hi = plan.dnm["seg_lo"][a:b], plan.dnm["seg_hi"][a:b]
+            base = np.where(seg_hi > seg_lo, res.seg_pair_off[np.minimum(seg_lo, len(res.seg_pair_off) - 1)], 0).astype(np.int64)
+            is_cnv = np.fromiter((plan.entries[d]["vartype"] in ("DEL", "DUP") for d in range(a, b)), dtype=bool, count=b - a)
+            n_c = np.where(is_cnv, n_c, 0)
+            tot = int(n_c.sum())
+            if tot:
+                owner = np.repeat(np.arange(b - a), n_c)
+                flat = np.repeat(base, n_c) + (np.arange(tot) - np.repeat(np.cumsum(n_c) - n_c, n_c))
+                w = res._np("cand_list").view(np.uint32)[flat]
+                dad_vote = ((w >> 31) & 1) == ((w >> 30) & 1)
+                strs = np.array(list(map(str, s.pos[(w & 0x3FFFFFFF).astype(np.int64)].tolist())), dtype=object)
+                d_flat, m_flat = strs[dad_vote].tolist(), strs[~dad_vote].tolist()
+                nd_ = np.bincount(owner[dad_vote], minlength=b - a)
+                od = np.concatenate([[0], np.cumsum(nd_)]).tolist()
+                om = np.concatenate([[0], np.cumsum(n_c - nd_)]).tolist()
+            flags_c = plan.dnm["flags"][a:b].tolist()
+            n_cl = n_c.tolist()
+            for i, d in enumerate(range(a, b)):
+                dn = plan.entries[d]
+                dad, mom = self.ped[dn["kid"]]["dad"], self.ped[dn["kid"]]["mom"]
+                if flags_c[i] & L.DNM_AUTOPHASE:
+                    cnv[dnm_key(dn)] = self._auto_record(dn, dad, mom)
+                    continue
+                if n_cl[i] == 0:
+                    continue
+                cnv[dnm_key(dn)] = {
+                    "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
+                    "vartype": dn["vartype"], "kid": dn["kid"], "dad": dad, "mom": mom,
+                    "cnv_dad_sites": d_flat[od[i]:od[i + 1]], "cnv_mom_sites": m_flat[om[i]:om[i + 1]],
+                    "cnv_evidence_type": "ALLELE-BALANCE",
+                    "dad_sites": "", "mom_sites": "", "evidence_type": "", "dad_reads": [], "mom_reads": [],
+                }
         ev = res.ev
         if ev is not None:
             # evidence lists compacted per DNM and per parent on the device: every string of the batch is made in

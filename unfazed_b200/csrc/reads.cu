@@ -57,19 +57,26 @@ __device__ __forceinline__ int count_bits(Ptr w, int b0, int b1) {
 //    are sorted by start): it advances 32 rows at a time out of a register prefetched one step
 //    ahead, so the steady state issues no dependent global load for it.  When a tile runs into the
 //    next read block that block's window is opened next to it and promoted when the tiles get there;
-//  * per read: CIGAR walk out of shared memory, branch-free search of the window, two mark-prefix
-//    gathers (L2), low-quality count by POPC over the staged bit span;
+//  * per read: CIGAR walk out of shared memory, forward probe of the window (row positions and their mark
+//    prefixes side by side: a read's hit count is a difference of two window entries), low-quality count by
+//    POPC over the staged bit span;
 //  * hit slots are numbered per tile: one warp scan, one total per tile, no cross-warp scan.
 // ------------------------------------------------------------------------------------------------
-// 5 warps x 4 CTAs per SM: the 20 warps spread evenly over the four sub-partitions (16 K registers each),
-// which leaves 96 registers per thread; 7 x 3 puts 6 warps on one sub-partition, caps the kernel at 80
-// registers and spills (measured: 0.42 ms vs 0.35 ms at 4000 DNMs)
+// 6 warps x 4 CTAs per SM (80 registers, no spills).  With quality BYTES staged the kernel was bandwidth-bound and
+// 5 x 4 (96 registers) was the best point; with one BIT per base it is bound by instruction issue (about 800 issue
+// slots per 32-read tile) and wants the extra warps: measured 0.522 ms (5 x 4), 0.493 ms (6 x 4), 0.613 ms (8 x 4: 64
+// registers, spills) for 22.7 M reads.
+#ifndef WP_MINB
 #define WP_MINB 4
-constexpr int WP_WARPS = 5;
+#endif
+#ifndef WP_WARPS_N
+#define WP_WARPS_N 6
+#endif
+constexpr int WP_WARPS = WP_WARPS_N;
 constexpr int WP_THREADS = WP_WARPS * 32;
 constexpr int WP_CIGW = 64;                               // staged CIGAR words per tile
 constexpr int WP_SPOS = 64;                               // site positions per window
-constexpr int WP_FIXED = 2 * WP_CIGW * 4 + 2 * WP_SPOS * 4;   // per warp, next to the two quality slices
+constexpr int WP_FIXED = 2 * WP_CIGW * 4 + 4 * WP_SPOS * 4;   // per warp, next to the two quality slices: CIGAR words, row positions + mark prefixes
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -139,6 +146,7 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
     uint8_t* my = smem + warp * (2 * qslice + WP_FIXED);
     uint32_t* cigbuf = reinterpret_cast<uint32_t*>(my + 2 * qslice);
     int32_t* spos = reinterpret_cast<int32_t*>(my + 2 * qslice + 2 * WP_CIGW * 4);
+    int32_t* smp = spos + 2 * WP_SPOS;                       // mark_prefix of the same rows: a read's hit count is a difference of two
 
     // read and row indices fit 32 bits (mate / row_lb are int32 in the ABI)
     const int n = (int)reads.n_reads;
@@ -204,7 +212,7 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
     long long cul = -1;                                           // floor(concordant_upper_len): |insert| is an integer
     // The window lives in shared memory only: registers written by global loads would make every hot-path
     // instruction that reads them wait on the (statically assigned) scoreboard of whatever load is in flight.
-    int32_t w2 = 0x7fffffff;                                     // rows row_base + 64 + lane, read only when the window advances
+    int32_t w2 = 0x7fffffff, w2m = 0;                            // rows row_base + 64 + lane, read only when the window advances
     int cur = 0;                                                 // first window entry >= the tile's first start (uniform)
     int bmax = 0;                                                // longest span seen in the current block
     int rb1 = -1, sblk1 = -1;                                    // the next block, opened when a tile runs into it
@@ -213,6 +221,7 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
     // (double)ins <= c for an integer ins >= 0  <=>  ins <= floor(c); NaN and negative bounds admit nothing
     auto cul_floor = [](double c) -> long long { return c >= 0.0 ? (c < 9.0e18 ? (long long)floor(c) : 0x7fffffffffffffffll) : -1; };
     auto row_at = [&](int i, int rend) -> int32_t { return i < rend ? __ldg(sites.pos + i) : 0x7fffffff; };
+    auto mp_at = [&](int i, int rend) -> int32_t { return __ldg(mark_prefix + min(i, rend)); };   // rows past the block: its total
     auto open_block = [&](int rb, int32_t first_start, int& sb, int& bend, long long& c, int& rbase, int& rend) {
         bend = (int)reads.blk_off[rb + 1];
         sb = reads.blk_sblk[rb];
@@ -244,14 +253,20 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
             if (rb0 == rb1) {                                  // opened while the previous tile ran into it
                 sblk = sblk1; blk_end = blk_end1; cul = cul1; row_base = row_base1; row_end = row_end1;
                 const int32_t a = spos[WP_SPOS + lane], b = spos[WP_SPOS + 32 + lane];
+                const int32_t am = smp[WP_SPOS + lane], bm = smp[WP_SPOS + 32 + lane];
                 spos[lane] = a;
                 spos[32 + lane] = b;
+                smp[lane] = am;
+                smp[32 + lane] = bm;
             } else {
                 open_block(rb0, f_start, sblk, blk_end, cul, row_base, row_end);
                 spos[lane] = row_at(row_base + lane, row_end);
                 spos[32 + lane] = row_at(row_base + 32 + lane, row_end);
+                smp[lane] = mp_at(row_base + lane, row_end);
+                smp[32 + lane] = mp_at(row_base + 32 + lane, row_end);
             }
             w2 = row_at(row_base + 64 + lane, row_end);
+            w2m = mp_at(row_base + 64 + lane, row_end);
             cur = 0;
             bmax = 0;
             __syncwarp();
@@ -263,15 +278,20 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
                 row_base = (int)warp_lower_bound(sites.pos, row_base + WP_SPOS, row_end, f_start, lane);
                 spos[lane] = row_at(row_base + lane, row_end);
                 spos[32 + lane] = row_at(row_base + 32 + lane, row_end);
+                smp[lane] = mp_at(row_base + lane, row_end);
+                smp[32 + lane] = mp_at(row_base + 32 + lane, row_end);
                 cur = 0;
             } else {
-                const int32_t b = spos[32 + lane];
+                const int32_t b = spos[32 + lane], bm = smp[32 + lane];
                 spos[lane] = b;
                 spos[32 + lane] = w2;
+                smp[lane] = bm;
+                smp[32 + lane] = w2m;
                 row_base += 32;
                 cur -= 32;
             }
             w2 = row_at(row_base + 64 + lane, row_end);        // consumed at the next advance
+            w2m = mp_at(row_base + 64 + lane, row_end);
             __syncwarp();
         }
         const bool two = last >= blk_end;                      // the tile runs into the next read block
@@ -281,6 +301,8 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
             open_block(rb1, first1, sblk1, blk_end1, cul1, row_base1, row_end1);
             spos[WP_SPOS + lane] = row_at(row_base1 + lane, row_end1);
             spos[WP_SPOS + 32 + lane] = row_at(row_base1 + 32 + lane, row_end1);
+            smp[WP_SPOS + lane] = mp_at(row_base1 + lane, row_end1);
+            smp[WP_SPOS + 32 + lane] = mp_at(row_base1 + 32 + lane, row_end1);
         }
 
         cp_async_wait<1>();                                    // this tile's spans have landed (all but the newest group)
@@ -352,14 +374,20 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
                 if (lo2 == WP_SPOS) {                          // ran off the staged window: finish in global memory
                     if (lo == WP_SPOS) lbs = (int)lower_bound_dev(sites.pos, rbase + WP_SPOS - 1, rend, start);
                     lbe = (int)lower_bound_dev(sites.pos, max(lbs, rbase + WP_SPOS - 1), rend, end);
+                    fmark = __ldg(mark_prefix + lbs);
+                    emark = __ldg(mark_prefix + lbe);
+                } else {                                       // the mark prefixes of the window's rows sit next to their positions
+                    const int32_t* wmp = smp + which * WP_SPOS;
+                    fmark = wmp[lo];
+                    emark = wmp[lo2];
                 }
             } else {
                 const int64_t a = sites.blk_off[sb], b = sites.blk_off[sb + 1];
                 lbs = (int)lower_bound_dev(sites.pos, a, b, start);
                 lbe = (int)lower_bound_dev(sites.pos, lbs, b, end);
+                fmark = __ldg(mark_prefix + lbs);
+                emark = __ldg(mark_prefix + lbe);
             }
-            fmark = __ldg(mark_prefix + lbs);                  // two L2 gathers, in flight during the quality count below
-            emark = __ldg(mark_prefix + lbe);
         }
 
         // ---- goodread: low-quality bases out of the staged span ---------------------------------------

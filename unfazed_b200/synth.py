@@ -113,12 +113,19 @@ def _place_dnms(cfg: SynthConfig, rng: np.random.Generator, trio: int):
     clustered = rng.random(n) < cfg.cluster_frac
     start = np.zeros(n, dtype=np.int64)
     base_stride = 2 * cfg.search_dist + 2 * cfg.read_margin + 2 * sp
+    # cohort mode: every trio gets its own stretch of each contig.  The site table stands in for a joint VCF, where a
+    # position holds ONE record; trios that shared coordinates would see each other's records in get_refalt (Q22)
+    trio_shift = 0
+    if cfg.trio_ids is not None:
+        per_contig = -(-n // max(ncont, 1)) + 2
+        trio_shift = trio * ((per_contig * (base_stride + 1000 + cfg.sv_max_len * (cfg.sv_frac > 0)) // sp + 4) * sp)
     cur = 0
     prev_c = -1
     for i in range(n):
         if contig[i] != prev_c:
             # sex chromosomes: start beyond PAR1 of either table (utils.py:26-43)
             cur = 3_000_000 if contig[i] >= ncont else 100 * sp
+            cur += trio_shift
             cur += cfg.search_dist + cfg.read_margin + int(rng.integers(0, 64)) * sp
             prev_c = contig[i]
             first = True

@@ -422,36 +422,43 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
     h2d_bytes = h2d_sites + host_reads.nbytes + plan.dnm.nbytes + plan.seg.nbytes + plan.alleles.nbytes
     d2h = {"bytes": 0}
 
+    gather = {"ms": 0.0, "n": 0}
+
     def step_e2e():
         recs = bpe.phase(ds.dnms, **phase_kw)
-        return recs
+        if cohort and world > 1:
+            # the cohort is ONE job: rank 0 ends every step holding the records of all ranks (what the CLI's
+            # _phase_multi_gpu does before it writes the output)
+            t_g = time.perf_counter()
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(recs, gathered, dst=0)
+            gather["ms"] += (time.perf_counter() - t_g) * 1e3
+            gather["n"] += 1
+            if rank == 0:
+                recs_all = {}
+                for g in gathered:
+                    recs_all.update(g)
+                return recs, len(recs_all)
+        return recs, len(recs)
 
     recs = None
     for _ in range(2):
-        recs = step_e2e()
+        recs, n_records = step_e2e()
+    gather["ms"], gather["n"] = 0.0, 0
     parts = {}
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        recs = step_e2e()
+        recs, n_records = step_e2e()
         for k, v in bpe.last_timing.items():
             parts[k] = parts.get(k, 0.0) + v / args.steps
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
-    n_records = len(recs)
-    # cohort: the host gather of the records on rank 0 belongs to the job
-    gather_ms = 0.0
-    if cohort and world > 1:
-        t0 = time.perf_counter()
-        gathered = [None] * world if rank == 0 else None
-        dist.gather_object(recs, gathered, dst=0)
-        gather_ms = (time.perf_counter() - t0) * 1e3
-        if rank == 0:
-            n_records = sum(len(g) for g in gathered)
+    gather_ms = gather["ms"] / max(gather["n"], 1)
     bpe.release_device()
 
     ms_step = ms_total / args.steps
-    t_max = torch.tensor([ms_step, e2e_s * 1000.0 + gather_ms / max(args.steps, 1)], device=dev, dtype=torch.float64)
+    t_max = torch.tensor([ms_step, e2e_s * 1000.0], device=dev, dtype=torch.float64)
     tot = torch.tensor([float(n_dnms), float(n_pairs), float(n_reads), float(phased), float(n_hits), float(win_reads)],
                        device=dev, dtype=torch.float64)
     if world > 1:
@@ -470,8 +477,8 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         hd = ds.reads.hdr
         n_cig, n_base = int(hd["n_cigar"].sum()), int(hd["l_seq"].sum())
-        # algorithmic bytes: header 32 + CIGAR 4/op + 1 bit per base in, 20 B summary out
-        rs_bytes = float(32 * n_reads + 4 * n_cig + n_base / 8.0 + 20 * n_reads)
+        # algorithmic bytes: header 32 + CIGAR 4/op + 1 bit per base in, 32 B summary + 4 B row index out
+        rs_bytes = float(32 * n_reads + 4 * n_cig + n_base / 8.0 + 36 * n_reads)
         # read-by-site allele lookup unit of SURVEY 8(d) in this format: scan bytes + 2-bit base and quality bit at
         # every hit + 4 B per hit word
         lookup_bytes = rs_bytes + float(n_hits) * (1 + 4)

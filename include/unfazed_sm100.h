@@ -126,13 +126,18 @@ typedef struct {
     int64_t         n_cigar;
 } UnfzReadCols;
 
-/* per-read summary written by unfz_read_scan (16 B) */
+/* per-read summary written by unfz_read_scan: ONE 32-byte sector holds everything the chaining asks about a read
+ * (its span, its mate, its filter flags and where its hit words are), so a candidate read costs one sector, not a
+ * summary sector plus a header sector */
 typedef struct {
     int32_t  end;         /* reference_end (exclusive) */
     int32_t  fmark;       /* number of marked site rows before the first row with pos >= start */
     uint16_t flags;       /* UNFZ_RS_* */
     uint16_t cnt;         /* marked site rows with start <= pos < end */
     uint32_t hoff;        /* first hit word of this read, relative to its scan tile (see unfz_read_scan) */
+    int32_t  start;       /* reference_start (copy of the header field) */
+    int32_t  mate;        /* mate index or -1 (copy of the header field) */
+    int32_t  _pad[2];
 } UnfzReadSum;
 
 typedef struct {

@@ -87,8 +87,9 @@ TALLY_DTYPE = np.dtype([
     ("cnv_dad", "<i4"), ("cnv_mom", "<i4"), ("has_record", "<i4"), ("status", "<i4"),
 ])
 CALL_DTYPE = np.dtype([("origin", "<i4"), ("evidence_count", "<i4"), ("evidence_types", "<i4"), ("emitted", "<i4")])
-RSUM_DTYPE = np.dtype([("end", "<i4"), ("fmark", "<i4"), ("flags", "<u2"), ("cnt", "<u2"), ("hoff", "<u4")])
-assert SEG_DTYPE.itemsize == 32 and DNM_DTYPE.itemsize == 48 and RSUM_DTYPE.itemsize == 16
+RSUM_DTYPE = np.dtype([("end", "<i4"), ("fmark", "<i4"), ("flags", "<u2"), ("cnt", "<u2"), ("hoff", "<u4"),
+                       ("start", "<i4"), ("mate", "<i4"), ("pad0", "<i4"), ("pad1", "<i4")])
+assert SEG_DTYPE.itemsize == 32 and DNM_DTYPE.itemsize == 48 and RSUM_DTYPE.itemsize == 32
 
 # constants of include/unfazed_sm100.h
 CLS_HET, CLS_CAND, CLS_ALT_IS_DAD, CLS_KID_ALT = 1, 2, 4, 8

@@ -74,14 +74,15 @@ struct ChainArgs {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
-__device__ __forceinline__ int32_t rd_start(const UnfzReadCols& R, int64_t r) { return __ldg(&R.hdr[r].start); }
-__device__ __forceinline__ int32_t rd_mate(const UnfzReadCols& R, int64_t r) { return __ldg(&R.hdr[r].mate); }
+// start and mate of a read come out of its 32-byte summary (same sector as end / flags / hit slots), not the header
+__device__ __forceinline__ int32_t rs_start(const UnfzReadSum* __restrict__ S, int64_t r) { return __ldg(&S[r].start); }
+__device__ __forceinline__ int32_t rs_mate(const UnfzReadSum* __restrict__ S, int64_t r) { return __ldg(&S[r].mate); }
 
 // first read index in [lo,hi) with start >= v
-__device__ __forceinline__ int64_t lb_start(const UnfzReadCols& R, int64_t lo, int64_t hi, int64_t v) {
+__device__ __forceinline__ int64_t lb_start(const UnfzReadSum* __restrict__ R, int64_t lo, int64_t hi, int64_t v) {
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)rd_start(R, mid) < v) lo = mid + 1; else hi = mid;
+        if ((int64_t)rs_start(R, mid) < v) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -134,16 +135,14 @@ __device__ __forceinline__ uint32_t hit_lookup(const ChainArgs& A, int64_t e, in
 
 // goodread + insert + mate + None-count + mate-overlap (read_collector.py:181-214, :395-418)
 __device__ bool pair_ok(const ChainArgs& A, int64_t r, bool ext) {
-    const UnfzReadSum s = load_rsum(A.rsum + r);
-    const int4 hr = __ldg(reinterpret_cast<const int4*>(A.reads.hdr + r));      // start, tlen, mate, cigar_off
+    const UnfzReadSum s = load_rsum(A.rsum + r);                                // one sector: span, mate, flags
     uint32_t need = UNFZ_RS_GOOD_CONC | UNFZ_RS_INS_OK | UNFZ_RS_HAS_MATE | UNFZ_RS_NONE_OK;
     if (ext) need |= UNFZ_RS_EXT_OK;
     const bool ok_r = (s.flags & need) == need;                                  // HAS_MATE: mate >= 0
-    const int64_t m = ok_r ? (int64_t)hr.z : r;
-    const UnfzReadSum sm = load_rsum(A.rsum + m);
-    const int32_t m0 = rd_start(A.reads, m);
+    const int64_t m = ok_r ? (int64_t)s.mate : r;
+    const UnfzReadSum sm = load_rsum(A.rsum + m);                               // one sector for the mate
     const uint32_t needm = UNFZ_RS_GOOD_CONC | UNFZ_RS_NONE_OK;
-    const int32_t r0 = hr.x, r1 = s.end, m1 = sm.end;
+    const int32_t r0 = s.start, r1 = s.end, m0 = sm.start, m1 = sm.end;
     return ok_r && (sm.flags & needm) == needm && !((m0 <= r0 && r0 <= m1) || (m0 <= r1 && r1 <= m1));
 }
 
@@ -224,7 +223,7 @@ __device__ bool sv_goodok(const ChainArgs& A, int64_t r) {
     const UnfzReadSum s = load_rsum(A.rsum + r);
     const uint32_t need = UNFZ_RS_GOOD_DISC | UNFZ_RS_HAS_MATE;
     if ((s.flags & need) != need) return false;
-    const int64_t m = rd_mate(A.reads, r);
+    const int64_t m = rs_mate(A.rsum, r);
     return (load_rsum(A.rsum + m).flags & UNFZ_RS_GOOD_DISC) != 0;
 }
 
@@ -250,7 +249,7 @@ __device__ int sv_support(const ChainArgs& A, const UnfzDnm& dn, int64_t r, int6
     if ((double)ins > cul) {
         const double ratio = fabs(var_len / (double)ins);
         if (0.7 < ratio && ratio < 1.3) {
-            const int64_t m0 = rd_start(A.reads, h.mate);
+            const int64_t m0 = rs_start(A.rsum, h.mate);
             const int64_t left0 = min(m0, r0), right0 = max(m0, r0);
             const int64_t w = (int64_t)cul;
             if ((dn.pos - w) < left0 && left0 < (dn.pos + w) && (dn.end - w) < right0 && right0 < (dn.end + w)) return 2;
@@ -344,7 +343,7 @@ __device__ int bisect_pivot(const int32_t* __restrict__ spos, int n, int32_t sta
 // bits2-3 target (needs the position in the PRIMARY read and base quality >= min)
 __device__ uint8_t allele_info(const ChainArgs& A, const Scratch& S, int64_t e0, int64_t row, char ref, char alt) {
     if (e0 < 0) return 0;
-    const int64_t e1 = rd_mate(A.reads, e0);          // in flight with the first lookup
+    const int64_t e1 = rs_mate(A.rsum, e0);          // in flight with the first lookup
     const uint32_t h0 = hit_lookup(A, e0, row);
     uint32_t h = h0;
     if (!(h0 & 0xffffu)) {
@@ -592,7 +591,7 @@ chain_setup_kernel(ChainArgs A) {
     };
     // canonical window slot of the pair a read belongs to (the lower read index inside the window)
     auto canon = [&](int64_t r) -> int {
-        const int64_t m = rd_mate(R, r);
+        const int64_t m = rs_mate(A.rsum, r);
         const int sr = slot_of(r), sm = m >= 0 ? slot_of(m) : -1;
         if (sr < 0) return sm;
         if (sm < 0) return sr;
@@ -652,7 +651,7 @@ chain_setup_kernel(ChainArgs A) {
             const int k = n_seed + 2 * block_prefix(hap != 0, &tot);
             if (hap && k + 1 < cap_seed) {
                 seed_e[k] = (int32_t)r; seed_hap[k] = (uint8_t)hap;
-                seed_e[k + 1] = rd_mate(R, r); seed_hap[k + 1] = (uint8_t)hap;
+                seed_e[k + 1] = rs_mate(A.rsum, r); seed_hap[k + 1] = (uint8_t)hap;
             }
             n_seed += 2 * tot;
         }
@@ -679,7 +678,7 @@ chain_setup_kernel(ChainArgs A) {
                 int tot;
                 const int k = n_seed + 2 * block_prefix(sup != 0, &tot);
                 if (sup && k + 1 < cap_seed) {
-                    const int32_t m = rd_mate(R, r);
+                    const int32_t m = rs_mate(A.rsum, r);
                     seed_e[k] = sup == 1 ? (int32_t)r : m; seed_hap[k] = 2;
                     seed_e[k + 1] = sup == 1 ? m : (int32_t)r; seed_hap[k + 1] = 2;
                 }
@@ -696,9 +695,9 @@ chain_setup_kernel(ChainArgs A) {
             int32_t e = 0;
             if (k < n_seed) {
                 e = seed_e[k];
-                const int64_t m = rd_mate(R, e);
+                const int64_t m = rs_mate(A.rsum, e);
                 auto in_end_fetch = [&](int64_t z) {
-                    return z >= e_lo && z < e_hi && (int64_t)A.rsum[z].end > e_flo && (int64_t)rd_start(R, z) < e_fhi;
+                    return z >= e_lo && z < e_hi && (int64_t)A.rsum[z].end > e_flo && (int64_t)rs_start(A.rsum, z) < e_fhi;
                 };
                 const bool banned = (in_end_fetch(e) && sv_banned(A, e)) || (m >= 0 && in_end_fetch(m) && sv_banned(A, m));
                 keep = !banned;
@@ -951,7 +950,7 @@ chain_setup_kernel(ChainArgs A) {
                 if (rec[x].key == (((unsigned long long)(reg + 1u) << 32) | (uint32_t)e))     // once per pair
                     V.front[0][atomicAdd(&s_front, 1)] = (PT)px;
                 if (nh_reg > 0) {
-                    st = rd_start(R, e);
+                    st = rs_start(A.rsum, e);
                     en = A.rsum[e].end;
                     piv = bisect_pivot(spos, nh_reg, st, en);
                     if (piv >= 0) {
@@ -1154,7 +1153,6 @@ chain_evidence_kernel(ChainArgs A) {
     const int32_t* x_of = S0.x_of + o_pair; const int32_t* prim = S0.prim + o_pair;
     const int32_t* cpos = S0.cpos + o_cand;
     uint8_t* cev = A.cand_evid + lbase;
-    const UnfzReadCols& R = A.reads;
 
     CH_MARK(7);
     // ---------------------------------------------------------------- phase 5: matching + evidence
@@ -1164,12 +1162,12 @@ chain_evidence_kernel(ChainArgs A) {
         const uint8_t lab = final_label[p];
         if (!lab) continue;
         const int64_t e0 = prim[p];
-        const int64_t ents[2] = {e0, (int64_t)rd_mate(R, e0)};
+        const int64_t ents[2] = {e0, (int64_t)rs_mate(A.rsum, e0)};
         uint8_t ev = 0;
         for (int t = 0; t < 2; ++t) {
             const int64_t e = ents[t];
             if (e < 0) continue;
-            const int32_t st = rd_start(R, e), en = A.rsum[e].end;
+            const int32_t st = rs_start(A.rsum, e), en = A.rsum[e].end;
             int lb = 0, hi = nc;
             while (lb < hi) { const int mid = (lb + hi) >> 1; if (cpos[mid] < st) lb = mid + 1; else hi = mid; }
             if (lb >= nc || cpos[lb] >= en) continue;           // binary_search finds nothing
@@ -1316,23 +1314,23 @@ __device__ __forceinline__ int64_t warp_max64(int64_t v) {
 }
 
 // lb_start by a whole warp: 32 probes per round trip (all lanes get the result)
-__device__ __forceinline__ int64_t warp_lb_start(const UnfzReadCols& R, int64_t lo, int64_t hi, int64_t v, int lane) {
+__device__ __forceinline__ int64_t warp_lb_start(const UnfzReadSum* __restrict__ R, int64_t lo, int64_t hi, int64_t v, int lane) {
     while (hi - lo > 32) {
         const int64_t step = (hi - lo + 32) / 33;
         const int64_t i = lo + (int64_t)(lane + 1) * step - 1;
-        const bool lt = i < hi && (int64_t)rd_start(R, i) < v;
+        const bool lt = i < hi && (int64_t)rs_start(R, i) < v;
         const int k = __popc(__ballot_sync(0xffffffffu, lt));
         const int64_t nhi = k < 32 ? min(hi, lo + (int64_t)(k + 1) * step - 1) : hi;
         lo += (int64_t)k * step;
         hi = nhi;
     }
-    const bool lt = lo + lane < hi && (int64_t)rd_start(R, lo + lane) < v;
+    const bool lt = lo + lane < hi && (int64_t)rs_start(R, lo + lane) < v;
     return lo + __popc(__ballot_sync(0xffffffffu, lt));
 }
 // lb_start when the answer is expected a few dozen reads after lo: gallop, then bisect
-__device__ __forceinline__ int64_t lb_start_near(const UnfzReadCols& R, int64_t lo, int64_t hi, int64_t v) {
+__device__ __forceinline__ int64_t lb_start_near(const UnfzReadSum* __restrict__ R, int64_t lo, int64_t hi, int64_t v) {
     int64_t step = 32, top = lo;
-    while (top + step < hi && (int64_t)rd_start(R, top + step - 1) < v) { top += step; step <<= 1; }
+    while (top + step < hi && (int64_t)rs_start(R, top + step - 1) < v) { top += step; step <<= 1; }
     return lb_start(R, top, min(hi, top + step), v);
 }
 
@@ -1381,8 +1379,8 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
             if (i < CS_HP) hp[i] = (int32_t)p;
             if (p < mid) { minA = min(minA, p); maxA = max(maxA, p + 1); }
             else { minB = min(minB, p); maxB = max(maxB, p + 1); }
-            const int64_t a = lb_start(reads, blk_lo, blk_hi, p - maxspan + 1);
-            const int64_t b = lb_start_near(reads, a, blk_hi, p + 1);
+            const int64_t a = lb_start(rsum, blk_lo, blk_hi, p - maxspan + 1);
+            const int64_t b = lb_start_near(rsum, a, blk_hi, p + 1);
             site_lo[lbase + i] = (int32_t)(a - blk_lo);
             site_n[lbase + i] = (int32_t)(b - a);
             incs += b - a;
@@ -1390,11 +1388,11 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
         minA = warp_min64(minA); maxA = warp_max64(maxA); minB = warp_min64(minB); maxB = warp_max64(maxB);
         nd[1] = warp_sum64(incs);
         __syncwarp();
-        a_lo = warp_lb_start(reads, blk_lo, blk_hi, minA - maxspan + 1, lane);
-        a_hi = warp_lb_start(reads, a_lo, blk_hi, maxA, lane);
+        a_lo = warp_lb_start(rsum, blk_lo, blk_hi, minA - maxspan + 1, lane);
+        a_hi = warp_lb_start(rsum, a_lo, blk_hi, maxA, lane);
         if (maxB > minB) {
-            b_lo = warp_lb_start(reads, blk_lo, blk_hi, minB - maxspan + 1, lane);
-            b_hi = warp_lb_start(reads, b_lo, blk_hi, maxB, lane);
+            b_lo = warp_lb_start(rsum, blk_lo, blk_hi, minB - maxspan + 1, lane);
+            b_hi = warp_lb_start(rsum, b_lo, blk_hi, maxB, lane);
             if (b_lo <= a_hi) { a_hi = max(a_hi, b_hi); a_lo = min(a_lo, b_lo); b_lo = b_hi = 0; }
         }
         nd[0] = ((a_hi - a_lo) + (b_hi - b_lo) + 3) & ~(int64_t)3;   // word-aligned label/evidence regions
@@ -1402,16 +1400,16 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
         int64_t seeds = 0, sincs = 0;
         for (int wdx = 0; wdx < (sv ? 2 : 1); ++wdx) {
             const int64_t flo = wdx ? sb_lo : sa_lo, fhi = wdx ? sb_hi : sa_hi;
-            const int64_t a = warp_lb_start(reads, blk_lo, blk_hi, flo - maxspan + 1, lane);
-            const int64_t b = warp_lb_start(reads, a, blk_hi, fhi, lane);
+            const int64_t a = warp_lb_start(rsum, blk_lo, blk_hi, flo - maxspan + 1, lane);
+            const int64_t b = warp_lb_start(rsum, a, blk_hi, fhi, lane);
             if (lane == 0) { seed_win[4 * (int64_t)d + 2 * wdx] = (int32_t)a; seed_win[4 * (int64_t)d + 2 * wdx + 1] = (int32_t)b; }
             seeds += 2 * (b - a);
             for (int64_t r = a + lane; r < b; r += 32) {
-                const int64_t ents[2] = {r, (int64_t)reads.hdr[r].mate};
+                const int64_t ents[2] = {r, (int64_t)rsum[r].mate};
                 for (int t = 0; t < 2; ++t) {
                     const int64_t e = ents[t];
                     if (e < 0) continue;
-                    const int64_t st = reads.hdr[e].start, en = rsum[e].end;
+                    const int64_t st = rsum[e].start, en = rsum[e].end;
                     int l = 0, h = nh;
                     int u;
                     if (nh <= CS_HP) {                               // het positions staged per warp

@@ -77,7 +77,9 @@ __device__ __forceinline__ UnfzRead load_read(const UnfzRead* __restrict__ p) {
 }
 
 __device__ __forceinline__ UnfzReadSum load_rsum(const UnfzReadSum* __restrict__ p) {
-    union { UnfzReadSum r; int4 v; } u;
-    u.v = __ldg(reinterpret_cast<const int4*>(p));
+    union { UnfzReadSum r; int4 v[2]; } u;
+    const int4* q = reinterpret_cast<const int4*>(p);
+    u.v[0] = __ldg(q);
+    u.v[1] = __ldg(q + 1);
     return u.r;
 }

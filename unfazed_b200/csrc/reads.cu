@@ -415,10 +415,9 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
             if (tile_info && lane == 0) tile_info[T] = make_uint2(has, (uint32_t)rb0);
         }
         if (live) {
-            UnfzReadSum o;
-            o.end = end; o.fmark = fmark; o.flags = (uint16_t)flags; o.cnt = (uint16_t)cnt;
-            o.hoff = (uint32_t)(incl - cnt);
-            *reinterpret_cast<int4*>(out + r) = *reinterpret_cast<const int4*>(&o);
+            int4* o = reinterpret_cast<int4*>(out + r);        // the 32-byte summary as two 16-byte stores
+            o[0] = make_int4(end, fmark, (int)((uint32_t)(flags & 0xffffu) | ((uint32_t)cnt << 16)), incl - cnt);
+            o[1] = make_int4(start, mate, 0, 0);
             if (row_lb) row_lb[r] = lbs;
         }
         __syncwarp();                                          // the slice may be refilled by the next iteration

@@ -29,6 +29,11 @@ def register_tables(name: str, sites: Optional[SiteTable] = None, reads: Optiona
     _registry[name] = (sites, reads)
 
 
+def is_registered(name: str) -> bool:
+    """True for a name bound to in-memory tables with register_tables() (such a name needs no file)."""
+    return name in _registry
+
+
 def _npz(name):
     if name not in _npz_cache:
         _npz_cache[name] = load_tables(name)

@@ -469,7 +469,7 @@ class Engine:
             z1.add("need", 8 * 6 * n)
             if want_ev:
                 z1.add("ev_need", 8 * 4 * n)
-            e1.add("rsum", 16 * N)
+            e1.add("rsum", 32 * N)
             e1.add("row_lb", 4 * N)
             tile_reads = int(lib.unfz_read_scan_tile_reads(dreads.max_l_seq))
             n_tiles = (N + tile_reads - 1) // tile_reads

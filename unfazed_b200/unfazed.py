@@ -10,7 +10,7 @@ import gzip
 import os
 import sys
 
-from . import __version__
+from . import __version__, datasource
 from .snv_phaser import phase_snvs
 from .sv_phaser import phase_svs
 from .utils import HET, HOM_ALT, LABELS, SNV_TYPES, SV_TYPES, VCF_TYPES
@@ -62,7 +62,7 @@ def get_bam_names(bam_dir, bam_pairs, cram_ref):
                 cram |= ext == "cram"
                 found.setdefault(os.path.splitext(os.path.basename(path))[0], set()).add(path)
     for sample, path in (bam_pairs or []):
-        if not os.path.isfile(path) and not path.startswith("mem://"):
+        if not os.path.isfile(path) and not datasource.is_registered(path):      # tables bound with register_tables()
             sys.exit("invalid filename " + path)
         found[sample] = {path}
         cram |= path.endswith("cram")

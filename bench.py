@@ -477,8 +477,8 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         hd = ds.reads.hdr
         n_cig, n_base = int(hd["n_cigar"].sum()), int(hd["l_seq"].sum())
-        # algorithmic bytes: header 32 + CIGAR 4/op + 1 bit per base in, 32 B summary + 4 B row index out
-        rs_bytes = float(32 * n_reads + 4 * n_cig + n_base / 8.0 + 36 * n_reads)
+        # algorithmic bytes: header 32 + CIGAR 4/op + 1 bit per base in, 32 B summary out
+        rs_bytes = float(32 * n_reads + 4 * n_cig + n_base / 8.0 + 32 * n_reads)
         # read-by-site allele lookup unit of SURVEY 8(d) in this format: scan bytes + 2-bit base and quality bit at
         # every hit + 4 B per hit word
         lookup_bytes = rs_bytes + float(n_hits) * (1 + 4)

@@ -113,6 +113,8 @@ typedef struct {
     const int32_t*  blk_sblk;    /* [n_blocks] site block holding this kid's trio on this contig, or -1 */
     const double*   blk_cul;     /* [n_blocks] concordant_upper_len of the kid */
     const UnfzRead* hdr;
+    const int32_t*  start;       /* dense copy of hdr[].start (unfz_read_starts): the window searches of the chaining bisect
+                                    over it -- 32 starts per 128-byte line instead of 4 */
     const uint32_t* cigar;       /* BAM encoding len<<4|op */
     const uint32_t* lowq;        /* 1 bit per query base (bit i&31 of word i>>5): base quality < --min-gt-qual.
                                     Every use of a base quality on this path is that one comparison (goodread
@@ -137,7 +139,8 @@ typedef struct {
     uint32_t hoff;        /* first hit word of this read, relative to its scan tile (see unfz_read_scan) */
     int32_t  start;       /* reference_start (copy of the header field) */
     int32_t  mate;        /* mate index or -1 (copy of the header field) */
-    int32_t  _pad[2];
+    int32_t  row_lb;      /* first site row of the read's block with pos >= start (where the allele lookup starts walking) */
+    int32_t  _pad;
 } UnfzReadSum;
 
 typedef struct {
@@ -263,6 +266,8 @@ int unfz_pack_site_rows(UnfzCtx*, int64_t n_rows, const int32_t* pos, const uint
  * (pysam hands out query_sequence as a string). */
 int unfz_expand_nlist(UnfzCtx*, const UnfzReadCols* reads, UnfzRead* hdr_rw, uint32_t* nmask_rw,
                       const int64_t* nidx, int64_t n_idx, void* stream);
+/* ... and the dense start column of UnfzReadCols out of the headers. */
+int unfz_read_starts(UnfzCtx*, const UnfzReadCols* reads, int32_t* start_rw, void* stream);
 
 /* Read scan: goodread :28-53, insert-size / None-count / CIGAR-op filters :181-203 :395-408,
  * reference_end and the number of marked site rows each read overlaps.
@@ -275,7 +280,6 @@ int32_t unfz_read_scan_tile_reads(int32_t max_l_seq);
 int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                    const int32_t* mark_prefix, const UnfzParams* h_params,
                    int32_t max_l_seq /* longest read, 0 = unknown: picks the staging strategy */, UnfzReadSum* out,
-                   int32_t* row_lb /* [n_reads] first site row with pos >= start (input of unfz_read_site_alleles) */,
                    int32_t* blk_maxspan /* [n_blocks], zeroed by the caller: max(end-start) */,
                    uint32_t* tile_tot /* [ceil(n_reads / tile_reads)] */,
                    uint32_t* tile_info /* [2 * n_tiles] or NULL: per tile {bit i: read i has hits, read block of the
@@ -288,7 +292,7 @@ int unfz_read_scan(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* site
  * bit16 base quality < --min-gt-qual, bit23 base is not ACGT, bits24-25 base code, bit26: index+1 < l_seq. */
 int unfz_read_site_alleles(UnfzCtx*, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                            const uint8_t* row_mark, const int32_t* mark_prefix,
-                           const UnfzReadSum* rsum, const int32_t* row_lb, const uint32_t* tile_base,
+                           const UnfzReadSum* rsum, const uint32_t* tile_base,
                            int32_t tile_reads, uint32_t* hits, const uint32_t* tile_info /* from unfz_read_scan, or NULL */,
                            void* stream);
 
@@ -376,7 +380,7 @@ typedef struct {
     int32_t* n_het;  int32_t* n_cand;  int32_t* cnv_dad;  int32_t* cnv_mom;
     UnfzTally* tally;  UnfzCall* calls_strict;  UnfzCall* calls_ambiguous;  int32_t* win;
     int32_t* blk_maxspan;  int64_t* need;  int64_t* off;          /* off: 6*(n_dnms+1) + 1 entries */
-    UnfzReadSum* rsum;  int32_t* row_lb;  uint32_t* tile_tot;  uint32_t* tile_base;  uint32_t* tile_info;
+    UnfzReadSum* rsum;  uint32_t* tile_tot;  uint32_t* tile_base;  uint32_t* tile_info;
     /* sized by cap_pairs */
     uint8_t* cls;  int32_t* het_list;  uint32_t* cand_list;  int32_t* site_lo;  int32_t* site_n;  int32_t* seed_win;
     uint8_t* cand_evid;

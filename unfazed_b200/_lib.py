@@ -30,7 +30,7 @@ class ReadCols(C.Structure):
     _fields_ = [
         ("n_reads", c_int64), ("n_blocks", c_int32), ("_pad", c_int32),
         ("blk_off", c_void_p), ("blk_sblk", c_void_p), ("blk_cul", c_void_p),
-        ("hdr", c_void_p), ("cigar", c_void_p), ("lowq", c_void_p), ("nmask", c_void_p), ("seq2", c_void_p),
+        ("hdr", c_void_p), ("start", c_void_p), ("cigar", c_void_p), ("lowq", c_void_p), ("nmask", c_void_p), ("seq2", c_void_p),
         ("n_qual", c_int64), ("n_cigar", c_int64),
     ]
 
@@ -60,7 +60,7 @@ class Batch(C.Structure):
         ("n_het", c_void_p), ("n_cand", c_void_p), ("cnv_dad", c_void_p), ("cnv_mom", c_void_p),
         ("tally", c_void_p), ("calls_strict", c_void_p), ("calls_ambiguous", c_void_p), ("win", c_void_p),
         ("blk_maxspan", c_void_p), ("need", c_void_p), ("off", c_void_p),
-        ("rsum", c_void_p), ("row_lb", c_void_p), ("tile_tot", c_void_p), ("tile_base", c_void_p), ("tile_info", c_void_p),
+        ("rsum", c_void_p), ("tile_tot", c_void_p), ("tile_base", c_void_p), ("tile_info", c_void_p),
         ("cls", c_void_p), ("het_list", c_void_p), ("cand_list", c_void_p), ("site_lo", c_void_p), ("site_n", c_void_p),
         ("seed_win", c_void_p), ("cand_evid", c_void_p),
         ("hits", c_void_p), ("scratch", c_void_p), ("scratch_bytes", c_int64), ("slot_label", c_void_p), ("slot_evid", c_void_p),
@@ -88,7 +88,7 @@ TALLY_DTYPE = np.dtype([
 ])
 CALL_DTYPE = np.dtype([("origin", "<i4"), ("evidence_count", "<i4"), ("evidence_types", "<i4"), ("emitted", "<i4")])
 RSUM_DTYPE = np.dtype([("end", "<i4"), ("fmark", "<i4"), ("flags", "<u2"), ("cnt", "<u2"), ("hoff", "<u4"),
-                       ("start", "<i4"), ("mate", "<i4"), ("pad0", "<i4"), ("pad1", "<i4")])
+                       ("start", "<i4"), ("mate", "<i4"), ("row_lb", "<i4"), ("pad", "<i4")])
 assert SEG_DTYPE.itemsize == 32 and DNM_DTYPE.itemsize == 48 and RSUM_DTYPE.itemsize == 32
 
 # constants of include/unfazed_sm100.h
@@ -124,8 +124,9 @@ SYMBOLS = {
     "unfz_pack_site_rows": (C.c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "unfz_expand_nlist": (C.c_int, [_P, C.POINTER(ReadCols), _P, _P, _P, c_int64, _P]),
     "unfz_read_scan_tile_reads": (c_int32, [c_int32]),
-    "unfz_read_scan": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, C.POINTER(Params), c_int32, _P, _P, _P, _P, _P, _P]),
-    "unfz_read_site_alleles": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, _P, _P, _P, _P, c_int32, _P, _P, _P]),
+    "unfz_read_scan": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, C.POINTER(Params), c_int32, _P, _P, _P, _P, _P]),
+    "unfz_read_site_alleles": (C.c_int, [_P, C.POINTER(ReadCols), C.POINTER(SiteCols), _P, _P, _P, _P, c_int32, _P, _P, _P]),
+    "unfz_read_starts": (C.c_int, [_P, C.POINTER(ReadCols), _P, _P]),
     "unfz_chain_size": (C.c_int, [_P, _P, c_int32, _P, _P, C.POINTER(SiteCols), C.POINTER(ReadCols), _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "unfz_chain_scratch_bytes": (c_int64, [c_int64] * 7),

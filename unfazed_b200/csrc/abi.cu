@@ -99,7 +99,7 @@ extern "C" int unfz_run_batch(UnfzCtx* ctx, const UnfzBatch* b, void* s) {
     UNFZ_RC(unfz_exclusive_scan_u8_i32(ctx, b->row_mark, b->mark_prefix, V, b->scan_work, s));
     if (b->reads != nullptr) {
         int64_t* total_hits = b->off + 6 * ((int64_t)n + 1);
-        UNFZ_RC(unfz_read_scan(ctx, b->reads, b->sites, b->mark_prefix, b->h_params, b->max_l_seq, b->rsum, b->row_lb,
+        UNFZ_RC(unfz_read_scan(ctx, b->reads, b->sites, b->mark_prefix, b->h_params, b->max_l_seq, b->rsum,
                                b->blk_maxspan, b->tile_tot, b->tile_info, s));
         UNFZ_RC(unfz_exclusive_scan_u32(ctx, b->tile_tot, b->tile_base, b->n_tiles, total_hits, b->scan_work, s));
         UNFZ_RC(unfz_chain_size(ctx, b->dnms, n, b->segs, b->seg_pair_off, b->sites, b->reads, b->rsum, b->blk_maxspan,
@@ -114,7 +114,7 @@ extern "C" int unfz_run_batch(UnfzCtx* ctx, const UnfzBatch* b, void* s) {
             c[6] = b->cap_hits;
             UNFZ_RC(unfz_check_caps(ctx, 7, t, c, b->guard, b->actual + 1, s));
         }
-        UNFZ_RC(unfz_read_site_alleles(ctx, b->reads, b->sites, b->row_mark, b->mark_prefix, b->rsum, b->row_lb, b->tile_base,
+        UNFZ_RC(unfz_read_site_alleles(ctx, b->reads, b->sites, b->row_mark, b->mark_prefix, b->rsum, b->tile_base,
                                        b->tile_reads, b->hits, b->tile_info, s));
         UNFZ_RC(unfz_chain_tally(ctx, b->dnms, n, b->segs, b->seg_pair_off, b->sites, b->reads, b->rsum, b->blk_maxspan,
                                  b->hits, b->tile_base, b->tile_reads, b->mark_prefix, b->het_list, b->n_het, b->cand_list,

@@ -79,10 +79,10 @@ __device__ __forceinline__ int32_t rs_start(const UnfzReadSum* __restrict__ S, i
 __device__ __forceinline__ int32_t rs_mate(const UnfzReadSum* __restrict__ S, int64_t r) { return __ldg(&S[r].mate); }
 
 // first read index in [lo,hi) with start >= v
-__device__ __forceinline__ int64_t lb_start(const UnfzReadSum* __restrict__ R, int64_t lo, int64_t hi, int64_t v) {
+__device__ __forceinline__ int64_t lb_start(const int32_t* __restrict__ R, int64_t lo, int64_t hi, int64_t v) {
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)rs_start(R, mid) < v) lo = mid + 1; else hi = mid;
+        if ((int64_t)__ldg(R + mid) < v) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -1314,23 +1314,23 @@ __device__ __forceinline__ int64_t warp_max64(int64_t v) {
 }
 
 // lb_start by a whole warp: 32 probes per round trip (all lanes get the result)
-__device__ __forceinline__ int64_t warp_lb_start(const UnfzReadSum* __restrict__ R, int64_t lo, int64_t hi, int64_t v, int lane) {
+__device__ __forceinline__ int64_t warp_lb_start(const int32_t* __restrict__ R, int64_t lo, int64_t hi, int64_t v, int lane) {
     while (hi - lo > 32) {
         const int64_t step = (hi - lo + 32) / 33;
         const int64_t i = lo + (int64_t)(lane + 1) * step - 1;
-        const bool lt = i < hi && (int64_t)rs_start(R, i) < v;
+        const bool lt = i < hi && (int64_t)__ldg(R + i) < v;
         const int k = __popc(__ballot_sync(0xffffffffu, lt));
         const int64_t nhi = k < 32 ? min(hi, lo + (int64_t)(k + 1) * step - 1) : hi;
         lo += (int64_t)k * step;
         hi = nhi;
     }
-    const bool lt = lo + lane < hi && (int64_t)rs_start(R, lo + lane) < v;
+    const bool lt = lo + lane < hi && (int64_t)__ldg(R + lo + lane) < v;
     return lo + __popc(__ballot_sync(0xffffffffu, lt));
 }
 // lb_start when the answer is expected a few dozen reads after lo: gallop, then bisect
-__device__ __forceinline__ int64_t lb_start_near(const UnfzReadSum* __restrict__ R, int64_t lo, int64_t hi, int64_t v) {
+__device__ __forceinline__ int64_t lb_start_near(const int32_t* __restrict__ R, int64_t lo, int64_t hi, int64_t v) {
     int64_t step = 32, top = lo;
-    while (top + step < hi && (int64_t)rs_start(R, top + step - 1) < v) { top += step; step <<= 1; }
+    while (top + step < hi && (int64_t)__ldg(R + top + step - 1) < v) { top += step; step <<= 1; }
     return lb_start(R, top, min(hi, top + step), v);
 }
 
@@ -1379,8 +1379,8 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
             if (i < CS_HP) hp[i] = (int32_t)p;
             if (p < mid) { minA = min(minA, p); maxA = max(maxA, p + 1); }
             else { minB = min(minB, p); maxB = max(maxB, p + 1); }
-            const int64_t a = lb_start(rsum, blk_lo, blk_hi, p - maxspan + 1);
-            const int64_t b = lb_start_near(rsum, a, blk_hi, p + 1);
+            const int64_t a = lb_start(reads.start, blk_lo, blk_hi, p - maxspan + 1);
+            const int64_t b = lb_start_near(reads.start, a, blk_hi, p + 1);
             site_lo[lbase + i] = (int32_t)(a - blk_lo);
             site_n[lbase + i] = (int32_t)(b - a);
             incs += b - a;
@@ -1388,11 +1388,11 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
         minA = warp_min64(minA); maxA = warp_max64(maxA); minB = warp_min64(minB); maxB = warp_max64(maxB);
         nd[1] = warp_sum64(incs);
         __syncwarp();
-        a_lo = warp_lb_start(rsum, blk_lo, blk_hi, minA - maxspan + 1, lane);
-        a_hi = warp_lb_start(rsum, a_lo, blk_hi, maxA, lane);
+        a_lo = warp_lb_start(reads.start, blk_lo, blk_hi, minA - maxspan + 1, lane);
+        a_hi = warp_lb_start(reads.start, a_lo, blk_hi, maxA, lane);
         if (maxB > minB) {
-            b_lo = warp_lb_start(rsum, blk_lo, blk_hi, minB - maxspan + 1, lane);
-            b_hi = warp_lb_start(rsum, b_lo, blk_hi, maxB, lane);
+            b_lo = warp_lb_start(reads.start, blk_lo, blk_hi, minB - maxspan + 1, lane);
+            b_hi = warp_lb_start(reads.start, b_lo, blk_hi, maxB, lane);
             if (b_lo <= a_hi) { a_hi = max(a_hi, b_hi); a_lo = min(a_lo, b_lo); b_lo = b_hi = 0; }
         }
         nd[0] = ((a_hi - a_lo) + (b_hi - b_lo) + 3) & ~(int64_t)3;   // word-aligned label/evidence regions
@@ -1400,8 +1400,8 @@ chain_size_kernel(const UnfzDnm* __restrict__ dnms, int32_t n_dnms, const int64_
         int64_t seeds = 0, sincs = 0;
         for (int wdx = 0; wdx < (sv ? 2 : 1); ++wdx) {
             const int64_t flo = wdx ? sb_lo : sa_lo, fhi = wdx ? sb_hi : sa_hi;
-            const int64_t a = warp_lb_start(rsum, blk_lo, blk_hi, flo - maxspan + 1, lane);
-            const int64_t b = warp_lb_start(rsum, a, blk_hi, fhi, lane);
+            const int64_t a = warp_lb_start(reads.start, blk_lo, blk_hi, flo - maxspan + 1, lane);
+            const int64_t b = warp_lb_start(reads.start, a, blk_hi, fhi, lane);
             if (lane == 0) { seed_win[4 * (int64_t)d + 2 * wdx] = (int32_t)a; seed_win[4 * (int64_t)d + 2 * wdx + 1] = (int32_t)b; }
             seeds += 2 * (b - a);
             for (int64_t r = a + lane; r < b; r += 32) {

@@ -137,7 +137,7 @@ struct WpSpan {               // where the staged spans of a tile start, and whe
 
 __global__ void __launch_bounds__(WP_THREADS, WP_MINB)
 read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __restrict__ mark_prefix, ScanParams P,
-                      int qslice, UnfzReadSum* __restrict__ out, int32_t* __restrict__ row_lb,
+                      int qslice, UnfzReadSum* __restrict__ out,
                       int32_t* __restrict__ blk_maxspan, uint32_t* __restrict__ tile_tot, uint2* __restrict__ tile_info,
                       const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
@@ -417,8 +417,7 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
         if (live) {
             int4* o = reinterpret_cast<int4*>(out + r);        // the 32-byte summary as two 16-byte stores
             o[0] = make_int4(end, fmark, (int)((uint32_t)(flags & 0xffffu) | ((uint32_t)cnt << 16)), incl - cnt);
-            o[1] = make_int4(start, mate, 0, 0);
-            if (row_lb) row_lb[r] = lbs;
+            o[1] = make_int4(start, mate, lbs, 0);
         }
         __syncwarp();                                          // the slice may be refilled by the next iteration
         hAa = hBa; hAb = hBb; hBa = hCa; hBb = hCb;
@@ -454,22 +453,11 @@ __device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n
 // ------------------------------------------------------------------------------------------------
 // K3: read x marked-site allele lookup
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
-                         const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
-                         const int32_t* __restrict__ row_lb, const uint32_t* __restrict__ tile_base, int32_t tile_reads,
-                         uint32_t* __restrict__ hits, const uint2* __restrict__ tile_info, const int32_t* __restrict__ guard) {
-    UNFZ_GUARD(guard);
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= reads.n_reads) return;
-    // 8 bytes per 32 reads say who has hits at all (84 % of the reads of a 30x trio have none and their
-    // summaries are never loaded) and in which read block the tile starts
-    int rb_hint = -1;
-    if (tile_info) {
-        const uint2 ti = __ldg(tile_info + (r >> 5));
-        if (!((ti.x >> (r & 31)) & 1u)) return;
-        rb_hint = (int)ti.y;
-    }
+// the lookup of ONE read with hits: walk the site rows it spans, CIGAR walk per marked row, three bit / base gathers
+__device__ __forceinline__ void read_alleles_one(const UnfzReadCols& reads, const UnfzSiteCols& sites,
+                                                 const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
+                                                 const uint32_t* __restrict__ tile_base, int32_t tile_reads,
+                                                 uint32_t* __restrict__ hits, int64_t r, int rb_hint) {
     const UnfzReadSum s = load_rsum(rsum + r);
     if (s.cnt == 0) return;
     const UnfzRead h = load_read(reads.hdr + r);
@@ -479,7 +467,7 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
     const int sb = reads.blk_sblk[rb];
     if (sb < 0) return;
     const int64_t b = sites.blk_off[sb + 1];
-    int64_t row = __ldg(row_lb + r);                       // first site row with pos >= start (from read_scan)
+    int64_t row = s.row_lb;                                // first site row with pos >= start (from read_scan)
     const uint32_t* cg = reads.cigar + h.cigar_off;
     const int64_t q0 = read_qoff(h);
     const int64_t hbase = (int64_t)__ldg(tile_base + (uint32_t)r / (uint32_t)tile_reads) + s.hoff;
@@ -488,7 +476,7 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
         const int32_t p = __ldg(sites.pos + row);
         if (p >= s.end) break;
         const int mp0 = __ldg(mark_prefix + row);
-        if (__ldg(mark_prefix + row + 1) == mp0) continue;      // not a marked row (same sectors as mp0: no row_mark load)
+        if (__ldg(mark_prefix + row + 1) == mp0) continue;      // not a marked row
         const int k = mp0 - s.fmark;
         uint32_t word = 0;
         const int q = cigar_qpos(cg, h.n_cigar, h.start, p);
@@ -504,6 +492,55 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
     }
 }
 
+// One warp per LK_TILES consecutive 32-read tiles.  Only one read in six overlaps a marked site: a thread per read
+// leaves five lanes of six idle through a chain of dependent gathers.  Here the warp first reads the tiles' "has hits"
+// masks (8 bytes per tile, written by the scan), then deals the reads that do have hits to its lanes densely -- the
+// j-th such read of the group goes to lane j mod 32 -- so every lane of an iteration carries a gather chain.
+constexpr int LK_TILES = 8;
+
+__global__ void __launch_bounds__(256)
+read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
+                         const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
+                         const uint32_t* __restrict__ tile_base, int32_t tile_reads,
+                         uint32_t* __restrict__ hits, const uint2* __restrict__ tile_info, const int32_t* __restrict__ guard) {
+    UNFZ_GUARD(guard);
+    (void)row_mark;
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_tiles = (reads.n_reads + 31) >> 5;
+    const int64_t t0 = w * LK_TILES;
+    if (t0 >= n_tiles) return;
+    uint32_t mask = 0;
+    int rbh = -1;
+    if (lane < LK_TILES && t0 + lane < n_tiles) {
+        const uint2 ti = __ldg(tile_info + t0 + lane);
+        mask = ti.x;
+        rbh = (int)ti.y;
+        if (((t0 + lane) << 5) + 32 > reads.n_reads) mask &= (1u << (reads.n_reads - ((t0 + lane) << 5))) - 1u;   // ragged last tile
+    }
+    // exclusive prefix of the populations over the group's tiles (lanes 0..LK_TILES-1)
+    const int c = __popc(mask);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < LK_TILES; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int total = __shfl_sync(0xffffffffu, incl, LK_TILES - 1);
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const int j = j0 + lane;
+        // tile of the j-th read with hits: the first tile whose inclusive prefix exceeds j
+        int t = 0;
+#pragma unroll
+        for (int q = 0; q < LK_TILES; ++q) t += (__shfl_sync(0xffffffffu, incl, q) <= j) ? 1 : 0;
+        const int tt = min(t, LK_TILES - 1);
+        const uint32_t m = __shfl_sync(0xffffffffu, mask, tt);
+        const int before = __shfl_sync(0xffffffffu, incl - c, tt);
+        const int hint = __shfl_sync(0xffffffffu, rbh, tt);
+        if (j < total) {
+            const int bit = __fns(m, 0, j - before + 1);           // the (j - before)-th set bit of the tile's mask
+            read_alleles_one(reads, sites, mark_prefix, rsum, tile_base, tile_reads, hits, ((t0 + tt) << 5) + bit, hint);
+        }
+    }
+}
+
 }  // namespace
 
 // bytes of one quality-bit slice of the streaming kernel: 32 reads + 16-byte alignment slop on either side
@@ -514,7 +551,7 @@ extern "C" int32_t unfz_read_scan_tile_reads(int32_t max_l_seq) { (void)max_l_se
 
 extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                               const int32_t* mark_prefix, const UnfzParams* hp, int32_t max_l_seq, UnfzReadSum* out,
-                              int32_t* row_lb, int32_t* blk_maxspan, uint32_t* tile_tot, uint32_t* tile_info, void* stream) {
+                              int32_t* blk_maxspan, uint32_t* tile_tot, uint32_t* tile_info, void* stream) {
     if (reads->n_reads <= 0) return 0;
     ScanParams P;
     P.min_mapq = hp->min_map_qual;
@@ -535,7 +572,7 @@ extern "C" int unfz_read_scan(UnfzCtx* ctx, const UnfzReadCols* reads, const Unf
     int64_t g = (int64_t)ctx->sm_count * per_sm;
     if (g * WP_WARPS > tiles) g = (tiles + WP_WARPS - 1) / WP_WARPS;
     read_scan_warp_kernel<<<(unsigned)g, WP_THREADS, smem2, (cudaStream_t)stream>>>(*reads, *sites, mark_prefix, P, qslice,
-                                                                                 out, row_lb, blk_maxspan, tile_tot,
+                                                                                 out, blk_maxspan, tile_tot,
                                                                                  reinterpret_cast<uint2*>(tile_info), ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
@@ -567,6 +604,20 @@ __global__ void expand_nlist_kernel(UnfzReadCols reads, UnfzRead* __restrict__ h
 }
 }  // namespace
 
+namespace {
+__global__ void read_starts_kernel(const UnfzRead* __restrict__ hdr, int64_t n, int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = hdr[i].start;
+}
+}  // namespace
+
+extern "C" int unfz_read_starts(UnfzCtx* ctx, const UnfzReadCols* reads, int32_t* start_rw, void* stream) {
+    if (reads->n_reads <= 0) return 0;
+    read_starts_kernel<<<(unsigned)((reads->n_reads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reads->hdr, reads->n_reads, start_rw);
+    UNFZ_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" int unfz_expand_nlist(UnfzCtx* ctx, const UnfzReadCols* reads, UnfzRead* hdr_rw, uint32_t* nmask_rw,
                                  const int64_t* nidx, int64_t n_idx, void* stream) {
     if (n_idx <= 0 || reads->n_reads <= 0) return 0;
@@ -577,13 +628,16 @@ extern "C" int unfz_expand_nlist(UnfzCtx* ctx, const UnfzReadCols* reads, UnfzRe
 
 extern "C" int unfz_read_site_alleles(UnfzCtx* ctx, const UnfzReadCols* reads, const UnfzSiteCols* sites,
                                       const uint8_t* row_mark, const int32_t* mark_prefix,
-                                      const UnfzReadSum* rsum, const int32_t* row_lb, const uint32_t* tile_base,
+                                      const UnfzReadSum* rsum, const uint32_t* tile_base,
                                       int32_t tile_reads, uint32_t* hits, const uint32_t* tile_info, void* stream) {
     if (reads->n_reads <= 0) return 0;
-    const int64_t blocks = (reads->n_reads + 255) / 256;
-    read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum, row_lb,
+    if (tile_reads != 32 || tile_info == nullptr) return unfz_fail(ctx, -21, "unfz_read_site_alleles needs the tile_info of unfz_read_scan (32-read tiles)");
+    const int64_t tiles = (reads->n_reads + 31) / 32;
+    const int64_t warps = (tiles + LK_TILES - 1) / LK_TILES;
+    const int64_t blocks = (warps + 7) / 8;                 // 8 warps per CTA
+    read_site_alleles_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*reads, *sites, row_mark, mark_prefix, rsum,
                                                                                  tile_base, tile_reads, hits,
-                                                                                 tile_reads == 32 ? reinterpret_cast<const uint2*>(tile_info) : nullptr, ctx->guard);
+                                                                                 reinterpret_cast<const uint2*>(tile_info), ctx->guard);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

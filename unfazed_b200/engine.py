@@ -134,12 +134,18 @@ class DeviceReads:
         c = L.ReadCols()
         c.n_reads, c.n_blocks = table.n_reads, table.n_blocks
         c.blk_off, c.blk_sblk, c.blk_cul = self.blk_off.data_ptr(), self.blk_sblk.data_ptr(), self.blk_cul.data_ptr()
+        self.start = torch.empty((max(table.n_reads, 1),), dtype=torch.int32, device=device)
         c.hdr, c.cigar, c.seq2 = self.hdr.data_ptr(), self.cigar.data_ptr(), self.seq2.data_ptr()
+        c.start = self.start.data_ptr()
         c.lowq, c.nmask = self.lowq.data_ptr(), self.nmask.data_ptr()
         c.n_qual, c.n_cigar = nq, int(table.cigar.shape[0])
         self.cols = c
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        if engine is not None:
+            engine._check(engine.lib.unfz_read_starts(engine.ctx, C.byref(c), self.start.data_ptr(), st), "read_starts")
+        else:
+            self.start.copy_(self.hdr.view(torch.int32).view(-1, 8)[:, 0]) if table.n_reads else None
         if engine is not None and packed.nidx.shape[0]:
-            st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             engine._check(engine.lib.unfz_expand_nlist(engine.ctx, C.byref(c), self.hdr.data_ptr(), self.nmask.data_ptr(),
                                                        self.nidx.data_ptr(), int(packed.nidx.shape[0]), st), "expand_nlist")
 
@@ -280,18 +286,28 @@ class Engine:
         head = getattr(t, "head_tlen", None) or {}
         for k, kid in enumerate(t.kids):
             blocks = [b for b in range(t.n_blocks) if int(t.blk_kid[b]) == k]
-            if kid in head:                       # packed from a real file: the head of the BAM is host data
-                from .plan import concordant_upper_lens as host_cul
-                return host_cul(t, readlen, insert_size_max_sample, stdevs)
-            first, count, left = [], [], insert_size_max_sample + 1
-            for b in blocks:
-                if left <= 0:
-                    break
-                lo, hi = int(t.blk_off[b]), int(t.blk_off[b + 1])
-                take = min(left, hi - lo)
-                first.append(lo)
-                count.append(take)
-                left -= take
+            cols = dreads.cols
+            if kid in head:
+                # packed from a real file: the estimate is made over the HEAD of the BAM (read_collector.py:11-25), whose
+                # template lengths the packer kept on the host.  They go through the same device selection as a
+                # one-column stand-in of the header array (only tlen is read).
+                h = np.asarray(head[kid][: insert_size_max_sample + 1], dtype=np.int64)
+                tmp_hdr = torch.zeros((max(h.shape[0], 1), 8), dtype=torch.int32, device=dev)
+                if h.shape[0]:
+                    tmp_hdr[: h.shape[0], 1] = torch.from_numpy(h.astype(np.int32)).to(dev)
+                cols = L.ReadCols()
+                cols.n_reads, cols.n_blocks, cols.hdr = int(h.shape[0]), 0, tmp_hdr.data_ptr()
+                first, count = [0], [int(h.shape[0])]
+            else:
+                first, count, left = [], [], insert_size_max_sample + 1
+                for b in blocks:
+                    if left <= 0:
+                        break
+                    lo, hi = int(t.blk_off[b]), int(t.blk_off[b + 1])
+                    take = min(left, hi - lo)
+                    first.append(lo)
+                    count.append(take)
+                    left -= take
             n = int(sum(count))
             if n == 0:
                 continue
@@ -301,7 +317,7 @@ class Engine:
             work = torch.zeros(nwork, dtype=torch.uint8, device=dev)
             vals = torch.zeros(4, dtype=torch.int32, device=dev)
             hf, hc = np.array(first, dtype=np.int64), np.array(count, dtype=np.int64)
-            self._check(lib.unfz_insert_size_order_stats(self.ctx, C.byref(dreads.cols), hf.ctypes.data, hc.ctypes.data, len(first),
+            self._check(lib.unfz_insert_size_order_stats(self.ctx, C.byref(cols), hf.ctypes.data, hc.ctypes.data, len(first),
                                                          int(readlen), ranks.ctypes.data, work.data_ptr(), vals.data_ptr(), st),
                         "insert_size_order_stats")
             v = vals.cpu().numpy().view(np.uint32).astype(np.int64)
@@ -470,7 +486,6 @@ class Engine:
             if want_ev:
                 z1.add("ev_need", 8 * 4 * n)
             e1.add("rsum", 32 * N)
-            e1.add("row_lb", 4 * N)
             tile_reads = int(lib.unfz_read_scan_tile_reads(dreads.max_l_seq))
             n_tiles = (N + tile_reads - 1) // tile_reads
             e1.add("tile_tot", 4 * n_tiles)
@@ -565,7 +580,7 @@ class Engine:
                 for i_, v_ in enumerate(caps["chain"]):
                     b.cap_chain[i_] = int(v_)
                 b.blk_maxspan, b.need, b.off = z1.ptr["blk_maxspan"], z1.ptr["need"], z1.ptr["off"]
-                b.rsum, b.row_lb = e1.ptr["rsum"], e1.ptr["row_lb"]
+                b.rsum = e1.ptr["rsum"]
                 b.tile_tot, b.tile_base, b.tile_info = e1.ptr["tile_tot"], e1.ptr["tile_base"], e1.ptr["tile_info"]
                 b.site_lo, b.site_n, b.seed_win = e2.ptr["site_lo"], e2.ptr["site_n"], e2.ptr["seed_win"]
                 b.hits, b.scratch, b.scratch_bytes = e3.ptr["hits"], e3.ptr["scratch"], nbytes
@@ -645,7 +660,7 @@ class Engine:
                 total_hits_ptr = off_ptr + 8 * 6 * (n + 1)
                 mark("alloc2")
                 self._check(lib.unfz_read_scan(ctx, rc_, sc, z1.ptr["mark_prefix"], C.byref(params), dreads.max_l_seq, e1.ptr["rsum"],
-                                               e1.ptr["row_lb"], z1.ptr["blk_maxspan"], e1.ptr["tile_tot"], e1.ptr["tile_info"], s),
+                                               z1.ptr["blk_maxspan"], e1.ptr["tile_tot"], e1.ptr["tile_info"], s),
                             "read_scan")
                 launches += 1
                 mark("read_scan")
@@ -679,7 +694,7 @@ class Engine:
                     z3, e3, nbytes = arena3(totals, n_hits)
                 mark("alloc3")
                 self._check(lib.unfz_read_site_alleles(ctx, rc_, sc, z1.ptr["row_mark"], z1.ptr["mark_prefix"], e1.ptr["rsum"],
-                                                       e1.ptr["row_lb"], e1.ptr["tile_base"], tile_reads, e3.ptr["hits"],
+                                                       e1.ptr["tile_base"], tile_reads, e3.ptr["hits"],
                                                        e1.ptr["tile_info"], s),
                             "read_site_alleles")
                 launches += 1

@@ -202,3 +202,28 @@ def test_speculative_sizing_equals_the_exact_path_and_survives_an_overflow():
     res_exact, _ = bp.run(large, [])
     for d in range(0, len(large), 17):
         assert bp.labels(res, d) == bp.labels(res_exact, d)
+
+
+def test_phase_stream_equals_one_call_per_batch(engine):
+    """BatchPhaser.phase_stream (device work of batch k+1 queued before the records of batch k are built, host
+    columns re-uploaded for every batch) yields exactly what phase() returns for each batch, in order."""
+    from unfazed_b200.phaser import BatchPhaser
+    ds = make_dataset(SynthConfig(dnms_per_trio=90, seed=606, indel_frac=0.1, sv_frac=0.2, sv_max_len=30000, coverage=20.0))
+    batches = [ds.dnms[:30], ds.dnms[30:45], ds.dnms[45:]]
+    packed = engine.pack_reads(ds.reads, min_gt_qual=20, pin=True)
+    bp = BatchPhaser(engine, ds.sites, packed, ds.pedigrees, resident=False)
+    want = [bp.phase(copy.deepcopy(b)) for b in batches]
+    got = list(bp.phase_stream([copy.deepcopy(b) for b in batches]))
+    assert len(got) == 3 and sum(len(w) for w in want) > 10
+    for g, w in zip(got, want):
+        assert set(g) == set(w)
+        for k in w:
+            assert norm_record(g[k]) == norm_record(w[k]), k
+    # and both equal the oracle
+    ref, _ = run_port(ds)
+    merged = {}
+    for g in got:
+        merged.update(g)
+    assert set(merged) == set(ref)
+    for k in ref:
+        assert norm_record(merged[k]) == norm_record(ref[k]), k

@@ -66,3 +66,43 @@ def test_autophaseable_matches_reference():
                             autophaseable(dict(dn), peds, build)
                         continue
                     assert bool(autophaseable(dict(dn), peds, build)) == bool(want), (build, chrom, kid, start)
+
+
+def test_phase_by_reads_and_phase_by_snvs_random():
+    """The per-variant evidence functions of the drop-in phasers against the reference's (truth table
+    snv_phaser.py:52-69, CNV votes sv_phaser.py:71-85) on random matches."""
+    mods = ref_driver.modules()
+    from unfazed_b200 import snv_phaser as new_snv, sv_phaser as new_sv
+    rng = random.Random(13)
+
+    class Read:
+        def __init__(self, start, seq, gaps):
+            self.reference_start, self.query_sequence, self._gaps = start, seq, gaps
+
+        def get_reference_positions(self, full_length=False):
+            out, p = [], self.reference_start
+            for i in range(len(self.query_sequence)):
+                if i in self._gaps:
+                    out.append(None)
+                else:
+                    out.append(p)
+                    p += 1
+            return out if full_length else [x for x in out if x is not None]
+
+    for _ in range(200):
+        sites = _sites(rng, rng.randint(1, 12))
+        for s in sites:
+            s["ref_allele"], s["alt_allele"] = rng.sample("ACGT", 2)
+            s["ref_parent"], s["alt_parent"] = rng.sample(["dad", "mom"], 2)      # a trio: the two parents, either way round
+            s["kid_allele"] = rng.choice(["ref_parent", "alt_parent"])
+        matches = {}
+        for hap in rng.choice([("ref", "alt"), ("alt", "ref")]):
+            lst = []
+            for _r in range(rng.randint(0, 6)):
+                st = rng.randint(0, 2900)
+                rd = Read(st, "".join(rng.choice("ACGTN") for _ in range(120)), set(rng.sample(range(120), rng.randint(0, 6))))
+                lst.append({"read": rd, "matches": rng.sample(sites, rng.randint(0, len(sites)))})
+            matches[hap] = lst
+        for ref_mod in (mods["snv_phaser"], mods["sv_phaser"]):
+            assert new_snv.phase_by_reads(matches) == ref_mod.phase_by_reads(matches)
+        assert new_sv.phase_by_snvs(sites) == mods["sv_phaser"].phase_by_snvs(sites)

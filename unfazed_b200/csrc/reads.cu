@@ -496,7 +496,10 @@ __device__ __forceinline__ void read_alleles_one(const UnfzReadCols& reads, cons
 // leaves five lanes of six idle through a chain of dependent gathers.  Here the warp first reads the tiles' "has hits"
 // masks (8 bytes per tile, written by the scan), then deals the reads that do have hits to its lanes densely -- the
 // j-th such read of the group goes to lane j mod 32 -- so every lane of an iteration carries a gather chain.
-constexpr int LK_TILES = 8;
+#ifndef LK_TILES_N
+#define LK_TILES_N 16
+#endif
+constexpr int LK_TILES = LK_TILES_N;
 
 __global__ void __launch_bounds__(256)
 read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,

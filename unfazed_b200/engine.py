@@ -159,7 +159,8 @@ def _to_device(a: np.ndarray, device, pin: bool, pad: int = 0) -> torch.Tensor:
     """Host array -> device tensor (+ ``pad`` zero elements).  Arrays that already live in pinned
     memory are copied asynchronously; ``pin`` stages pageable arrays through a pinned copy."""
     t = torch.from_numpy(a.view(np.uint8).reshape(-1)) if a.dtype.fields is not None else torch.from_numpy(a)
-    if pin and not t.is_pinned():
+    # small pageable arrays are staged through pinned memory too: a pageable source makes the host wait for the stream
+    if not t.is_pinned() and (pin or t.numel() * t.element_size() <= (1 << 20)):
         t = t.pin_memory()
     out = torch.empty(t.shape[:-1] + (t.shape[-1] + pad,), dtype=t.dtype, device=device) if pad else torch.empty_like(t, device=device)
     if pad:
@@ -234,6 +235,21 @@ class BatchResult:
         return self._np("rsum").view(L.RSUM_DTYPE)
 
 
+class PendingBatch:
+    """A batch whose launches are on the stream but whose results have not been waited for
+    (``Engine.run(defer=True)``): ``finish()`` waits for THIS batch's download only, so the next batch's copies and
+    kernels, already queued behind it, keep the GPU busy while the host turns these results into records."""
+
+    def __init__(self, finish):
+        self._finish = finish
+
+    def finish(self) -> "BatchResult":
+        f, self._finish = self._finish, None
+        if f is None:
+            raise RuntimeError("PendingBatch.finish() called twice")
+        return f()
+
+
 class Engine:
     """One engine per (process, GPU)."""
 
@@ -251,7 +267,9 @@ class Engine:
         # everything the engine does runs on its own stream: CUDA cannot capture the legacy default stream, and the
         # batch is replayed as a CUDA graph (unfz_run_batch_graph)
         self.stream = torch.cuda.Stream(self.device)
+        self.stream2 = torch.cuda.Stream(self.device)      # late downloads of a deferred batch (see PendingBatch)
         self.use_graph = not os.environ.get("UNFZ_NO_GRAPH")
+        self._caps = None                                  # capacities seen so far (speculative sizing)
 
     def on_stream(self):
         """Context: torch's current stream is the engine's (uploads, runs, events recorded by callers)."""
@@ -350,6 +368,21 @@ class Engine:
     def pack_reads(self, table: ReadTable, min_gt_qual=20, pin: bool = True) -> PackedReads:
         return PackedReads(table, min_base_qual(min_gt_qual), pin)
 
+    def _pinned(self, a: np.ndarray) -> torch.Tensor:
+        """Small host array -> pinned staging tensor.  A copy out of PAGEABLE memory makes the host wait for everything
+        queued on the stream before it (the driver stages it in order), which would serialise a deferred batch behind
+        the previous batch's 2 GB of uploads; a pinned source keeps the call asynchronous.  The last few staging
+        buffers are kept alive until their copies are certainly done."""
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep = self.__dict__.setdefault("_staging", [])
+        keep.append(t)
+        if len(keep) > 64:
+            del keep[:32]
+        return t
+
+    def _h2d(self, a: np.ndarray) -> torch.Tensor:
+        return self._pinned(a).to(self.device, non_blocking=True)
+
     def _check(self, rc: int, what: str):
         if rc != 0:
             raise RuntimeError("%s failed (%d): %s" % (what, rc, self.lib.unfz_last_error(self.ctx).decode()))
@@ -364,22 +397,13 @@ class Engine:
         return self._empty(self.lib.unfz_scan_work_bytes(int(n)), torch.uint8)
 
     # ------------------------------------------------------------------------------------
-    def _download(self, t: torch.Tensor) -> np.ndarray:
-        """Device bytes -> host array in pinned memory (torch's caching host allocator recycles the
-        buffers; a pageable D2H copy is several times slower and serialises with the driver).  The
-        arrays of the result are views of it."""
-        buf = torch.empty((t.numel(),), dtype=torch.uint8, pin_memory=True)
-        buf.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return buf.numpy()
-
     def run(self, *args, **kw) -> BatchResult:
         with self.on_stream():
             return self._run(*args, **kw)
 
     def _run(self, dsites: DeviceSites, dreads: Optional[DeviceReads], plan: Plan, params: L.Params,
              blk_cul: Optional[np.ndarray] = None, time_stages: bool = False, download: bool = True,
-             keep_device: bool = True, speculative: bool = True, evidence: bool = False) -> BatchResult:
+             keep_device: bool = True, speculative: bool = True, evidence: bool = False, defer: bool = False):
         """One batch through the pipeline.  The sizes of the variable outputs (pairs; hits + chain
         scratch) are only known on the device.  The first batch reads them back (two host syncs); later
         batches allocate from the capacities the engine has seen (+25 %), have the device check them
@@ -441,7 +465,7 @@ class Engine:
         else:
             hp = np.concatenate([plan.dnm.view(np.uint8).reshape(-1), plan.seg.view(np.uint8).reshape(-1), plan.alleles,
                                  np.zeros(16, np.uint8)])
-            d_plan = torch.from_numpy(hp).to(dev)
+            d_plan = self._h2d(hp)
             try:
                 plan._resident = (dev, d_plan, (plan.dnm.nbytes, plan.seg.nbytes, plan.alleles.nbytes))
             except AttributeError:
@@ -551,9 +575,9 @@ class Engine:
                 if plan.rblk_sblk:
                     keys = np.fromiter(plan.rblk_sblk.keys(), dtype=np.int64, count=len(plan.rblk_sblk))
                     sb[keys] = np.fromiter(plan.rblk_sblk.values(), dtype=np.int32, count=len(plan.rblk_sblk))
-                dreads.blk_sblk.copy_(torch.from_numpy(sb))
+                dreads.blk_sblk.copy_(self._pinned(sb), non_blocking=True)
                 if blk_cul is not None:
-                    dreads.blk_cul[: blk_cul.shape[0]].copy_(torch.from_numpy(np.frombuffer(cul_bytes, dtype=np.float64).copy()))
+                    dreads.blk_cul[: blk_cul.shape[0]].copy_(self._pinned(np.frombuffer(cul_bytes, dtype=np.float64).copy()), non_blocking=True)
                 dreads._bound = bound
 
         fast = spec and not time_stages
@@ -732,74 +756,94 @@ class Engine:
         # ---- results: ONE device-to-host copy of the int32 result block ----------------------------
         if spec:
             lib.unfz_ctx_set_guard(ctx, None)
+        front_buf, done = None, None
         if download:
-            front = self._download(z1.buf[:dl_end])
-            self.last_d2h_bytes = int(dl_end)
-            item = {nm: (off, nb) for nm, off, nb in z1.items}
-            sect = lambda nm: front[item[nm][0]: item[nm][0] + item[nm][1]]
-            hr = sect("result").view(np.int32)
-            if spec:
-                g_ = sect("guard")
-                actual = g_[64: 64 + 64].view(np.int64)
-                if int(g_[:4].view(np.int32)[0]) != 0:
-                    # a capacity was exceeded: nothing was written out of bounds, run again with exact sizes
-                    self._caps = None
-                    dv.clear()
-                    return self._run(dsites, dreads, plan, params, blk_cul=blk_cul, time_stages=time_stages,
-                                    download=download, keep_device=keep_device, speculative=False, evidence=evidence)
-                h_pair_off = sect("seg_pair_off").view(np.int64)[: S + 1].copy()
-                res.seg_pair_off = h_pair_off
-                res.n_pairs = int(actual[0])
-                if has_reads:
-                    o0 = item["off"][0]
-                    res.slot_off = front[o0: o0 + 8 * (n + 1)].view(np.int64).copy()
-                    res.n_hits = int(actual[7])
-                    chain_now = [int(x) for x in actual[1:7]]
-            elif has_reads:
-                chain_now = [int(x) for x in h_off[:, n]]
-            # capacities for the next batch: what this one needed, plus a quarter
-            need_now = {"pairs": res.n_pairs, "hits": res.n_hits, "chain": chain_now if has_reads else [0] * 6}
-            grow = lambda v: int(v * 1.25) + 4096
-            if caps is None:
-                self._caps = {"pairs": grow(need_now["pairs"]), "hits": grow(need_now["hits"]),
-                              "chain": [grow(v) for v in need_now["chain"]]}
-            else:
-                caps["pairs"] = max(caps["pairs"], grow(need_now["pairs"]) if need_now["pairs"] > 0.9 * caps["pairs"] else 0)
-                caps["hits"] = max(caps["hits"], grow(need_now["hits"]) if need_now["hits"] > 0.9 * caps["hits"] else 0)
-                caps["chain"] = [max(c, grow(v) if v > 0.9 * c else 0) for c, v in zip(caps["chain"], need_now["chain"])]
-            g = lambda nm, cnt: hr[r_off[nm]: r_off[nm] + cnt]
-            res.seg_row_lo = g("seg_row_lo", S)
-            res.n_het, res.n_cand = g("n_het", n), g("n_cand", n)
-            res.cnv_dad, res.cnv_mom = g("cnv_dad", n), g("cnv_mom", n)
-            res.tally = g("tally", 8 * n).view(L.TALLY_DTYPE)
-            res.calls_strict = g("calls_s", 4 * n).view(L.CALL_DTYPE)
-            res.calls_ambiguous = g("calls_a", 4 * n).view(L.CALL_DTYPE)
-            res.win = g("win", 4 * n).reshape(4, n)
-            if want_ev:
-                # second, small download: the evidence lists, now that their lengths are on the host
-                eo = sect("ev_off").view(np.int64).reshape(4, n + 1).copy()
-                tot = [int(eo[q, n]) for q in range(4)]
-                parts = [(e3.view["ev_read_dad"], 4 * tot[0]), (e3.view["ev_read_mom"], 4 * tot[1]),
-                         (e2.view["ev_pos_dad"], 4 * tot[2]), (e2.view["ev_pos_mom"], 4 * tot[3])]
-                bufs = []
-                for t_, nb_ in parts:
-                    hb = torch.empty((max(nb_, 4),), dtype=torch.uint8, pin_memory=True)
-                    if nb_:
-                        hb[:nb_].copy_(t_[:nb_], non_blocking=True)
-                    bufs.append(hb.numpy()[:nb_].view(np.int32))
-                torch.cuda.current_stream(dev).synchronize()
-                res.ev = {"off": eo, "read_dad": bufs[0], "read_mom": bufs[1], "pos_dad": bufs[2], "pos_mom": bufs[3]}
-                self.last_d2h_bytes += 4 * sum(tot)
-        mark("download")
-        res.launches = launches
-        if time_stages:
-            torch.cuda.synchronize(dev)
-            for (n0, e0), (n1, e1_) in zip(ev[:-1], ev[1:]):
-                res.timings_ms[n1] = res.timings_ms.get(n1, 0.0) + e0.elapsed_time(e1_)
-        if not keep_device:
-            dv.clear()
-            if len(pool) > 12:
-                pool.clear()
-            for a_ in arenas:
-                pool[a_.key] = a_.buf
-        return res
+            # pinned target (torch's caching host allocator recycles the buffers; a pageable D2H copy is several times
+            # slower and serialises with the driver); the arrays of the result are views of it
+            front_buf = torch.empty((dl_end,), dtype=torch.uint8, pin_memory=True)
+            front_buf.copy_(z1.buf[:dl_end], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(st)
+
+        def finish():
+            nonlocal res
+            if download:
+                done.synchronize()
+                front = front_buf.numpy()
+                self.last_d2h_bytes = int(dl_end)
+                item = {nm: (off, nb) for nm, off, nb in z1.items}
+                sect = lambda nm: front[item[nm][0]: item[nm][0] + item[nm][1]]
+                hr = sect("result").view(np.int32)
+                if spec:
+                    g_ = sect("guard")
+                    actual = g_[64: 64 + 64].view(np.int64)
+                    if int(g_[:4].view(np.int32)[0]) != 0:
+                        # a capacity was exceeded: nothing was written out of bounds, run again with exact sizes
+                        self._caps = None
+                        dv.clear()
+                        return self.run(dsites, dreads, plan, params, blk_cul=blk_cul, time_stages=time_stages,
+                                        download=download, keep_device=keep_device, speculative=False, evidence=evidence)
+                    res.seg_pair_off = sect("seg_pair_off").view(np.int64)[: S + 1].copy()
+                    res.n_pairs = int(actual[0])
+                    if has_reads:
+                        o0 = item["off"][0]
+                        res.slot_off = front[o0: o0 + 8 * (n + 1)].view(np.int64).copy()
+                        res.n_hits = int(actual[7])
+                        chain_now = [int(x) for x in actual[1:7]]
+                elif has_reads:
+                    chain_now = [int(x) for x in h_off[:, n]]
+                # capacities for the next batch: what this one needed, plus a quarter
+                need_now = {"pairs": res.n_pairs, "hits": res.n_hits, "chain": chain_now if has_reads else [0] * 6}
+                grow = lambda v: int(v * 1.25) + 4096
+                cur = getattr(self, "_caps", None)
+                if cur is None:
+                    self._caps = {"pairs": grow(need_now["pairs"]), "hits": grow(need_now["hits"]),
+                                  "chain": [grow(v) for v in need_now["chain"]]}
+                else:
+                    cur["pairs"] = max(cur["pairs"], grow(need_now["pairs"]) if need_now["pairs"] > 0.9 * cur["pairs"] else 0)
+                    cur["hits"] = max(cur["hits"], grow(need_now["hits"]) if need_now["hits"] > 0.9 * cur["hits"] else 0)
+                    cur["chain"] = [max(c, grow(v) if v > 0.9 * c else 0) for c, v in zip(cur["chain"], need_now["chain"])]
+                g = lambda nm, cnt: hr[r_off[nm]: r_off[nm] + cnt]
+                res.seg_row_lo = g("seg_row_lo", S)
+                res.n_het, res.n_cand = g("n_het", n), g("n_cand", n)
+                res.cnv_dad, res.cnv_mom = g("cnv_dad", n), g("cnv_mom", n)
+                res.tally = g("tally", 8 * n).view(L.TALLY_DTYPE)
+                res.calls_strict = g("calls_s", 4 * n).view(L.CALL_DTYPE)
+                res.calls_ambiguous = g("calls_a", 4 * n).view(L.CALL_DTYPE)
+                res.win = g("win", 4 * n).reshape(4, n)
+                if want_ev:
+                    # second, small download: the evidence lists, now that their lengths are on the host.  It goes over
+                    # the side stream: behind a deferred batch the main stream may already hold the next batch's copies
+                    eo = sect("ev_off").view(np.int64).reshape(4, n + 1).copy()
+                    tot = [int(eo[q, n]) for q in range(4)]
+                    parts = [(e3.view["ev_read_dad"], 4 * tot[0]), (e3.view["ev_read_mom"], 4 * tot[1]),
+                             (e2.view["ev_pos_dad"], 4 * tot[2]), (e2.view["ev_pos_mom"], 4 * tot[3])]
+                    bufs = []
+                    with torch.cuda.stream(self.stream2):
+                        for t_, nb_ in parts:
+                            hb = torch.empty((max(nb_, 4),), dtype=torch.uint8, pin_memory=True)
+                            if nb_:
+                                hb[:nb_].copy_(t_[:nb_], non_blocking=True)
+                            bufs.append(hb.numpy()[:nb_].view(np.int32))
+                    self.stream2.synchronize()
+                    res.ev = {"off": eo, "read_dad": bufs[0], "read_mom": bufs[1], "pos_dad": bufs[2], "pos_mom": bufs[3]}
+                    self.last_d2h_bytes += 4 * sum(tot)
+            mark("download")
+            res.launches = launches
+            if time_stages:
+                torch.cuda.synchronize(dev)
+                for (n0, e0), (n1, e1_) in zip(ev[:-1], ev[1:]):
+                    res.timings_ms[n1] = res.timings_ms.get(n1, 0.0) + e0.elapsed_time(e1_)
+            if not keep_device:
+                dv.clear()
+                if len(pool) > 12:
+                    pool.clear()
+                for a_ in arenas:
+                    pool[a_.key] = a_.buf
+            return res
+
+        if defer:
+            if time_stages or not download:
+                raise ValueError("defer=True needs download=True and no stage timers")
+            return PendingBatch(finish)
+        return finish()

@@ -129,8 +129,9 @@ class BatchPhaser:
             multiread_proc_min=1000, ab_homref=(0.0, 0.2), ab_homalt=(0.8, 1.0), ab_het=(0.2, 0.8),
             min_gt_qual=20, min_depth=10, search_dist=5000, insert_size_max_sample=1000000, stdevs=3,
             min_map_qual=1, readlen=151, split_error_margin=5, evidence_min_ratio=10,
-            time_stages=False, evidence=True):
-        """Plan + run all entries of one call.  Returns (result, layout)."""
+            time_stages=False, evidence=True, keep_device=True, defer=False):
+        """Plan + run all entries of one call.  Returns (result, layout); with ``defer`` the first element is an
+        engine.PendingBatch whose ``finish()`` gives the result (see ``phase_stream``)."""
         import time as _t
         t0 = _t.perf_counter()
         if not self.resident:
@@ -147,7 +148,7 @@ class BatchPhaser:
         dreads = self.dreads_for(min_gt_qual)
         res = self.engine.run(self.dsites, dreads, plan, params,
                               blk_cul=self.cul(readlen, insert_size_max_sample, stdevs), time_stages=time_stages,
-                              evidence=evidence)
+                              evidence=evidence, keep_device=keep_device, defer=defer)
         t3 = _t.perf_counter()
         if not self.resident:
             self.release_device()
@@ -238,32 +239,36 @@ class BatchPhaser:
             nm_d, nm_m = self.reads.names_of(ev["read_dad"]), self.reads.names_of(ev["read_mom"])
             sp_d, sp_m = list(map(str, ev["pos_dad"].tolist())), list(map(str, ev["pos_mom"].tolist()))
             o_rd, o_rm, o_sd, o_sm = (ev["off"][q].tolist() for q in range(4))
-        flags = plan.dnm["flags"].tolist()
-        has = res.tally["has_record"].tolist() if res.tally is not None else None
+        flags_a = plan.dnm["flags"]
+        has_a = res.tally["has_record"] if res.tally is not None else np.zeros(len(flags_a), dtype=np.int32)
         ped = self.ped
+        entries = plan.entries
         for name, out in (("sv_read", out_sv), ("snv", out_snv)):
             a, b = layout[name]
-            for d in range(a, b):
-                dn = plan.entries[d]
-                if flags[d] & L.DNM_AUTOPHASE:
-                    out[dnm_key(dn)] = self._auto_record(dn, ped[dn["kid"]]["dad"], ped[dn["kid"]]["mom"])
-                    continue
-                if has is None or not has[d]:
-                    continue
-                if ev is None:
-                    out[dnm_key(dn)] = self._read_record(res, d, dn)
-                    continue
+            # only the entries that get a record are visited (in entry order): autophased ones and those with matches
+            live = a + np.flatnonzero(((flags_a[a:b] & L.DNM_AUTOPHASE) != 0) | (has_a[a:b] != 0))
+            auto = (flags_a[live] & L.DNM_AUTOPHASE) != 0
+            for d, is_auto in zip(live.tolist(), auto.tolist()):
+                dn = entries[d]
                 kid = dn["kid"]
-                # one pair = one window slot = one name, so the read lists are unique as they come (slot order); a site
-                # seen through two overlapping windows (Q9) appears twice, the reference keeps a set of str(pos)
-                out[dnm_key(dn)] = {
-                    "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
-                    "vartype": dn["vartype"], "kid": kid, "dad": ped[kid]["dad"], "mom": ped[kid]["mom"],
-                    "dad_sites": sorted(set(sp_d[o_sd[d]:o_sd[d + 1]])),
-                    "mom_sites": sorted(set(sp_m[o_sm[d]:o_sm[d + 1]])), "evidence_type": "readbacked",
-                    "dad_reads": nm_d[o_rd[d]:o_rd[d + 1]], "mom_reads": nm_m[o_rm[d]:o_rm[d + 1]],
-                    "cnv_dad_sites": "", "cnv_mom_sites": "", "cnv_evidence_type": "",
-                }
+                p = ped[kid]
+                key = "_".join([str(dn["chrom"]), str(dn["start"]), str(dn["end"]), kid, dn["vartype"]])      # dnm_key
+                if is_auto:
+                    out[key] = self._auto_record(dn, p["dad"], p["mom"])
+                elif ev is None:
+                    out[key] = self._read_record(res, d, dn)
+                else:
+                    # one pair = one window slot = one name, so the read lists are unique as they come (slot order); a
+                    # site seen through two overlapping windows (Q9) appears twice, the reference keeps a set of str(pos)
+                    sd, sm = sp_d[o_sd[d]:o_sd[d + 1]], sp_m[o_sm[d]:o_sm[d + 1]]
+                    out[key] = {
+                        "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
+                        "vartype": dn["vartype"], "kid": kid, "dad": p["dad"], "mom": p["mom"],
+                        "dad_sites": sorted(set(sd)) if len(sd) > 1 else sd,
+                        "mom_sites": sorted(set(sm)) if len(sm) > 1 else sm, "evidence_type": "readbacked",
+                        "dad_reads": nm_d[o_rd[d]:o_rd[d + 1]], "mom_reads": nm_m[o_rm[d]:o_rm[d + 1]],
+                        "cnv_dad_sites": "", "cnv_mom_sites": "", "cnv_evidence_type": "",
+                    }
         for k, c in cnv.items():                                  # sv_phaser.py:484-492
             if k not in out_sv:
                 out_sv[k] = c
@@ -281,13 +286,43 @@ class BatchPhaser:
         xs = np.nonzero(lab)[0]
         return {self.reads.name_of(int(r)): names[int(lab[x])] for x, r in zip(xs, res.slot_reads(d, xs))}
 
-    def phase(self, dnms: List[dict], **params) -> Dict[str, dict]:
+    def _split(self, dnms: List[dict]):
         kids = set(self.ped)
         svs = [d for d in dnms if d["vartype"].upper() in SV_TYPES and d["kid"] in kids]
         snvs = [d for d in dnms if d["vartype"].upper() in SNV_TYPES and d["kid"] in kids]
+        return snvs, svs
+
+    def phase(self, dnms: List[dict], **params) -> Dict[str, dict]:
         import time as _t
-        res, layout = self.run(snvs, svs, **params)
+        snvs, svs = self._split(dnms)
+        # the CNV votes of SVs are read from the device lists while the records are built; otherwise nothing has to
+        # stay on the device and the engine recycles its buffers (and replays the batch as a CUDA graph)
+        res, layout = self.run(snvs, svs, keep_device=bool(svs), **params)
         t0 = _t.perf_counter()
         out = self.records(res, layout)
         self.last_timing["records_ms"] = (_t.perf_counter() - t0) * 1e3
         return out
+
+    def phase_stream(self, batches, **params):
+        """Phase a sequence of DNM lists, yielding one record dict per list, in order.  Software pipeline of depth two:
+        the copies and kernels of list k+1 are put on the stream BEFORE the host waits for list k and turns its
+        results into record dicts, so host work (about half of an end-to-end step) and PCIe/GPU work overlap."""
+        import time as _t
+        pending = None
+
+        def finish(p):
+            t0 = _t.perf_counter()
+            res = p[0].finish()
+            t1 = _t.perf_counter()
+            out = self.records(res, p[1])
+            self.last_timing.update(wait_results_ms=(t1 - t0) * 1e3, records_ms=(_t.perf_counter() - t1) * 1e3)
+            return out
+
+        for dnms in batches:
+            snvs, svs = self._split(dnms)
+            h, layout = self.run(snvs, svs, keep_device=bool(svs), defer=True, **params)
+            if pending is not None:
+                yield finish(pending)
+            pending = (h, layout)
+        if pending is not None:
+            yield finish(pending)

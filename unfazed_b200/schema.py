@@ -193,15 +193,24 @@ class ReadTable:
         m = int(self.hdr["mate"][r])
         return "q%d" % (min(r, m) if m >= 0 else r)
 
+    def pair_ids(self) -> np.ndarray:
+        """Dense per-read id of its pair (the lower index of the two mates): what a synthesized read name is made of.
+        Cached; a table packed from a BAM carries ``names`` instead."""
+        p = self.__dict__.get("_pair_ids")
+        if p is None or p.shape[0] != self.n_reads:
+            m = self.hdr["mate"].astype(np.int64)
+            r = np.arange(self.n_reads, dtype=np.int64)
+            p = np.where(m >= 0, np.minimum(r, m), r)
+            self.__dict__["_pair_ids"] = p
+        return p
+
     def names_of(self, idx: np.ndarray) -> List[str]:
         """query_name of many reads at once (both mates of a pair share it)."""
         idx = np.asarray(idx, dtype=np.int64)
         if self.names is not None:
             nm = self.names
             return [nm[i] for i in idx.tolist()]
-        m = self.hdr["mate"][idx].astype(np.int64)
-        ids = np.where(m >= 0, np.minimum(idx, m), idx)
-        return ["q%d" % i for i in ids.tolist()]
+        return ["q%d" % i for i in self.pair_ids()[idx].tolist()]
 
     def lowq_plane(self, min_bq: int, chunk: int = 1 << 26) -> np.ndarray:
         """One bit per query base, bit i&7 of byte i>>3: ``(qual & 0x7f) < min_bq``.  This is what the

@@ -18,6 +18,35 @@ def _say(msg):
         print(msg, file=sys.stderr)
 
 
+def phase_by_reads(matches):
+    """Per-variant interface of the reference (``snv_phaser.py:16-70``, repeated at ``sv_phaser.py:14-68``) for callers
+    that hold ``match_informative_sites`` output: every (read, matched site) whose base at the site is the site's REF
+    or ALT allele becomes an evidence item ``[read, pos]``, credited to the site's alt_parent when the read's origin
+    (REF base -> ref_parent) and its haplotype relative to the DNM agree in being "ref", else to ref_parent (truth
+    table :52-69).  The batched path does this in ``chain_evidence_kernel``; this is the host mirror."""
+    credit = {}
+    for hap, infos in matches.items():
+        for info in infos:
+            read = info["read"]
+            for site in info["matches"]:
+                if not credit:
+                    credit[site["ref_parent"]] = []
+                    credit[site["alt_parent"]] = []
+                positions = read.get_reference_positions(full_length=True)
+                if site["pos"] not in positions:
+                    continue
+                base = read.query_sequence[positions.index(site["pos"])]
+                if base == site["ref_allele"]:
+                    from_ref_parent = True
+                elif base == site["alt_allele"]:
+                    from_ref_parent = False
+                else:
+                    continue
+                side = "alt_parent" if from_ref_parent == (hap == "ref") else "ref_parent"
+                credit[site[side]].append([read, site["pos"]])
+    return credit
+
+
 def run_batch(snvs, svs, pedigrees, sites, threads, build, no_extended, multiread_proc_min, ab_homref, ab_homalt,
               ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample, stdevs, min_map_qual, readlen,
               split_error_margin):

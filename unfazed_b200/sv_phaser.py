@@ -5,7 +5,19 @@ allele-balance phasing over the sites inside DEL/DUP events (``run_cnv_phasing``
 from __future__ import annotations
 
 from . import snv_phaser
+from .snv_phaser import phase_by_reads  # noqa: F401  (sv_phaser.py:14-68 is the same function)
 
+
+def phase_by_snvs(informative_sites):
+    """``sv_phaser.py:71-85``: every CNV candidate site votes for ``site[site["kid_allele"]]``; returns
+    ``{parent: [site, ...]}`` keyed by the parents of the FIRST site, or None without sites.  Host mirror of the
+    vote count ``unfz_compact_sites`` keeps per DNM."""
+    if not informative_sites:
+        return None
+    votes = {informative_sites[0]["ref_parent"]: [], informative_sites[0]["alt_parent"]: []}
+    for site in informative_sites:
+        votes[site[site["kid_allele"]]].append(site)
+    return votes
 
 def phase_svs(dnms, kids, pedigrees, sites, threads, build, no_extended, multiread_proc_min, quiet_mode,
               ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample,

@@ -378,6 +378,7 @@ class Bam:
         self.start = h["start"]
         self.end = reads.ref_ends()
         self._cache: Dict[int, tuple] = {}
+        self._max_span: Dict[int, int] = {}
 
     def all_reads(self):
         t = self.t
@@ -386,6 +387,9 @@ class Bam:
                 yield from range(int(t.blk_off[b]), int(t.blk_off[b + 1]))
 
     def fetch(self, contig: str, start, stop) -> List[int]:
+        """pysam fetch(contig, start, stop): reads overlapping the 0-based half-open interval, in file order.  Like
+        an indexed BAM it does not walk the contig from its beginning: no read is longer than the longest span
+        of its block, so the candidates start in [start - max_span, stop)."""
         t = self.t
         if contig not in t.contigs:
             raise ValueError(contig)
@@ -394,9 +398,13 @@ class Bam:
         if b < 0:
             return []
         lo, hi = int(t.blk_off[b]), int(t.blk_off[b + 1])
+        span = self._max_span.get(b)
+        if span is None:
+            span = self._max_span[b] = int((self.end[lo:hi] - self.start[lo:hi]).max()) if hi > lo else 0
+        j0 = int(np.searchsorted(self.start[lo:hi], start - span, side="left"))
         j1 = int(np.searchsorted(self.start[lo:hi], stop, side="left"))
-        sel = np.nonzero(self.end[lo:lo + j1] > start)[0]
-        return [lo + int(i) for i in sel]
+        sel = np.nonzero(self.end[lo + j0:lo + j1] > start)[0]
+        return [lo + j0 + int(i) for i in sel]
 
     def mate(self, r: int) -> int:
         h = self.t.hdr[r]

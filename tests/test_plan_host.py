@@ -19,12 +19,13 @@ CFGS = [
 
 
 @pytest.mark.parametrize("cfg", CFGS, ids=[str(c.seed) for c in CFGS])
-@pytest.mark.parametrize("whole_region", [False, True])
-def test_fast_planner_equals_generic(cfg, whole_region):
+@pytest.mark.parametrize("whole_region,mpm", [(False, 10 ** 9), (True, 10 ** 9), (False, 1), (True, 1)],
+                         ids=["reads", "cnv", "reads_many", "cnv_many"])
+def test_fast_planner_equals_generic(cfg, whole_region, mpm):
     ds = make_dataset(cfg)
     sidx = SiteIndex(ds.sites)
-    kw = dict(search_dist=0 if whole_region else 5000, whole_region=whole_region, build="38", multiread_proc_min=10 ** 9,
-              threads=1, with_reads=not whole_region, first_entry=7, alleles_base=11, sv_quirk=not whole_region)
+    kw = dict(search_dist=0 if whole_region else 5000, whole_region=whole_region, build="38", multiread_proc_min=mpm,
+              threads=2, with_reads=not whole_region, first_entry=7, alleles_base=11, sv_quirk=not whole_region)
     a = plan_find(ds.dnms, ds.pedigrees, sidx, ds.reads, **kw)
     b = plan_find_fast(ds.dnms, ds.pedigrees, sidx, ds.reads, **kw)
     assert np.array_equal(a.seg, b.seg)

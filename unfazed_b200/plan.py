@@ -279,11 +279,14 @@ def plan_find(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Optiona
 def plan_find_fast(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Optional[ReadTable], *,
                    search_dist: int, whole_region: bool, build: str, multiread_proc_min: int, threads: int,
                    with_reads: bool, first_entry: int = 0, alleles_base: int = 0, sv_quirk: bool = False) -> Plan:
-    """Vectorised ``plan_find`` for the per-DNM ``find`` path (len(dnms) < multiread_proc_min):
-    identical output, numpy instead of a Python loop per DNM (the planner would otherwise dominate
-    the end-to-end time of a 10 k-DNM batch).  ``find_many`` batches use the generic planner."""
+    """Vectorised ``plan_find`` for the per-DNM ``find`` path (len(dnms) < multiread_proc_min) and for
+    ``find_many`` in read mode (whole_region=False: one window per DNM around its start, repeated once per
+    DNM location of the kid that coincides with it, :392-395,:412-419,:451-452): identical output, numpy
+    instead of a Python loop per DNM (the planner would otherwise dominate the end-to-end time of a
+    10 k-DNM batch).  ``find_many`` in CNV mode (Q12's KeyError logic) uses the generic planner."""
     n = len(dnms)
-    if n >= multiread_proc_min or n == 0:
+    use_many = n >= multiread_proc_min
+    if (use_many and whole_region) or n == 0:
         return plan_find(dnms, pedigrees, sidx, reads, search_dist=search_dist, whole_region=whole_region, build=build,
                          multiread_proc_min=multiread_proc_min, threads=threads, with_reads=with_reads,
                          first_entry=first_entry, alleles_base=alleles_base, sv_quirk=sv_quirk)
@@ -353,8 +356,27 @@ def plan_find_fast(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Op
     ex_lo = np.where(small, start, 0)
     ex_hi = np.where(small, end, 0)
     single = whole_region | ((end - start) <= sd)
-    nseg = np.where(found, np.where(single, 1, 0), 0).astype(np.int64)
-    multi_idx = np.nonzero(found & ~single)[0]
+    has_win = found
+    mult1 = np.ones(n, dtype=np.int64)
+    if use_many:
+        # find_many: only the start window; the VCF's contig name must equal the DNM's spelling (Q11); a site is appended
+        # once per occurrence of the kid in the location list of the DNM's start -- DNM starts, and ends of events
+        # longer than 2 bp (:392-395) -- of every non-autophased DNM
+        from collections import Counter
+        single = np.ones(n, dtype=bool)
+        g_same = np.array([g_contig[g] == groups[g][1] for g in range(G)], dtype=bool)
+        has_win = found & g_same[gids]
+        cnt = Counter()
+        for g, s_, e_, a_ in zip(gids.tolist(), start.tolist(), end.tolist(), auto.tolist()):
+            if a_:
+                continue
+            cnt[(g, s_)] += 1
+            if e_ - s_ > 2:
+                cnt[(g, e_)] += 1
+        mult1 = np.fromiter((cnt[(g, s_)] for g, s_ in zip(gids.tolist(), start.tolist())), dtype=np.int64, count=n)
+        has_win &= mult1 > 0
+    nseg = np.where(has_win, np.where(single, 1, 0), 0).astype(np.int64)
+    multi_idx = np.nonzero(has_win & ~single)[0]
     multi_wins = {}
     for i in multi_idx:
         w = [x for x in _find_windows(dnms[i], sd, whole_region) if x[1] >= x[0] and x[2] > 0]
@@ -365,12 +387,12 @@ def plan_find_fast(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Op
     dnm["seg_hi"] = seg_lo_idx + nseg
     S = int(nseg.sum())
     seg = np.zeros(S, dtype=L.SEG_DTYPE)
-    one = np.nonzero(found & single)[0]
+    one = np.nonzero(has_win & single)[0]
     at = seg_lo_idx[one]
     seg["sblk"][at] = g_sblk[gids[one]]
     seg["lo_pos"][at] = start[one] - sd - 1
     seg["hi_pos"][at] = (end[one] if whole_region else start[one]) + sd - 1
-    seg["mult"][at] = 1
+    seg["mult"][at] = mult1[one]
     seg["dnm"][at] = first_entry + one
     seg["excl_lo"][at], seg["excl_hi"][at], seg["mode"][at] = ex_lo[one], ex_hi[one], mode[one]
     for i, wins in multi_wins.items():

@@ -12,6 +12,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import _lib as L
+from . import _records            # csrc/records.c, built in-tree by csrc/Makefile (no Python fallback)
 from .engine import BatchResult, DeviceReads, DeviceSites, Engine, PackedReads, make_params
 from .plan import (SNV_TYPES, SV_TYPES, Plan, SiteIndex, concat_plans, concordant_upper_lens,
                    plan_find_fast)
@@ -190,6 +191,18 @@ class BatchPhaser:
 
     def records(self, res: BatchResult, layout) -> Dict[str, dict]:
         """The dict ``phase_snvs``/``phase_svs`` return, merged as unfazed.py:648-649 does."""
+        # tens of thousands of small containers are created below; a cyclic-GC pass in the middle only costs time
+        # (nothing here can form a cycle), so the collector is paused for the duration of the call
+        import gc
+        was_on = gc.isenabled()
+        gc.disable()
+        try:
+            return self._records(res, layout)
+        finally:
+            if was_on:
+                gc.enable()
+
+    def _records(self, res: BatchResult, layout) -> Dict[str, dict]:
         plan = res.plan
         out_sv: Dict[str, dict] = {}
         out_snv: Dict[str, dict] = {}
@@ -233,12 +246,6 @@ class BatchPhaser:
                     "dad_sites": "", "mom_sites": "", "evidence_type": "", "dad_reads": [], "mom_reads": [],
                 }
         ev = res.ev
-        if ev is not None:
-            # evidence lists compacted per DNM and per parent on the device: every string of the batch is made in
-            # four flat passes, a record is then slices of those lists (no per-read work in the loop below)
-            nm_d, nm_m = self.reads.names_of(ev["read_dad"]), self.reads.names_of(ev["read_mom"])
-            sp_d, sp_m = list(map(str, ev["pos_dad"].tolist())), list(map(str, ev["pos_mom"].tolist()))
-            o_rd, o_rm, o_sd, o_sm = (ev["off"][q].tolist() for q in range(4))
         flags_a = plan.dnm["flags"]
         has_a = res.tally["has_record"] if res.tally is not None else np.zeros(len(flags_a), dtype=np.int32)
         ped = self.ped
@@ -248,27 +255,24 @@ class BatchPhaser:
             # only the entries that get a record are visited (in entry order): autophased ones and those with matches
             live = a + np.flatnonzero(((flags_a[a:b] & L.DNM_AUTOPHASE) != 0) | (has_a[a:b] != 0))
             auto = (flags_a[live] & L.DNM_AUTOPHASE) != 0
+            if ev is not None:
+                # evidence lists compacted per DNM and per parent on the device (evidence_lists_kernel): the native builder
+                # (csrc/records.c) cuts every record out of the four flat lists.  One pair = one window slot = one name, so
+                # the read lists are unique as they come (slot order); a site seen through two overlapping windows (Q9)
+                # appears twice, the reference keeps a set of str(pos) -> sorted(set(...)) there too
+                names = self.reads.names
+                if names is not None and not isinstance(names, list):
+                    names = self.reads.names = list(names)
+                _records.read_records(out, entries, ped, np.ascontiguousarray(live, dtype=np.int64),
+                                      np.ascontiguousarray(auto, dtype=np.uint8), names,
+                                      None if names is not None else np.ascontiguousarray(self.reads.pair_ids(), dtype=np.int64),
+                                      ev["read_dad"], ev["read_mom"], ev["pos_dad"], ev["pos_mom"],
+                                      np.ascontiguousarray(ev["off"], dtype=np.int64))
+                continue
             for d, is_auto in zip(live.tolist(), auto.tolist()):
                 dn = entries[d]
-                kid = dn["kid"]
-                p = ped[kid]
-                key = "_".join([str(dn["chrom"]), str(dn["start"]), str(dn["end"]), kid, dn["vartype"]])      # dnm_key
-                if is_auto:
-                    out[key] = self._auto_record(dn, p["dad"], p["mom"])
-                elif ev is None:
-                    out[key] = self._read_record(res, d, dn)
-                else:
-                    # one pair = one window slot = one name, so the read lists are unique as they come (slot order); a
-                    # site seen through two overlapping windows (Q9) appears twice, the reference keeps a set of str(pos)
-                    sd, sm = sp_d[o_sd[d]:o_sd[d + 1]], sp_m[o_sm[d]:o_sm[d + 1]]
-                    out[key] = {
-                        "region": {"chrom": dn["chrom"], "start": dn["start"], "end": dn["end"]},
-                        "vartype": dn["vartype"], "kid": kid, "dad": p["dad"], "mom": p["mom"],
-                        "dad_sites": sorted(set(sd)) if len(sd) > 1 else sd,
-                        "mom_sites": sorted(set(sm)) if len(sm) > 1 else sm, "evidence_type": "readbacked",
-                        "dad_reads": nm_d[o_rd[d]:o_rd[d + 1]], "mom_reads": nm_m[o_rm[d]:o_rm[d + 1]],
-                        "cnv_dad_sites": "", "cnv_mom_sites": "", "cnv_evidence_type": "",
-                    }
+                p = ped[dn["kid"]]
+                out[dnm_key(dn)] = self._auto_record(dn, p["dad"], p["mom"]) if is_auto else self._read_record(res, d, dn)
         for k, c in cnv.items():                                  # sv_phaser.py:484-492
             if k not in out_sv:
                 out_sv[k] = c

@@ -429,6 +429,8 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
     bpe._cul_cache[(151, 1000000, 3)] = cul
     phase_kw = dict(threads=1, build=runkw.get("build", "38"), multiread_proc_min=runkw["multiread_proc_min"],
                     search_dist=runkw["search_dist"], readlen=151)
+    if cohort and world > 1:
+        phase_kw["compact"] = True        # a rank ships arrays; rank 0 builds every record dict (as the CLI's multi-GPU path)
     h2d_bytes = h2d_sites + host_reads.nbytes + plan.dnm.nbytes + plan.seg.nbytes + plan.alleles.nbytes
     d2h = {"bytes": 0}
 
@@ -440,11 +442,18 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
         if cohort and world > 1:
             t_g = time.perf_counter()
             gathered = [None] * world if rank == 0 else None
-            dist.gather_object(recs, gathered, dst=0)
+            dist.gather_object(recs, gathered, dst=0)            # CompactRecords (arrays) from every rank
+            n_out = 0
+            if rank == 0:
+                from unfazed_b200.shard import merge_part
+                merged = {}
+                for g in gathered:
+                    merge_part(merged, g)                        # ... become the record dicts here (native builder)
+                n_out = len(merged)
             gather["ms"] += (time.perf_counter() - t_g) * 1e3
             gather["n"] += 1
             if rank == 0:
-                return sum(len(g) for g in gathered)
+                return n_out
         return len(recs)
 
     # (1) one call per batch, nothing overlapped: BatchPhaser.phase(dnms)

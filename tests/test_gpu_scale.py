@@ -227,3 +227,25 @@ def test_phase_stream_equals_one_call_per_batch(engine):
     assert set(merged) == set(ref)
     for k in ref:
         assert norm_record(merged[k]) == norm_record(ref[k]), k
+
+
+def test_compact_records_equal_the_record_dicts(engine):
+    """BatchPhaser.phase(compact=True) (what a rank ships to rank 0 in a multi-GPU run) survives a pickle round trip and
+    ``to_records()`` gives exactly the dict ``phase()`` returns, autophased entries included; a batch with SVs falls
+    back to the dict itself."""
+    import pickle
+    from unfazed_b200.phaser import BatchPhaser, CompactRecords
+    cfg = SynthConfig(n_trios=6, dnms_per_trio=12, seed=411, sex_chrom_frac=0.3, male_frac=0.5, coverage=16.0, indel_frac=0.2)
+    ds = make_dataset(cfg)
+    bp = BatchPhaser(engine, ds.sites, ds.reads, ds.pedigrees)
+    want = bp.phase(copy.deepcopy(ds.dnms), build="38")
+    c = bp.phase(copy.deepcopy(ds.dnms), build="38", compact=True)
+    assert isinstance(c, CompactRecords) and len(c) == len(want) > 10
+    assert any(r["evidence_type"] == "SEX-CHROM" for r in want.values())
+    got = pickle.loads(pickle.dumps(c)).to_records()
+    assert got == want and list(got) == list(want)
+    for got_s in bp.phase_stream([copy.deepcopy(ds.dnms)] * 2, build="38", compact=True):
+        assert got_s.to_records() == want
+    ds2 = make_dataset(SynthConfig(dnms_per_trio=20, seed=412, sv_frac=0.5, sv_max_len=20000, coverage=16.0))
+    bp2 = BatchPhaser(engine, ds2.sites, ds2.reads, ds2.pedigrees)
+    assert isinstance(bp2.phase(copy.deepcopy(ds2.dnms), compact=True), dict)

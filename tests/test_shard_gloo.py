@@ -73,7 +73,31 @@ def test_cross_kid_coupling_detector():
     assert not cross_kid_coupling([sv("k1", "1", 100, 500), sv("k1", "1", 500, 502), sv("k2", "1", 900, 902)], ped, "38", 2)
 
 
-def _worker(rank, world, port_no, out_path, n_trios, per_trio):
+def _compact_from_records(recs):
+    """Test helper: finished read-backed records -> phaser.CompactRecords (what a GPU rank ships to rank 0)."""
+    import numpy as np
+    from unfazed_b200.phaser import CompactRecords
+    entries, auto, names_d, names_m, pd, pm = [], [], [], [], [], []
+    off = [[0], [0], [0], [0]]
+    ped = {}
+    for r in recs.values():
+        entries.append({"chrom": r["region"]["chrom"], "start": r["region"]["start"], "end": r["region"]["end"], "kid": r["kid"],
+                        "vartype": r["vartype"]})
+        ped[r["kid"]] = {"dad": r["dad"], "mom": r["mom"]}
+        is_auto = r["evidence_type"] == "SEX-CHROM"
+        auto.append(1 if is_auto else 0)
+        if not is_auto:
+            names_d += r["dad_reads"]
+            names_m += r["mom_reads"]
+            pd += [int(x) for x in r["dad_sites"]]
+            pm += [int(x) for x in r["mom_sites"]]
+        for q, lst in enumerate((names_d, names_m, pd, pm)):
+            off[q].append(len(lst))
+    return CompactRecords(entries, ped, np.array(auto, dtype=np.uint8), names_d + names_m, None, len(names_d),
+                          np.array(pd, dtype=np.int32), np.array(pm, dtype=np.int32), np.array(off, dtype=np.int64))
+
+
+def _worker(rank, world, port_no, out_path, n_trios, per_trio, compact_rank=-1):
     import pickle
     import torch.distributed as dist
     from oracle import port
@@ -85,7 +109,8 @@ def _worker(rank, world, port_no, out_path, n_trios, per_trio):
 
     def phase_fn(dnms):
         ph = port.Phaser(ds.sites, ds.reads, ds.pedigrees, port.Params())
-        return ph.phase(copy.deepcopy(dnms))
+        recs = ph.phase(copy.deepcopy(dnms))
+        return _compact_from_records(recs) if rank == compact_rank else recs
 
     if n_trios == 1:                            # the family is split: both ranks must get work
         from unfazed_b200.shard import shard_dnms as _sd
@@ -100,8 +125,9 @@ def _worker(rank, world, port_no, out_path, n_trios, per_trio):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_trios,per_trio", [(3, 4), (1, 10)])
-def test_sharded_equals_single_process(tmp_path, n_trios, per_trio):
+@pytest.mark.parametrize("n_trios,per_trio,compact_rank", [(3, 4, -1), (1, 10, -1), (3, 4, 1), (3, 4, 0)],
+                         ids=["kids", "slices", "compact_from_rank1", "compact_from_rank0"])
+def test_sharded_equals_single_process(tmp_path, n_trios, per_trio, compact_rank):
     import pickle
     from oracle import port
     s = socket.socket()
@@ -109,7 +135,7 @@ def test_sharded_equals_single_process(tmp_path, n_trios, per_trio):
     port_no = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "recs.pkl")
-    mp.spawn(_worker, args=(2, port_no, out, n_trios, per_trio), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port_no, out, n_trios, per_trio, compact_rank), nprocs=2, join=True)
     got = pickle.load(open(out, "rb"))
     ds = make_dataset(SynthConfig(n_trios=n_trios, dnms_per_trio=per_trio, seed=77, coverage=16.0))
     want = port.Phaser(ds.sites, ds.reads, ds.pedigrees, port.Params()).phase(copy.deepcopy(ds.dnms))
@@ -117,3 +143,5 @@ def test_sharded_equals_single_process(tmp_path, n_trios, per_trio):
     for k in want:
         for f in ("dad_sites", "mom_sites", "dad_reads", "mom_reads"):
             assert sorted(got[k][f]) == sorted(want[k][f])
+        for f in ("region", "vartype", "kid", "dad", "mom", "evidence_type", "cnv_dad_sites", "cnv_mom_sites", "cnv_evidence_type"):
+            assert got[k][f] == want[k][f], (k, f)

@@ -24,6 +24,44 @@ def dnm_key(dn: dict) -> str:
     return "_".join([str(dn["chrom"]), str(dn["start"]), str(dn["end"]), dn["kid"], dn["vartype"]])
 
 
+class CompactRecords:
+    """The records of one shard before they are Python dicts: the live DNM entries plus the flat evidence lists they are
+    cut from.  This is what a rank sends to rank 0 in a multi-GPU run -- a few numpy arrays pickle and unpickle in
+    microseconds, whereas unpickling the finished dicts (hundreds of thousands of small strings) made rank 0 the serial
+    bottleneck of the cohort job.  ``to_records()`` is the same native builder ``BatchPhaser.records`` uses."""
+
+    def __init__(self, entries, ped, auto, names, pair_ids, n_read_dad, pos_dad, pos_mom, off):
+        self.entries, self.ped, self.auto = entries, ped, auto
+        self.names, self.pair_ids, self.n_read_dad = names, pair_ids, int(n_read_dad)
+        self.pos_dad, self.pos_mom, self.off = pos_dad, pos_mom, off
+
+    def __len__(self):
+        return len(self.entries)
+
+    def to_records(self, out: Optional[Dict[str, dict]] = None) -> Dict[str, dict]:
+        out = {} if out is None else out
+        k = len(self.entries)
+        n_r = len(self.names) if self.names is not None else int(self.pair_ids.shape[0])
+        idx = np.arange(n_r, dtype=np.int32)
+        _records.read_records(out, self.entries, self.ped, np.arange(k, dtype=np.int64), np.ascontiguousarray(self.auto, dtype=np.uint8),
+                              self.names, self.pair_ids, idx[: self.n_read_dad], idx[self.n_read_dad:],
+                              np.ascontiguousarray(self.pos_dad, dtype=np.int32), np.ascontiguousarray(self.pos_mom, dtype=np.int32),
+                              np.ascontiguousarray(self.off, dtype=np.int64))
+        return out
+
+
+def _cut(flat: np.ndarray, off: np.ndarray, live: np.ndarray):
+    """The slices flat[off[d]:off[d+1]] of the entries in ``live``, concatenated, and their new offsets."""
+    lens = off[live + 1] - off[live]
+    new_off = np.zeros(live.shape[0] + 1, dtype=np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    tot = int(new_off[-1])
+    if tot == int(flat.shape[0]):                    # entries without a record own no evidence: nothing to drop
+        return flat, new_off
+    src = np.repeat(off[live] - new_off[:-1], lens) + np.arange(tot, dtype=np.int64)
+    return flat[src], new_off
+
+
 class BatchPhaser:
     """``resident=True`` (default): the site and read columns are uploaded once and stay in HBM across
     calls.  ``resident=False``: every call copies them from the host arrays it was given (pinned
@@ -283,6 +321,35 @@ class BatchPhaser:
         out_snv.update(out_sv)
         return out_snv
 
+    def compact(self, res: BatchResult, layout) -> Optional[CompactRecords]:
+        """The records of a batch in compact form (see CompactRecords), or None when the batch needs the general path
+        (SV entries merge CNV votes into their records; runs without device evidence lists)."""
+        if res.ev is None or layout["sv_cnv"][1] > layout["sv_cnv"][0] or layout["sv_read"][1] > layout["sv_read"][0]:
+            return None
+        plan, ev = res.plan, res.ev
+        a, b = layout["snv"]
+        flags_a = plan.dnm["flags"]
+        has_a = res.tally["has_record"] if res.tally is not None else np.zeros(len(flags_a), dtype=np.int32)
+        live = a + np.flatnonzero(((flags_a[a:b] & L.DNM_AUTOPHASE) != 0) | (has_a[a:b] != 0))
+        auto = ((flags_a[live] & L.DNM_AUTOPHASE) != 0).astype(np.uint8)
+        entries = [plan.entries[d] for d in live.tolist()]
+        entries = [{"chrom": e["chrom"], "start": e["start"], "end": e["end"], "kid": e["kid"], "vartype": e["vartype"]} for e in entries]
+        ped = {k: {"dad": self.ped[k]["dad"], "mom": self.ped[k]["mom"]} for k in {e["kid"] for e in entries}}
+        off = np.asarray(ev["off"], dtype=np.int64)
+        rd, o_rd = _cut(ev["read_dad"], off[0], live)
+        rm, o_rm = _cut(ev["read_mom"], off[1], live)
+        pd_, o_pd = _cut(ev["pos_dad"], off[2], live)
+        pm_, o_pm = _cut(ev["pos_mom"], off[3], live)
+        ridx = np.concatenate([rd, rm]).astype(np.int64)
+        if self.reads.names is not None:
+            nm = self.reads.names
+            names, pair_ids = [nm[i] for i in ridx.tolist()], None
+        else:
+            names, pair_ids = None, np.ascontiguousarray(self.reads.pair_ids()[ridx], dtype=np.int64)
+        o_rm = o_rm                                             # offsets of the mom lists index the second half
+        return CompactRecords(entries, ped, auto, names, pair_ids, rd.shape[0], np.array(pd_, dtype=np.int32),
+                              np.array(pm_, dtype=np.int32), np.stack([o_rd, o_rm, o_pd, o_pm]))
+
     def labels(self, res: BatchResult, d: int) -> Dict[str, str]:
         """read name -> haplotype ('ref' | 'alt' | 'ref+alt') of entry d (parity checks)."""
         lab = res.slot_labels(d)
@@ -296,18 +363,27 @@ class BatchPhaser:
         snvs = [d for d in dnms if d["vartype"].upper() in SNV_TYPES and d["kid"] in kids]
         return snvs, svs
 
-    def phase(self, dnms: List[dict], **params) -> Dict[str, dict]:
+    def _deliver(self, res: BatchResult, layout, compact: bool):
+        if compact:
+            c = self.compact(res, layout)
+            if c is not None:
+                return c
+        return self.records(res, layout)
+
+    def phase(self, dnms: List[dict], compact: bool = False, **params):
+        """DNM dicts in, the record dict of phase_snvs/phase_svs out.  ``compact=True`` returns a CompactRecords when the
+        batch allows it (what a rank ships to rank 0 in a multi-GPU run; ``.to_records()`` gives the same dict)."""
         import time as _t
         snvs, svs = self._split(dnms)
         # the CNV votes of SVs are read from the device lists while the records are built; otherwise nothing has to
         # stay on the device and the engine recycles its buffers (and replays the batch as a CUDA graph)
         res, layout = self.run(snvs, svs, keep_device=bool(svs), **params)
         t0 = _t.perf_counter()
-        out = self.records(res, layout)
+        out = self._deliver(res, layout, compact)
         self.last_timing["records_ms"] = (_t.perf_counter() - t0) * 1e3
         return out
 
-    def phase_stream(self, batches, **params):
+    def phase_stream(self, batches, compact: bool = False, **params):
         """Phase a sequence of DNM lists, yielding one record dict per list, in order.  Software pipeline of depth two:
         the copies and kernels of list k+1 are put on the stream BEFORE the host waits for list k and turns its
         results into record dicts, so host work (about half of an end-to-end step) and PCIe/GPU work overlap."""
@@ -318,7 +394,7 @@ class BatchPhaser:
             t0 = _t.perf_counter()
             res = p[0].finish()
             t1 = _t.perf_counter()
-            out = self.records(res, p[1])
+            out = self._deliver(res, p[1], compact)
             self.last_timing.update(wait_results_ms=(t1 - t0) * 1e3, records_ms=(_t.perf_counter() - t1) * 1e3)
             return out
 

@@ -109,7 +109,7 @@ def cross_kid_coupling(svs: Sequence[dict], pedigrees: dict, build, multiread_pr
     return any(any(v) and not all(v) for v in by_chrom.values())
 
 
-def phase_sharded(phase_fn: Callable[[List[dict]], Dict[str, dict]], dnms: Sequence[dict],
+def phase_sharded(phase_fn: Callable[[List[dict]], object], dnms: Sequence[dict],
                   reads_per_kid: Optional[Dict[str, int]] = None,
                   split_heavy: bool = True, all_on_rank0: bool = False) -> Optional[Dict[str, dict]]:
     """Run ``phase_fn`` on this rank's shard and gather the record dicts on rank 0 (None elsewhere).
@@ -117,7 +117,9 @@ def phase_sharded(phase_fn: Callable[[List[dict]], Dict[str, dict]], dnms: Seque
     on rank 0 (runs whose kids are coupled) while every rank still takes part in the gather."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return phase_fn(list(dnms))
+        out = {}
+        merge_part(out, phase_fn(list(dnms)))
+        return out
     rank, world = dist.get_rank(), dist.get_world_size()
     if all_on_rank0:
         mine = list(dnms) if rank == 0 else []
@@ -138,5 +140,14 @@ def phase_sharded(phase_fn: Callable[[List[dict]], Dict[str, dict]], dnms: Seque
         if not ok:
             raise part
     for _, part in gathered:
-        out.update(part)
+        merge_part(out, part)
     return out
+
+
+def merge_part(out: Dict[str, dict], part) -> None:
+    """A rank's contribution is either the record dict itself or its compact form (phaser.CompactRecords: arrays that
+    pickle in microseconds); the compact form becomes dicts here, on rank 0, through the native builder."""
+    if hasattr(part, "to_records"):
+        part.to_records(out)
+    else:
+        out.update(part)

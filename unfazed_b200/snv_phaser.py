@@ -49,7 +49,7 @@ def phase_by_reads(matches):
 
 def run_batch(snvs, svs, pedigrees, sites, threads, build, no_extended, multiread_proc_min, ab_homref, ab_homalt,
               ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample, stdevs, min_map_qual, readlen,
-              split_error_margin):
+              split_error_margin, compact=False):
     from .phaser import BatchPhaser
     dnms = list(svs) + list(snvs)
     site_table = datasource.load_sites(sites, dnms, pedigrees, search_dist)
@@ -74,7 +74,7 @@ def run_batch(snvs, svs, pedigrees, sites, threads, build, no_extended, multirea
                 _say("No usable genotype for variant {}:{}-{}".format(dn["chrom"], dn["start"], dn["end"]))
             elif res.tally is not None and not res.tally["has_record"][d]:
                 _say("No reads overlap informative sites for variant {}:{}-{}".format(dn["chrom"], dn["start"], dn["end"]))
-    return bp.records(res, layout)
+    return bp._deliver(res, layout, compact)
 
 
 def phase_snvs(dnms, kids, pedigrees, sites, threads, build, no_extended, multithread_proc_min, quiet_mode,
@@ -85,3 +85,15 @@ def phase_snvs(dnms, kids, pedigrees, sites, threads, build, no_extended, multit
     return run_batch(dnms, [], pedigrees, sites, threads, build, no_extended, multithread_proc_min, ab_homref,
                      ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample, stdevs,
                      min_map_qual, readlen, split_error_margin)
+
+
+def phase_snvs_compact(dnms, kids, pedigrees, sites, threads, build, no_extended, multithread_proc_min, quiet_mode,
+                       ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample,
+                       stdevs, min_map_qual, readlen, split_error_margin):
+    """``phase_snvs`` for a rank of a multi-GPU run: the same batch, returned as phaser.CompactRecords (arrays) so that
+    the gather on rank 0 does not unpickle finished dicts; ``shard.merge_part`` turns it into the record dict."""
+    global QUIET_MODE
+    QUIET_MODE = quiet_mode
+    return run_batch(dnms, [], pedigrees, sites, threads, build, no_extended, multithread_proc_min, ab_homref,
+                     ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample, stdevs,
+                     min_map_qual, readlen, split_error_margin, compact=True)

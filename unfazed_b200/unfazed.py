@@ -262,6 +262,10 @@ def _phase_multi_gpu(snvs, svs, common):
     def phase_fn(mine):
         my_svs = [d for d in mine if d["vartype"].upper() in SV_TYPES]
         my_snvs = [d for d in mine if d["vartype"].upper() in SNV_TYPES]
+        if my_snvs and not my_svs:
+            # the shard travels to rank 0 as arrays and becomes record dicts there (shard.merge_part)
+            from .snv_phaser import phase_snvs_compact
+            return phase_snvs_compact(my_snvs, *with_mpm(len(snvs)))
         out = phase_snvs(my_snvs, *with_mpm(len(snvs))) if my_snvs else {}
         out.update(phase_svs(my_svs, *with_mpm(len(svs))) if my_svs else {})
         return out

@@ -13,7 +13,16 @@ from unfazed_b200.synth import SynthConfig, make_dataset  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 sd = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
 cov = float(sys.argv[3]) if len(sys.argv) > 3 else 30.0
-ds = make_dataset(SynthConfig(dnms_per_trio=n, seed=1, search_dist=sd, coverage=cov))
+import pickle  # noqa: E402
+cache = "/tmp/dbg_chain_%d_%d_%g.pkl" % (n, sd, cov)     # several library variants are timed on the same data set
+if os.path.exists(cache):
+    ds = pickle.load(open(cache, "rb"))
+else:
+    ds = make_dataset(SynthConfig(dnms_per_trio=n, seed=1, search_dist=sd, coverage=cov))
+    try:
+        pickle.dump(ds, open(cache, "wb"), protocol=5)
+    except Exception:
+        pass
 eng = Engine(0)
 bp = BatchPhaser(eng, ds.sites, ds.reads, ds.pedigrees)
 params = make_params(readlen=151)

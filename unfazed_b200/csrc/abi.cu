@@ -1,4 +1,6 @@
 // Context management of libunfazed_sm100.so.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 extern "C" int unfz_abi_version(void) { return UNFZ_ABI_VERSION; }
@@ -18,6 +20,7 @@ extern "C" int unfz_ctx_create(int device, UnfzCtx** out) {
     c->guard = nullptr;
     c->scan_smem_attr = 0;
     c->chain_carveout_set = false;
+    c->cls_params = nullptr;
     memset(c->graphs, 0, sizeof(c->graphs));
     c->graph_tick = 0;
     c->err[0] = 0;
@@ -29,6 +32,7 @@ extern "C" void unfz_ctx_destroy(UnfzCtx* ctx) {
     if (!ctx) return;
     for (auto& g : ctx->graphs)
         if (g.key) cudaGraphExecDestroy(g.exec);
+    free(ctx->cls_params);
     delete ctx;
 }
 

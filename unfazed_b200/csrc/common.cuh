@@ -19,6 +19,8 @@ struct UnfzCtx {
     const int32_t* guard;     // device flag of the speculative-sizing mode (unfz_ctx_set_guard), or null
     bool chain_carveout_set;  // shared-memory carve-out preference of the chaining kernel set on THIS device
     size_t scan_smem_attr;    // opt-in dynamic shared memory already granted to the read scan on THIS device
+    void* cls_params;         // classifier thresholds + allele-balance interval table of cls_key (sites.cu), malloc'ed
+    double cls_key[8];        // ab_homref, ab_het, ab_homalt, min_gt_qual, min_depth the table was made for
     UnfzGraphSlot graphs[8];  // instantiated batch graphs (unfz_run_batch_graph)
     uint64_t graph_tick;
     char err[512];

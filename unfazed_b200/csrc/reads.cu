@@ -427,11 +427,11 @@ read_scan_warp_kernel(UnfzReadCols reads, UnfzSiteCols sites, const int32_t* __r
 }
 
 // query index of reference position p, or -1 (pysam get_reference_positions(full_length=True).index)
-__device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n_cigar, int32_t start, int32_t p) {
+__device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n_cigar, int32_t start, int32_t p, uint32_t w0) {
     int32_t cur = start;
     int q = 0;
     for (int k = 0; k < n_cigar; ++k) {
-        const uint32_t w = __ldg(cg + k);
+        const uint32_t w = k == 0 ? w0 : __ldg(cg + k);     // the first word was requested together with the row data
         const uint32_t op = w & 15u;
         const int32_t ln = (int32_t)(w >> 4);
         if (op == 0 || op == 7 || op == 8) {
@@ -453,42 +453,49 @@ __device__ __forceinline__ int cigar_qpos(const uint32_t* __restrict__ cg, int n
 // ------------------------------------------------------------------------------------------------
 // K3: read x marked-site allele lookup
 // ------------------------------------------------------------------------------------------------
-// the lookup of ONE read with hits: walk the site rows it spans, CIGAR walk per marked row, three bit / base gathers
+// the lookup of ONE read with hits: walk the site rows it spans, CIGAR walk per marked row, three bit / base gathers.
+// The kernel lives on the latency of dependent gathers, so everything whose address is known is requested at once:
+// summary and header together; then the first CIGAR word, the first row's position and its two mark prefixes; inside
+// the walk the next row is requested before the current one is looked up.  Three round trips for the common read
+// (one M operation, one marked site) instead of seven.
 __device__ __forceinline__ void read_alleles_one(const UnfzReadCols& reads, const UnfzSiteCols& sites,
                                                  const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
                                                  const uint32_t* __restrict__ tile_base, int32_t tile_reads,
-                                                 uint32_t* __restrict__ hits, int64_t r, int rb_hint) {
+                                                 uint32_t* __restrict__ hits, int64_t r) {
     const UnfzReadSum s = load_rsum(rsum + r);
+    const UnfzRead h = load_read(reads.hdr + r);           // independent of the summary: both sectors fly together
     if (s.cnt == 0) return;
-    const UnfzRead h = load_read(reads.hdr + r);
-    int rb;
-    if (rb_hint >= 0) { rb = rb_hint; while (r >= reads.blk_off[rb + 1]) ++rb; }
-    else rb = (int)(upper_bound_dev(reads.blk_off, 0, (int64_t)reads.n_blocks + 1, r) - 1);
-    const int sb = reads.blk_sblk[rb];
-    if (sb < 0) return;
-    const int64_t b = sites.blk_off[sb + 1];
+    // The scan counted s.cnt marked rows with start <= pos < end from row_lb on, all inside the read's site block:
+    // the walk ends when they are written, so the block's end is never consulted (n_rows only bounds the prefetch)
+    const int64_t n_rows = sites.n_rows;
     int64_t row = s.row_lb;                                // first site row with pos >= start (from read_scan)
     const uint32_t* cg = reads.cigar + h.cigar_off;
+    const uint32_t cg0 = h.n_cigar > 0 ? __ldg(cg) : 0u;
+    int32_t p = row < n_rows ? __ldg(sites.pos + row) : 0x7fffffff;
+    int mp0 = __ldg(mark_prefix + min(row, n_rows));
+    int mp1 = __ldg(mark_prefix + min(row + 1, n_rows));
     const int64_t q0 = read_qoff(h);
     const int64_t hbase = (int64_t)__ldg(tile_base + (uint32_t)r / (uint32_t)tile_reads) + s.hoff;
     int written = 0;
-    for (; row < b && written < s.cnt; ++row) {
-        const int32_t p = __ldg(sites.pos + row);
-        if (p >= s.end) break;
-        const int mp0 = __ldg(mark_prefix + row);
-        if (__ldg(mark_prefix + row + 1) == mp0) continue;      // not a marked row
-        const int k = mp0 - s.fmark;
-        uint32_t word = 0;
-        const int q = cigar_qpos(cg, h.n_cigar, h.start, p);
-        if (q >= 0 && q < 0xffff) {
-            const int64_t g = q0 + q;
-            const uint32_t lq = (__ldg(reads.lowq + (g >> 5)) >> (g & 31)) & 1u;
-            const uint32_t nb = (h.aux & 4u) ? ((__ldg(reads.nmask + (g >> 5)) >> (g & 31)) & 1u) : 0u;
-            const uint32_t code = (__ldg(reads.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
-            word = (uint32_t)(q + 1) | (lq << 16) | (nb << 23) | (code << 24) | ((q + 1 < h.l_seq) ? (1u << 26) : 0u);
+    while (written < s.cnt && p < s.end) {
+        const int64_t nrow = row + 1;                      // requested now, used by the next iteration
+        const int32_t pn = nrow < n_rows ? __ldg(sites.pos + nrow) : 0x7fffffff;
+        const int mp2 = __ldg(mark_prefix + min(nrow + 1, n_rows));
+        if (mp1 != mp0) {                                  // a marked row
+            const int k = mp0 - s.fmark;
+            uint32_t word = 0;
+            const int q = cigar_qpos(cg, h.n_cigar, h.start, p, cg0);
+            if (q >= 0 && q < 0xffff) {
+                const int64_t g = q0 + q;
+                const uint32_t lq = (__ldg(reads.lowq + (g >> 5)) >> (g & 31)) & 1u;
+                const uint32_t nb = (h.aux & 4u) ? ((__ldg(reads.nmask + (g >> 5)) >> (g & 31)) & 1u) : 0u;
+                const uint32_t code = (__ldg(reads.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
+                word = (uint32_t)(q + 1) | (lq << 16) | (nb << 23) | (code << 24) | ((q + 1 < h.l_seq) ? (1u << 26) : 0u);
+            }
+            if (k >= 0 && k < s.cnt) hits[hbase + k] = word;
+            ++written;
         }
-        if (k >= 0 && k < s.cnt) hits[hbase + k] = word;
-        ++written;
+        row = nrow; p = pn; mp0 = mp1; mp1 = mp2;
     }
 }
 
@@ -500,8 +507,13 @@ __device__ __forceinline__ void read_alleles_one(const UnfzReadCols& reads, cons
 #define LK_TILES_N 16
 #endif
 constexpr int LK_TILES = LK_TILES_N;
+// the lookup is a chain of dependent gathers per read: it lives on resident warps.  8 CTAs x 256 threads per SM (32
+// registers, a few spilled words) beat 6 x 40 registers without spills (measured with the single-M shortcut build: 0.153 vs 0.173 ms)
+#ifndef LK_MINB
+#define LK_MINB 8
+#endif
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LK_MINB)
 read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* __restrict__ row_mark,
                          const int32_t* __restrict__ mark_prefix, const UnfzReadSum* __restrict__ rsum,
                          const uint32_t* __restrict__ tile_base, int32_t tile_reads,
@@ -514,11 +526,9 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
     const int64_t t0 = w * LK_TILES;
     if (t0 >= n_tiles) return;
     uint32_t mask = 0;
-    int rbh = -1;
     if (lane < LK_TILES && t0 + lane < n_tiles) {
         const uint2 ti = __ldg(tile_info + t0 + lane);
         mask = ti.x;
-        rbh = (int)ti.y;
         if (((t0 + lane) << 5) + 32 > reads.n_reads) mask &= (1u << (reads.n_reads - ((t0 + lane) << 5))) - 1u;   // ragged last tile
     }
     // exclusive prefix of the populations over the group's tiles (lanes 0..LK_TILES-1)
@@ -536,10 +546,9 @@ read_site_alleles_kernel(UnfzReadCols reads, UnfzSiteCols sites, const uint8_t* 
         const int tt = min(t, LK_TILES - 1);
         const uint32_t m = __shfl_sync(0xffffffffu, mask, tt);
         const int before = __shfl_sync(0xffffffffu, incl - c, tt);
-        const int hint = __shfl_sync(0xffffffffu, rbh, tt);
         if (j < total) {
             const int bit = __fns(m, 0, j - before + 1);           // the (j - before)-th set bit of the tile's mask
-            read_alleles_one(reads, sites, mark_prefix, rsum, tile_base, tile_reads, hits, ((t0 + tt) << 5) + bit, hint);
+            read_alleles_one(reads, sites, mark_prefix, rsum, tile_base, tile_reads, hits, ((t0 + tt) << 5) + bit);
         }
     }
 }

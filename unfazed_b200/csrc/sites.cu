@@ -33,20 +33,20 @@ __global__ void window_search_kernel(UnfzSiteCols sites, const UnfzSegIn* __rest
 // ------------------------------------------------------------------------------------------------
 // K1: classification
 // ------------------------------------------------------------------------------------------------
-// per-genotype thresholds, indexed by the cyvcf2 gt code (2 = unknown -> never high quality).
-// fp32 pre-filter of the allele-balance test: q ~ ad/tot in fp32 (a few ulp), so q inside
-// [in_lo, in_hi] proves the fp64 test true and q outside [out_lo, out_hi] proves it false; only
-// ratios within ~1e-6 of a threshold take the exact IEEE fp64 division.  ad == 0 / ad == tot give
-// exactly 0.0 / 1.0 and are decided on the host in fp64 (flags).
-struct GtThr {
-    float4 f;             // in_lo, in_hi, out_lo, out_hi
-    double lo, hi;        // the fp64 thresholds for the exact path
-    int32_t flags;        // bit0 valid genotype, bit1 0.0 in range, bit2 1.0 in range
-    int32_t _pad;
-};
+// Allele balance without a division.  For a member with genotype g and total depth tot the reference asks
+// min_ab <= float(ad / float(tot)) <= max_ab (informative_site_finder.py:69-71).  The quotient is monotone in ad, so
+// for every (genotype class, tot) the passing ad form one interval [min_ad, max_ad]; the host works the intervals
+// out ONCE with the very IEEE double division the reference performs (unfz_classify_sites) for every tot below
+// CLS_TAB_TOT, folds "genotype is known" and "tot >= min_depth" into them (empty interval) and hands the table to the
+// kernel, which stages it in shared memory: one LDS + two integer compares per member instead of a reciprocal, a
+// multiply, six float compares and a guard band.  Depths of CLS_TAB_TOT and more, and negative counts, take the exact
+// fp64 division (ab_exact) as before.
+constexpr int CLS_TAB_TOT = 1024;
+constexpr int CLS_TAB_ROWS = 4;           // homref, het, homalt, unknown/invalid (always empty)
 
 struct ClsParams {
-    GtThr thr[4];
+    uint32_t tab[CLS_TAB_ROWS * CLS_TAB_TOT];   // min_ad | max_ad << 16; empty: min 1, max 0
+    double lo[4], hi[4];                  // fp64 thresholds per table row for the exact path (row 3: NaN, never true)
     float min_gq_f;       // smallest float >= min_gq: for a float gq, (double)gq < min_gq <=> gq < min_gq_f
     int32_t min_depth;
 };
@@ -75,7 +75,8 @@ __device__ __noinline__ int kid_allele_dup(int32_t rd0, int32_t ad0, int32_t rd1
 // be taken by some lane anyway); all predicates are pure, so the evaluation order is irrelevant.
 // Only two rare events branch: an allele balance within 1e-6 of a threshold (exact fp64 division)
 // and the DUP allele-balance rule.
-__device__ __forceinline__ uint8_t classify_pair(const GtThr* __restrict__ thr, const uint8_t* __restrict__ gt_lut,
+__device__ __forceinline__ uint8_t classify_pair(const uint32_t* __restrict__ tab, const double* __restrict__ lohi,
+                                                 const uint8_t* __restrict__ gt_lut,
                                                  float min_gq_f, int32_t min_depth, int mode,
                                                  int32_t pos, int32_t excl_lo, int32_t excl_hi, uint32_t meta,
                                                  const float gq[3], const int32_t rd[3], const int32_t ad[3]) {
@@ -84,29 +85,25 @@ __device__ __forceinline__ uint8_t classify_pair(const GtThr* __restrict__ thr, 
     const bool read_mode = mode == UNFZ_MODE_READ;
     bool hq[3], need[3];
     int32_t tot[3];
+    int trow[3];
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
         const int g = m == 0 ? gk : (m == 1 ? gd : gm);
-        const GtThr t = thr[g & 3];
-        const bool valid = (g <= 3) & (t.flags & 1);
+        // table row of the cyvcf2 gt code: 0 -> 0, 1 -> 1, 3 -> 2, 2 (unknown) and anything else -> 3 (empty)
+        const int row = g > 3 ? 3 : (int)((0x2310u >> (g << 2)) & 3u);
+        trow[m] = row;
         tot[m] = (int32_t)((uint32_t)rd[m] + (uint32_t)ad[m]);             // numpy int32 add wraps
-        const bool pre = valid & !(gq[m] < min_gq_f) & (tot[m] >= min_depth);
-        // 0 <= ad <= tot, 0 < tot < 2^24 as two unsigned compares
-        const bool fv = ((uint32_t)ad[m] <= (uint32_t)tot[m]) & ((uint32_t)(tot[m] - 1) < (uint32_t)((1 << 24) - 1));
-        const float q = __fdividef((float)ad[m], (float)tot[m]);           // <= 2 ulp; the margin is 1e-6
-        const bool is0 = ad[m] == 0, is1 = ad[m] == tot[m];               // exactly 0.0 / 1.0 (very common)
-        const bool in = is0 ? ((t.flags & 2) != 0) : (is1 ? ((t.flags & 4) != 0) : ((q >= t.f.x) & (q <= t.f.y)));
-        const bool out = (q < t.f.z) | (q > t.f.w);
-        hq[m] = pre & fv & in;
-        need[m] = pre & !(fv & (is0 | is1 | in | out));
+        const bool gq_ok = !(gq[m] < min_gq_f);
+        // inside the table: 0 <= tot < CLS_TAB_TOT and 0 <= ad <= tot, as two unsigned compares
+        const bool in_tab = ((uint32_t)tot[m] < (uint32_t)CLS_TAB_TOT) & ((uint32_t)ad[m] <= (uint32_t)tot[m]);
+        const uint32_t e = tab[row * CLS_TAB_TOT + (in_tab ? tot[m] : 0)];
+        hq[m] = gq_ok & in_tab & ((uint32_t)ad[m] >= (e & 0xffffu)) & ((uint32_t)ad[m] <= (e >> 16));
+        need[m] = gq_ok & !in_tab & (row != 3) & (tot[m] >= min_depth);
     }
-    if (base && (need[0] | need[1] | need[2])) {                           // rare
+    if (base && (need[0] | need[1] | need[2])) {                           // rare: depth >= CLS_TAB_TOT or negative counts
 #pragma unroll
         for (int m = 0; m < 3; ++m)
-            if (need[m]) {
-                const int g = m == 0 ? gk : (m == 1 ? gd : gm);
-                hq[m] = ab_exact(thr[g & 3].lo, thr[g & 3].hi, ad[m], tot[m]);
-            }
+            if (need[m]) hq[m] = ab_exact(lohi[trow[m]], lohi[4 + trow[m]], ad[m], tot[m]);
     }
     const bool parents = hq[1] & hq[2];
     int ka = 0;                                                            // get_kid_allele
@@ -148,7 +145,7 @@ constexpr int CLS_SMEM_SEGS = 512;
 // inclusive prefix is the index of the last segment starting at or before the pair).
 __global__ void __launch_bounds__(CLS_THREADS, CLS_MINB)
 classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const int32_t* __restrict__ seg_row_lo,
-                const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs_cap, ClsParams P,
+                const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs_cap, const __grid_constant__ ClsParams P,
                 uint8_t* __restrict__ out, const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
     // the launch is sized for n_pairs_cap (the caller's buffer); the batch's own total is on the device
@@ -157,14 +154,16 @@ classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const in
     __shared__ int4 s_seg[CLS_SMEM_SEGS];            // row_lo, mult | mode << 24, excl_lo, excl_hi
     __shared__ int32_t s_map[CLS_TILE];
     __shared__ int32_t s_warp[CLS_THREADS / 32];
-    __shared__ GtThr s_thr[4];
+    __shared__ uint32_t s_tab[CLS_TAB_ROWS * CLS_TAB_TOT];
+    __shared__ double s_lohi[8];
     __shared__ uint8_t s_lut[64];
     __shared__ int32_t s_seg0;
     const int64_t n_tiles = (n_pairs + CLS_TILE - 1) / CLS_TILE;
     const int64_t tpc = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * tpc, t1 = min(t0 + tpc, n_tiles);
     if (t0 >= t1) return;
-    if (threadIdx.x == 0) { s_thr[0] = P.thr[0]; s_thr[1] = P.thr[1]; s_thr[2] = P.thr[2]; s_thr[3] = P.thr[3]; }
+    for (int i = threadIdx.x; i < CLS_TAB_ROWS * CLS_TAB_TOT; i += CLS_THREADS) s_tab[i] = P.tab[i];
+    if (threadIdx.x < 8) s_lohi[threadIdx.x] = threadIdx.x < 4 ? P.lo[threadIdx.x] : P.hi[threadIdx.x - 4];
     if (threadIdx.x < 64) {
         const int gk = threadIdx.x >> 4, gd = (threadIdx.x >> 2) & 3, gm = threadIdx.x & 3;
         const bool p1 = ((gd == 1) | (gd == 3)) & (gm == 0);
@@ -270,7 +269,7 @@ classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const in
             if (j + 1 < CLS_PER_THREAD) nxt = fetch(j + 1);
             const float gq[3] = {cur.rc.y, cur.rc.z, cur.rc.w};
             const int32_t rd[3] = {cur.d0.x, cur.d1.x, cur.d2.x}, ad[3] = {cur.d0.y, cur.d1.y, cur.d2.y};
-            const uint8_t code = classify_pair(s_thr, s_lut, P.min_gq_f, P.min_depth, cur.mode, __float_as_int(cur.rc.x), cur.exlo,
+            const uint8_t code = classify_pair(s_tab, s_lohi, s_lut, P.min_gq_f, P.min_depth, cur.mode, __float_as_int(cur.rc.x), cur.exlo,
                                                cur.exhi, cur.meta, gq, rd, ad);
             const int q_raw = j * CLS_THREADS + threadIdx.x;
             if (q_raw < npair) out[p0 + q_raw] = code;
@@ -378,28 +377,48 @@ extern "C" int unfz_window_search(UnfzCtx* ctx, const UnfzSiteCols* sites, const
     return 0;
 }
 
-extern "C" int unfz_classify_sites(UnfzCtx* ctx, const UnfzSiteCols* sites, const UnfzSegIn* segs,
-                                   const int32_t* seg_row_lo, const int64_t* seg_pair_off, int32_t n_segs,
-                                   int64_t n_pairs, const UnfzParams* hp, uint8_t* out_class, void* stream) {
-    if (n_pairs <= 0) return 0;
-    ClsParams P;
+// The classifier's parameter block for the thresholds of this call; rebuilt only when they change (the engine passes
+// the same ones batch after batch).  Interval ends are found with the reference's own arithmetic -- IEEE double
+// division of the two counts, inclusive compares -- starting next to lo*tot / hi*tot, so building all 3 x 1024
+// intervals is a few thousand divisions.
+static ClsParams* cls_params_for(UnfzCtx* ctx, const UnfzParams* hp) {
+    const double key[8] = {hp->ab_homref[0], hp->ab_homref[1], hp->ab_het[0], hp->ab_het[1], hp->ab_homalt[0], hp->ab_homalt[1],
+                           hp->min_gt_qual, (double)hp->min_depth};
+    if (ctx->cls_params && memcmp(key, ctx->cls_key, sizeof(key)) == 0) return static_cast<ClsParams*>(ctx->cls_params);
+    if (!ctx->cls_params) ctx->cls_params = malloc(sizeof(ClsParams));
+    ClsParams& P = *static_cast<ClsParams*>(ctx->cls_params);
     const double ab[3][2] = {{hp->ab_homref[0], hp->ab_homref[1]}, {hp->ab_het[0], hp->ab_het[1]}, {hp->ab_homalt[0], hp->ab_homalt[1]}};
-    for (int g = 0; g < 4; ++g) {
-        const int r = g == 0 ? 0 : (g == 3 ? 2 : 1);
-        GtThr t;
-        t.f.x = nextafterf((float)(ab[r][0] + 1e-6), INFINITY);
-        t.f.y = nextafterf((float)(ab[r][1] - 1e-6), -INFINITY);
-        t.f.z = nextafterf((float)(ab[r][0] - 1e-6), -INFINITY);
-        t.f.w = nextafterf((float)(ab[r][1] + 1e-6), INFINITY);
-        t.lo = ab[r][0];
-        t.hi = ab[r][1];
-        t.flags = g == 2 ? 0 : (1 | ((ab[r][0] <= 0.0 && 0.0 <= ab[r][1]) ? 2 : 0) | ((ab[r][0] <= 1.0 && 1.0 <= ab[r][1]) ? 4 : 0));
-        t._pad = 0;
-        P.thr[g] = t;
+    for (int r = 0; r < CLS_TAB_ROWS; ++r) {
+        P.lo[r] = r < 3 ? ab[r][0] : NAN;
+        P.hi[r] = r < 3 ? ab[r][1] : NAN;
+        for (int tot = 0; tot < CLS_TAB_TOT; ++tot) {
+            uint32_t e = 1u;                                               // empty: min 1 > max 0
+            if (r < 3 && tot >= 1 && tot >= hp->min_depth) {
+                const double lo = ab[r][0], hi = ab[r][1], t = (double)tot;
+                auto pass = [&](int a) { const double q = (double)a / t; return lo <= q && q <= hi; };
+                // smallest passing ad: start two below the real-valued bound, walk up; largest: two above, walk down
+                double g0 = floor(lo * t) - 2.0, g1 = ceil(hi * t) + 2.0;
+                int a0 = !(g0 > 0.0) ? 0 : (g0 > t ? tot + 1 : (int)g0);
+                int a1 = !(g1 < t) ? tot : (g1 < 0.0 ? -1 : (int)g1);
+                while (a0 <= tot && !pass(a0)) ++a0;
+                while (a1 >= 0 && !pass(a1)) --a1;
+                if (a0 <= a1) e = (uint32_t)a0 | ((uint32_t)a1 << 16);
+            }
+            P.tab[r * CLS_TAB_TOT + tot] = e;
+        }
     }
     P.min_gq_f = (float)hp->min_gt_qual;
     if ((double)P.min_gq_f < hp->min_gt_qual) P.min_gq_f = nextafterf(P.min_gq_f, INFINITY);
     P.min_depth = hp->min_depth;
+    memcpy(ctx->cls_key, key, sizeof(key));
+    return &P;
+}
+
+extern "C" int unfz_classify_sites(UnfzCtx* ctx, const UnfzSiteCols* sites, const UnfzSegIn* segs,
+                                   const int32_t* seg_row_lo, const int64_t* seg_pair_off, int32_t n_segs,
+                                   int64_t n_pairs, const UnfzParams* hp, uint8_t* out_class, void* stream) {
+    if (n_pairs <= 0) return 0;
+    ClsParams& P = *cls_params_for(ctx, hp);
     const int64_t n_tiles = (n_pairs + CLS_TILE - 1) / CLS_TILE;
     // persistent grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
     int64_t grid = (int64_t)ctx->sm_count * 8;

@@ -249,3 +249,29 @@ def test_compact_records_equal_the_record_dicts(engine):
     ds2 = make_dataset(SynthConfig(dnms_per_trio=20, seed=412, sv_frac=0.5, sv_max_len=20000, coverage=16.0))
     bp2 = BatchPhaser(engine, ds2.sites, ds2.reads, ds2.pedigrees)
     assert isinstance(bp2.phase(copy.deepcopy(ds2.dnms), compact=True), dict)
+
+
+@pytest.mark.parametrize("shape", ["wide", "small"])
+def test_both_chaining_cta_shapes_give_the_oracle_records(shape, monkeypatch):
+    """The chaining kernels exist in two CTA shapes (128 threads for ordinary windows, 512 for deep / wide ones,
+    chosen per batch from the incidence count).  Forced either way, a small-window batch with indels and SVs, a
+    > 128-het-site window and a 50 kb window all reproduce the oracle's records -- first call (exact sizes) and
+    second call (speculative sizes, CUDA graph)."""
+    from unfazed_b200.engine import Engine
+    from unfazed_b200.phaser import BatchPhaser
+    monkeypatch.setenv("UNFZ_CHAIN_SHAPE", shape)
+    eng = Engine(0)                       # its own context: the batch graphs of the shared engine were captured with the default choice
+    cases = [
+        (SynthConfig(dnms_per_trio=40, seed=701, indel_frac=0.2, sv_frac=0.2, sv_max_len=20000, coverage=20.0), {}),
+        (SynthConfig(dnms_per_trio=4, seed=702, search_dist=50000, coverage=45.0), dict(search_dist=50000)),
+        (SynthConfig(dnms_per_trio=3, seed=703, search_dist=30000, coverage=12.0, site_spacing=150), dict(search_dist=30000)),
+    ]
+    for cfg, params in cases:
+        ds = make_dataset(cfg)
+        want, _ = run_port(ds, **params)
+        bp = BatchPhaser(eng, ds.sites, ds.reads, ds.pedigrees)
+        for _ in range(2):
+            got = bp.phase(copy.deepcopy(ds.dnms), **gpu_kwargs(**params))
+            assert set(got) == set(want) and len(want) > 0
+            for k in want:
+                assert norm_record(got[k]) == norm_record(want[k]), (shape, cfg.seed, k)

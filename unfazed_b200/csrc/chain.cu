@@ -11,18 +11,18 @@
 //   claim[pair] = min best[site] over the sites where the pair is an eligible target
 // The order of the next level's lists is (claiming key, position in the site's read list), which is
 // recovered with per-site ballot ranks and a rank of the sites by key -- no global sort.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace {
 
-#ifndef CH_THREADS_N
-#define CH_THREADS_N 128
-#endif
-constexpr int CH_THREADS = CH_THREADS_N;
-constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr unsigned long long KEY_NONE = ~0ull;
+#ifndef UNFZ_CHAIN_WIDE_MIN_INC
+#define UNFZ_CHAIN_WIDE_MIN_INC 2048     // incidences per DNM from which the 512-thread CTA shape is launched
+#endif
 constexpr int CH_SMEM_SITES = 128;         // per-site state lives in shared memory up to this many het sites
 
 // what a window slot carries: the key that elects a pair's last writer and the pair's dense id
@@ -278,50 +278,6 @@ __device__ int sv_support(const ChainArgs& A, const UnfzDnm& dn, int64_t r, int6
     return (before_none || after_none) ? 2 : 0;
 }
 
-// exclusive prefix of `flag` over the CTA in thread order + total
-__device__ __forceinline__ int block_prefix(bool flag, int* total) {
-    __shared__ int wsum[CH_WARPS];
-    const unsigned b = __ballot_sync(0xffffffffu, flag);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) wsum[w] = __popc(b);
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < CH_WARPS; ++i) { if (i < w) base += wsum[i]; tot += wsum[i]; }
-    __syncthreads();
-    *total = tot;
-    return base + __popc(b & ((1u << lane) - 1u));
-}
-
-// exclusive prefix SUM of v over the CTA in thread order + total
-__device__ __forceinline__ int block_prefix_sum(int v, int* total) {
-    __shared__ int wsum3[CH_WARPS];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) wsum3[w] = x;
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < CH_WARPS; ++i) { if (i < w) base += wsum3[i]; tot += wsum3[i]; }
-    __syncthreads();
-    *total = tot;
-    return base + x - v;
-}
-
-__device__ __forceinline__ int block_sum(int v) {
-    __shared__ int wsum2[CH_WARPS];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) wsum2[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int tot = 0;
-#pragma unroll
-    for (int i = 0; i < CH_WARPS; ++i) tot += wsum2[i];
-    __syncthreads();
-    return tot;
-}
 
 // site_searcher.binary_search pivot (:6-47); -1 when no site has start <= pos < end
 __device__ int bisect_pivot(const int32_t* __restrict__ spos, int n, int32_t start, int32_t end) {
@@ -370,873 +326,33 @@ __device__ unsigned long long g_ch_dbg[16];
 #endif
 
 // ------------------------------------------------------------------------------------------------
-// The breadth-first 2-colouring over DENSE pair ids, one instantiation per storage class:
-//   <uint16_t, uint8_t>  everything in shared memory (the common case: a 5 kb window at 30x has a few
-//                        hundred pairs and incidences) -- a level is a handful of shared-memory passes
-//   <int32_t, int32_t>   everything in global scratch (deep / wide windows)
-// A level touches only its FRONTIER (the pairs labelled by the previous level, through a pair-major
-// adjacency of the incidences where the pair can read an allele) and the ACTIVE sites (those some
-// frontier pair reaches), so a level costs what it does, not a rescan of every incidence.
+// the three chaining kernels, instantiated for two CTA shapes (see chain_cta.inc)
 // ------------------------------------------------------------------------------------------------
-template <typename PT, typename ST>
-struct BfsView {
-    // per dense pair
-    uint32_t* ord; int32_t* fpos; int32_t* tmp; unsigned long long* minkey; uint8_t* label;
-    // per het-site incidence (site-major): pair, site, allele codes (bits0-1 finder, bits2-3 target)
-    PT* inc_px; ST* inc_site; uint8_t* inc_al;
-    // per seed incidence: pair, site, position in the pair's site list, allele codes
-    PT* sinc_px; ST* sinc_site; uint32_t* sinc_sidx; uint8_t* sinc_al;
-    // pair-major adjacency over finder-capable entries (entry e < n_inc: incidence e, else seed incidence e - n_inc)
-    PT* adj; PT* adj_off;
-    PT* front[2];
-    // per het site
-    const int32_t* spos; const int32_t* site_off; unsigned long long* bestkey; int32_t* site_cnt; int32_t* site_base;
-    ST* active;
-};
-
-template <typename PT, typename ST>
-__device__ void bfs_levels(const BfsView<PT, ST>& V, int nh, int n_inc, int n_front0) {
-    __shared__ int s_nact, s_nnext;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int n_front = n_front0;
-    PT* fcur = V.front[0];
-    PT* fnext = V.front[1];
-    for (;;) {
-        for (int i = tid; i < nh; i += CH_THREADS) V.bestkey[i] = KEY_NONE;
-        if (tid == 0) { s_nact = 0; s_nnext = 0; }
-        __syncthreads();
-        // a. best finder per site, over the frontier only; the finder's haplotype and allele ride in the low key bits
-        for (int f = tid; f < n_front; f += CH_THREADS) {
-            const int p = (int)fcur[f];
-            const uint8_t fh = (V.label[p] & 2) ? 2 : 1;            // level 0: the "alt" visit comes first
-            const unsigned long long okey = (unsigned long long)V.ord[p] << 36;
-            const int32_t fp = V.fpos[p];
-            const int q1 = (int)V.adj_off[p + 1];
-            for (int q = (int)V.adj_off[p]; q < q1; ++q) {
-                const int e = (int)V.adj[q];
-                const bool sd = e >= n_inc;
-                const int kk = sd ? e - n_inc : e;
-                const int i = sd ? (int)V.sinc_site[kk] : (int)V.inc_site[kk];
-                if (V.spos[i] == fp) continue;
-                const uint8_t al = sd ? V.sinc_al[kk] : V.inc_al[kk];
-                const uint32_t sidx = sd ? V.sinc_sidx[kk] : (uint32_t)i;   // registered sites come in site order
-                atomicMin(V.bestkey + i, okey | ((unsigned long long)sidx << 4) | (unsigned long long)((fh << 2) | (al & 3)));
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < nh; i += CH_THREADS)
-            if (V.bestkey[i] != KEY_NONE) V.active[atomicAdd(&s_nact, 1)] = (ST)i;
-        __syncthreads();
-        const int n_act = s_nact;
-        if (n_act == 0) break;
-        // b. earliest claiming key per unlabelled pair, over the active sites' incidences
-        for (int a = warp; a < n_act; a += CH_WARPS) {
-            const int i = (int)V.active[a];
-            const unsigned long long bk = V.bestkey[i];
-            const int k1 = V.site_off[i + 1];
-            for (int k = V.site_off[i] + lane; k < k1; k += 32) {
-                const int p = (int)V.inc_px[k];
-                if (V.label[p] == 0 && (V.inc_al[k] >> 2)) atomicMin(V.minkey + p, bk);
-            }
-        }
-        __syncthreads();
-        // c. claim, one warp per active site, in the order of the site's read list
-        for (int a = warp; a < n_act; a += CH_WARPS) {
-            const int i = (int)V.active[a];
-            const unsigned long long bk = V.bestkey[i];
-            const int k0 = V.site_off[i], k1 = V.site_off[i + 1];
-            int cnt = 0;
-            for (int kb = k0; kb < k1; kb += 32) {
-                const int k = kb + lane;
-                bool claim = false;
-                int p = 0;
-                uint8_t ta = 0;
-                if (k < k1) {
-                    p = (int)V.inc_px[k];
-                    ta = V.inc_al[k] >> 2;
-                    claim = V.label[p] == 0 && ta && V.minkey[p] == bk;
-                }
-                const unsigned b = __ballot_sync(0xffffffffu, claim);
-                if (claim) {
-                    const uint8_t fh = (uint8_t)((bk >> 2) & 3), fa = (uint8_t)(bk & 3);
-                    const uint8_t nh_ = (ta == fa) ? fh : (uint8_t)(3 - fh);
-                    V.tmp[p] = (i << 8) | (nh_ << 4) | 1;
-                    V.ord[p] = (uint32_t)(cnt + __popc(b & ((1u << lane) - 1u)));   // rank inside the site
-                }
-                cnt += __popc(b);
-            }
-            if (lane == 0) V.site_cnt[i] = cnt;
-        }
-        __syncthreads();
-        // d. order of the active sites by key -> base offsets
-        int assigned = 0;
-        for (int a = tid; a < n_act; a += CH_THREADS) {
-            const int i = (int)V.active[a];
-            const int c = V.site_cnt[i];
-            int base = 0;
-            if (c > 0) {
-                const unsigned long long bk = V.bestkey[i];
-                for (int b = 0; b < n_act; ++b) {
-                    const int j = (int)V.active[b];
-                    if (V.site_cnt[j] > 0 && V.bestkey[j] < bk) base += V.site_cnt[j];
-                }
-            }
-            V.site_base[i] = base;
-            assigned += c;
-        }
-        assigned = block_sum(assigned);
-        if (assigned == 0) break;
-        // e. commit the new level; the newly labelled pairs are the next frontier
-        for (int a = warp; a < n_act; a += CH_WARPS) {
-            const int i = (int)V.active[a];
-            const unsigned long long bk = V.bestkey[i];
-            const int k1 = V.site_off[i + 1];
-            for (int k = V.site_off[i] + lane; k < k1; k += 32) {
-                const int p = (int)V.inc_px[k];
-                if (V.label[p] != 0) continue;
-                const int t = V.tmp[p];
-                if (!(t & 1)) { V.minkey[p] = KEY_NONE; continue; }      // still unlabelled: re-arm for the next level
-                if ((t >> 8) != i || V.minkey[p] != bk || !(V.inc_al[k] >> 2)) continue;
-                const uint8_t nhap = (t >> 4) & 3;
-                V.ord[p] = ((nhap == 1 ? 0u : 1u) << 24) | ((uint32_t)V.site_base[i] + V.ord[p]);   // deeper levels: "ref" list first
-                V.fpos[p] = V.spos[i];
-                V.tmp[p] = 0;
-                V.label[p] = nhap;
-                fnext[atomicAdd(&s_nnext, 1)] = (PT)p;
-            }
-        }
-        __syncthreads();
-        n_front = s_nnext;
-        { PT* t_ = fcur; fcur = fnext; fnext = t_; }
-        __syncthreads();                                   // s_nnext is cleared at the top of the next level
-    }
-    __syncthreads();
-}
-
-// The chaining of one DNM runs as three kernels, one CTA per DNM each, because its parts want opposite things:
-//   chain_setup_kernel     seeds, het-site incidences, dense pair ids, allele codes, adjacency: chains of dependent
-//                          gathers -> as many resident CTAs as possible (16 per SM, almost no shared memory)
-//   chain_bfs_kernel       the level-synchronous colouring: no gathers at all once its few KB of state sit in shared
-//                          memory -> few CTAs per SM, each fast
-//   chain_evidence_kernel  matching against the informative sites + tallies: gathers again
-// The hand-over between them is the per-DNM global scratch the wide-window mode uses anyway.
+#ifndef CH_THREADS_N            // profiling builds may override the small shape
+#define CH_THREADS_N 128
+#endif
 #ifndef CH_MINB
 #define CH_MINB 16
 #endif
-constexpr int META_INTS = 8;              // per DNM: pairs (-1: nothing to do), incidences, seed incidences, level-0 frontier, status
-
-__global__ void __launch_bounds__(CH_THREADS, CH_MINB)
-chain_setup_kernel(ChainArgs A) {
-    UNFZ_GUARD(A.guard);
-#ifdef CH_DEBUG
-    long long ch_t0 = clock64();
-#endif
-    const int d = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const UnfzDnm dn = A.dnms[d];
-    const Scratch& S0 = A.S;
-
-    UnfzTally T;
-    T.n_dad_sites = T.n_mom_sites = T.n_dad_reads = T.n_mom_reads = 0;
-    T.cnv_dad = T.cnv_mom = 0;
-    T.has_record = 0;
-    T.status = 0;
-    const int nh = A.n_het[d], nc = A.n_cand[d];
-    if (dn.kind == UNFZ_KIND_SKIP || dn.rblk < 0 || nc <= 0 || dn.seg_hi <= dn.seg_lo) {
-        if (tid == 0) {
-            A.tally[d] = T;
-            if (A.ev_need) for (int q = 0; q < 4; ++q) A.ev_need[(int64_t)q * A.n_dnms + d] = 0;
-            S0.meta[(int64_t)d * META_INTS] = -1;
-        }
-        return;
-    }
-    const int64_t lbase = A.seg_pair_off[dn.seg_lo];
-    const int32_t* H = A.het_list + lbase;
-    const uint32_t* C = A.cand_list + lbase;
-    const int64_t* off = A.off;
-    const int64_t n1 = (int64_t)A.n_dnms + 1;
-    const int64_t o_slot = off[0 * n1 + d], o_inc = off[1 * n1 + d], o_seed = off[2 * n1 + d];
-    const int64_t o_sinc = off[3 * n1 + d], o_het = off[4 * n1 + d], o_cand = off[5 * n1 + d];
-    const int64_t cap_inc = off[1 * n1 + d + 1] - o_inc, cap_seed = off[2 * n1 + d + 1] - o_seed;
-    const int64_t cap_sinc = off[3 * n1 + d + 1] - o_sinc;
-    const int64_t o_pair = o_inc + o_seed, o_adj = o_inc + o_sinc;      // pairs <= incidences + seed entries
-
-    // per-DNM views of the global scratch
-    SlotRec* rec = S0.slot + o_slot;
-    int32_t* inc_r = S0.inc_r + o_inc; int32_t* inc_x = S0.inc_x + o_inc; int32_t* inc_site = S0.inc_site + o_inc;
-    int32_t* seed_e = S0.seed_e + o_seed; uint8_t* seed_hap = S0.seed_hap + o_seed; uint32_t* seed_reg = S0.seed_reg + o_seed;
-    int32_t* x_of = S0.x_of + o_pair; int32_t* prim = S0.prim + o_pair;
-    __shared__ int32_t sh_spos[CH_SMEM_SITES], sh_site_off[CH_SMEM_SITES + 1], sh_cand_off[CH_SMEM_SITES + 1];
-    __shared__ int32_t sh_site_cnt[CH_SMEM_SITES], sh_site_base[CH_SMEM_SITES];
-    __shared__ uint8_t sh_sref[CH_SMEM_SITES], sh_salt[CH_SMEM_SITES];
-    const bool small_sites = nh <= CH_SMEM_SITES;
-    int32_t* spos = small_sites ? sh_spos : S0.spos + o_het;
-    uint8_t* sref = small_sites ? sh_sref : S0.sref + o_het;
-    uint8_t* salt = small_sites ? sh_salt : S0.salt + o_het;
-    int32_t* site_off = small_sites ? sh_site_off : S0.site_off + o_het + d;
-    int32_t* cand_off = small_sites ? sh_cand_off : S0.cand_off + o_het + d;
-    int32_t* site_cnt = small_sites ? sh_site_cnt : S0.site_cnt + o_het;
-    int32_t* site_base = small_sites ? sh_site_base : S0.site_base + o_het;
-    int32_t* cpos = S0.cpos + o_cand;
-
-    const UnfzReadCols& R = A.reads;
-    const int64_t blk_lo = R.blk_off[dn.rblk];
-    // the read window is the union of two index ranges (second one only for far-apart SV breakpoints)
-    const int64_t nd_ = A.n_dnms;
-    const int64_t a_lo = A.win[d], a_hi = A.win[nd_ + d], b_lo = A.win[2 * nd_ + d], b_hi = A.win[3 * nd_ + d];
-    auto slot_of = [&](int64_t r) -> int {
-        if (r >= a_lo && r < a_hi) return (int)(r - a_lo);
-        if (r >= b_lo && r < b_hi) return (int)((a_hi - a_lo) + (r - b_lo));
-        return -1;
-    };
-    // canonical window slot of the pair a read belongs to (the lower read index inside the window)
-    auto canon = [&](int64_t r) -> int {
-        const int64_t m = rs_mate(A.rsum, r);
-        const int sr = slot_of(r), sm = m >= 0 ? slot_of(m) : -1;
-        if (sr < 0) return sm;
-        if (sm < 0) return sr;
-        return m < r ? sm : sr;
-    };
-    const double cul = R.blk_cul[dn.rblk];
-
-    // a window slot only carries what maps a pair to its DENSE id (16 bytes, initialised lazily for the pairs
-    // that get touched: seeds + registered reads); all chaining state is indexed by the dense id
-    auto init_slot = [&](int x) { *reinterpret_cast<int4*>(rec + x) = make_int4(0, 0, -1, 0); };   // key 0, dense -1
-#ifdef CH_PREFETCH   // measured on B200: SLOWER (0.638 vs 0.595 ms at 10 k DNMs) -- the set-up is bound by sector throughput, not latency
-    // Everything below is chains of dependent gathers into the summaries and headers of the window's reads (and their
-    // mates, which lie in the same window).  Their addresses are known now: ask L2 for the lines up front, so that the
-    // gathers that follow find them there instead of paying a DRAM round trip each.
-    {
-        const char* p0 = reinterpret_cast<const char*>(A.rsum + a_lo);
-        const char* p1 = reinterpret_cast<const char*>(A.rsum + a_hi);
-        for (const char* q = p0 + (size_t)tid * 128; q < p1; q += (size_t)CH_THREADS * 128) prefetch_l2(q);
-        p0 = reinterpret_cast<const char*>(R.hdr + a_lo);
-        p1 = reinterpret_cast<const char*>(R.hdr + a_hi);
-        for (const char* q = p0 + (size_t)tid * 128; q < p1; q += (size_t)CH_THREADS * 128) prefetch_l2(q);
-        if (b_hi > b_lo) {
-            p0 = reinterpret_cast<const char*>(A.rsum + b_lo);
-            p1 = reinterpret_cast<const char*>(A.rsum + b_hi);
-            for (const char* q = p0 + (size_t)tid * 128; q < p1; q += (size_t)CH_THREADS * 128) prefetch_l2(q);
-            p0 = reinterpret_cast<const char*>(R.hdr + b_lo);
-            p1 = reinterpret_cast<const char*>(R.hdr + b_hi);
-            for (const char* q = p0 + (size_t)tid * 128; q < p1; q += (size_t)CH_THREADS * 128) prefetch_l2(q);
-        }
-    }
-#endif
-    for (int i = tid; i < nh; i += CH_THREADS) {
-        const int64_t row = H[i];
-        spos[i] = __ldg(A.sites.pos + row);
-        sref[i] = __ldg(A.sites.ref + row);
-        salt[i] = __ldg(A.sites.alt + row);
-    }
-    for (int j = tid; j < nc; j += CH_THREADS) {
-        cpos[j] = __ldg(A.sites.pos + (int64_t)(C[j] & 0x3fffffffu));   // cand_evid is zeroed by the caller
-    }
-    __syncthreads();
-
-    CH_MARK(0);
-    // ---------------------------------------------------------------- phase 1: seed reads
-    // seeds are kept as ENTRIES (one read per entry) in the order the reference appends them
-    int n_seed = 0;
-    if (dn.kind == UNFZ_KIND_SNV || dn.kind == UNFZ_KIND_INDEL) {
-        // fetch(chrom, pos-1, pos+1); after a failed fetch the reference retries with (pos, pos+1) (Q24)
-        const int64_t flo = (dn.flags & 8) ? (int64_t)dn.pos : (int64_t)dn.pos - 1;
-        const int64_t lo = A.seed_win[4 * (int64_t)d], hi = A.seed_win[4 * (int64_t)d + 1];   // from chain_size
-        for (int64_t base = lo; base < hi; base += CH_THREADS) {
-            const int64_t r = base + tid;
-            int hap = 0;
-            if (r < hi && (int64_t)A.rsum[r].end > flo && pair_ok(A, r, false))
-                hap = dn.kind == UNFZ_KIND_SNV ? seed_snv(A, dn, r) : seed_indel(A, dn, r);
-            int tot;
-            const int k = n_seed + 2 * block_prefix(hap != 0, &tot);
-            if (hap && k + 1 < cap_seed) {
-                seed_e[k] = (int32_t)r; seed_hap[k] = (uint8_t)hap;
-                seed_e[k + 1] = rs_mate(A.rsum, r); seed_hap[k + 1] = (uint8_t)hap;
-            }
-            n_seed += 2 * tot;
-        }
-        if (n_seed > cap_seed) { n_seed = (int)cap_seed & ~1; T.status |= 1; }
-    } else if (dn.kind == UNFZ_KIND_SV) {
-        int64_t e_lo = 0, e_hi = 0, e_flo = 0, e_fhi = 0;
-        for (int wdx = 0; wdx < 2; ++wdx) {
-            const int64_t position = wdx == 0 ? dn.pos : dn.end;
-            const double dlo = (double)position - cul;
-            const int64_t flo = dlo > 0.0 ? (int64_t)dlo : 0;
-            const int64_t fhi = (int64_t)((double)position + cul);
-            const int64_t lo = A.seed_win[4 * (int64_t)d + 2 * wdx], hi = A.seed_win[4 * (int64_t)d + 2 * wdx + 1];
-            if (wdx == 1) { e_lo = lo; e_hi = hi; e_flo = flo; e_fhi = fhi; }
-            for (int64_t base = lo; base < hi; base += CH_THREADS) {
-                const int64_t r = base + tid;
-                int sup = 0;
-                if (r < hi && (int64_t)A.rsum[r].end > flo && sv_goodok(A, r)) {
-                    const UnfzRead h = load_read(R.hdr + r);
-                    const int64_t m = h.mate;
-                    // name already banned by the mate earlier in this fetch?
-                    const bool skip = m < r && m >= lo && (int64_t)A.rsum[m].end > flo && sv_banned(A, m);
-                    if (!skip && !sv_bad_ends(R.cigar + h.cigar_off, h.n_cigar)) sup = sv_support(A, dn, r, position, cul);
-                }
-                int tot;
-                const int k = n_seed + 2 * block_prefix(sup != 0, &tot);
-                if (sup && k + 1 < cap_seed) {
-                    const int32_t m = rs_mate(A.rsum, r);
-                    seed_e[k] = sup == 1 ? (int32_t)r : m; seed_hap[k] = 2;
-                    seed_e[k + 1] = sup == 1 ? m : (int32_t)r; seed_hap[k + 1] = 2;
-                }
-                n_seed += 2 * tot;
-            }
-        }
-        if (n_seed > cap_seed) { n_seed = (int)cap_seed & ~1; T.status |= 1; }
-        __syncthreads();
-        // drop entries whose name was banned while scanning the END breakpoint (:588-591), in place
-        int kept = 0;
-        for (int base = 0; base < n_seed; base += CH_THREADS) {
-            const int k = base + tid;
-            bool keep = false;
-            int32_t e = 0;
-            if (k < n_seed) {
-                e = seed_e[k];
-                const int64_t m = rs_mate(A.rsum, e);
-                auto in_end_fetch = [&](int64_t z) {
-                    return z >= e_lo && z < e_hi && (int64_t)A.rsum[z].end > e_flo && (int64_t)rs_start(A.rsum, z) < e_fhi;
-                };
-                const bool banned = (in_end_fetch(e) && sv_banned(A, e)) || (m >= 0 && in_end_fetch(m) && sv_banned(A, m));
-                keep = !banned;
-            }
-            int tot;
-            const int kk = kept + block_prefix(keep, &tot);     // block_prefix syncs: all reads precede the writes
-            if (keep) { seed_e[kk] = e; seed_hap[kk] = 2; }
-            kept += tot;
-            __syncthreads();
-        }
-        n_seed = kept < 2 ? 0 : kept;
-    }
-    __syncthreads();
-
-    CH_MARK(1);
-    for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) init_slot(x); }
-    __syncthreads();
-    int n_inc = 0, n_sinc = 0;
-    int P = 0;                                     // dense pairs
-    const int nh_reg = A.no_extended ? 0 : nh;     // --no-extended: seeds are the haplotype lists
-    if (!A.no_extended) {
-        // ------------------------------------------------------------ phase 2: het-site incidences
-        // (a) candidate read range of every het site: fetch(chrom, pos, pos+1) as index range
-        for (int i = tid; i < nh; i += CH_THREADS) {          // found by chain_size, no search here
-            site_base[i] = A.site_lo[lbase + i];
-            site_cnt[i] = A.site_n[lbase + i];
-        }
-        __syncthreads();
-        // (b) exclusive scan of the range sizes (warp 0), candidates are flattened site-major
-        if (warp == 0) {
-            int run = 0;
-            for (int b0 = 0; b0 < nh; b0 += 32) {
-                const int i = b0 + lane;
-                const int v = i < nh ? site_cnt[i] : 0;
-                int x = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-                if (i < nh) cand_off[i] = run + x - v;
-                run += __shfl_sync(0xffffffffu, x, 31);
-            }
-            if (lane == 0) cand_off[nh] = run;
-        }
-        for (int i = tid; i <= nh; i += CH_THREADS) site_off[i] = 0x7fffffff;
-        __syncthreads();
-        const int n_candidates = cand_off[nh];
-    CH_MARK(2);
-        // (c) one ordered pass over all (site, read) candidates.  The filter (three dependent gathers per
-        // candidate) runs without any barrier: each batch of CH_THREADS candidates leaves only its four warp
-        // ballots in shared memory; one scan over the ballots then gives every survivor its slot, and a second,
-        // load-free pass writes them in candidate order.
-        constexpr int CH_SB = 32;                                  // batches per round (ballots kept in smem)
-        __shared__ uint32_t s_bal[CH_SB * CH_WARPS];
-        __shared__ int32_t s_bpre[CH_SB * CH_WARPS];
-        __shared__ int32_t s_btot;
-        for (int c0 = 0; c0 < n_candidates; c0 += CH_SB * CH_THREADS) {
-            const int nb = min(CH_SB, (n_candidates - c0 + CH_THREADS - 1) / CH_THREADS);
-            int i0 = 0;                                            // site of this thread's first candidate
-            if (c0 + tid < n_candidates) {
-                int lo = 0, hi = nh;                               // last i with cand_off[i] <= c
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_off[mid] <= c0 + tid) lo = mid; else hi = mid; }
-                i0 = lo;
-            }
-            int i = i0;
-#pragma unroll 4
-            for (int b = 0; b < nb; ++b) {
-                const int c = c0 + b * CH_THREADS + tid;
-                bool ok = false;
-                if (c < n_candidates) {
-                    while (cand_off[i + 1] <= c) ++i;              // candidates are site-major: the cursor only moves forward
-                    const int64_t r = blk_lo + site_base[i] + (c - cand_off[i]);
-                    const int32_t p = spos[i];
-                    bool ov = A.rsum[r].end > p;
-                    if (ov && site_cnt[i] > A.ext_goal) {          // Q2: `i > EXTENDED_RB_READ_GOAL` (never in practice)
-                        int idx = 0;
-                        for (int64_t q = blk_lo + site_base[i]; q < r; ++q) idx += A.rsum[q].end > p;
-                        ov = idx <= A.ext_goal;
-                    }
-                    ok = ov && pair_ok(A, r, true);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                if (lane == 0) s_bal[b * CH_WARPS + warp] = bal;
-            }
-            __syncthreads();
-            if (warp == 0) {                                       // exclusive prefix of the ballot populations
-                int run = 0;
-                for (int j0 = 0; j0 < nb * CH_WARPS; j0 += 32) {
-                    const int j = j0 + lane;
-                    const int v = j < nb * CH_WARPS ? __popc(s_bal[j]) : 0;
-                    int x = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-                    if (j < nb * CH_WARPS) s_bpre[j] = run + x - v;
-                    run += __shfl_sync(0xffffffffu, x, 31);
-                }
-                if (lane == 0) s_btot = run;
-            }
-            __syncthreads();
-            i = i0;
-            for (int b = 0; b < nb; ++b) {
-                const int c = c0 + b * CH_THREADS + tid;
-                const unsigned bal = s_bal[b * CH_WARPS + warp];
-                if (c < n_candidates && ((bal >> lane) & 1u)) {
-                    while (cand_off[i + 1] <= c) ++i;
-                    const int64_t r = blk_lo + site_base[i] + (c - cand_off[i]);
-                    const int k = n_inc + s_bpre[b * CH_WARPS + warp] + __popc(bal & ((1u << lane) - 1u));
-                    if (k < cap_inc) {
-                        inc_r[k] = (int32_t)r;
-                        inc_x[k] = canon(r);
-                        inc_site[k] = i;
-                    }
-                }
-            }
-            n_inc += s_btot;
-            __syncthreads();                                       // the ballots are reused by the next round
-        }
-    CH_MARK(3);
-        if (n_inc > cap_inc) { n_inc = (int)cap_inc; T.status |= 2; }
-        __syncthreads();
-        for (int k = tid; k < n_inc; k += CH_THREADS) {
-            if (k == 0 || inc_site[k - 1] != inc_site[k]) site_off[inc_site[k]] = k;
-            init_slot(inc_x[k]);                                    // idempotent
-        }
-        __syncthreads();
-        // fetched_reads[name] = [read, mate]: the last writer (highest site) wins (Q18)
-        for (int k = tid; k < n_inc; k += CH_THREADS)
-            atomicMax(&rec[inc_x[k]].key, ((unsigned long long)(uint32_t)(inc_site[k] + 1) << 32) | (uint32_t)inc_r[k]);
-        __syncthreads();
-        // the winning incidence of a pair gives it its dense id (ids in incidence order) and its primary read
-        for (int base = 0; base < n_inc; base += CH_THREADS) {
-            const int k = base + tid;
-            bool rep = false;
-            int x = 0;
-            if (k < n_inc) {
-                x = inc_x[k];
-                rep = rec[x].key == (((unsigned long long)(uint32_t)(inc_site[k] + 1) << 32) | (uint32_t)inc_r[k]);
-            }
-            int tot;
-            const int id = P + block_prefix(rep, &tot);
-            if (rep) { rec[x].dense = id; x_of[id] = x; prim[id] = inc_r[k]; }
-            P += tot;
-        }
-        if (tid == 0) {                                             // empty sites inherit the next offset
-            int nxt = n_inc;
-            site_off[nh] = n_inc;
-            for (int i = nh - 1; i >= 0; --i) { if (site_off[i] == 0x7fffffff) site_off[i] = nxt; else nxt = site_off[i]; }
-        }
-        __syncthreads();
-    }
-    CH_MARK(4);
-    // ------------------------------------------------------------ phase 3: seed registration
-    // Entries register in the order "ref" list then "alt" list (:226-249); the level-0 visit order
-    // is "alt" list first (Q19).  Everything is resolved with order keys instead of a serial loop:
-    //   reg(k)   = position of entry k in the registration order
-    //   prim[p]  = entry with the largest reg  (last writer wins)
-    //   ord[p]   = smallest visit position of the pair
-    int n_ref_entries = 0;
-    for (int base = 0; base < n_seed; base += CH_THREADS) {
-        const int k = base + tid;
-        int tot;
-        block_prefix(k < n_seed && seed_hap[k] == 1, &tot);
-        n_ref_entries += tot;
-    }
-    for (int k = tid; k < n_inc; k += CH_THREADS) rec[inc_x[k]].key = 0ull;
-    for (int k = tid; k < n_seed; k += CH_THREADS) { const int x = canon(seed_e[k]); if (x >= 0) rec[x].key = 0ull; }
-    __syncthreads();
-    {
-        // pass A: registration keys; the entry with the largest one is the pair's last writer
-        int ref_seen = 0, alt_seen = 0;
-        for (int base = 0; base < n_seed; base += CH_THREADS) {
-            const int k = base + tid;
-            const bool live = k < n_seed;
-            const int hap = live ? seed_hap[k] : 0;
-            int tot_ref, tot_alt;
-            const int pr = block_prefix(hap == 1, &tot_ref);
-            const int pa = block_prefix(hap == 2, &tot_alt);
-            if (live) {
-                const int32_t e = seed_e[k];
-                const int x = canon(e);
-                const unsigned reg = hap == 1 ? (unsigned)(ref_seen + pr) : (unsigned)(n_ref_entries + alt_seen + pa);
-                // visit order at level 0: alt entries first, then ref entries
-                const unsigned visit = hap == 2 ? (unsigned)(alt_seen + pa) : (unsigned)(ref_seen + pr);
-                seed_reg[k] = reg;
-                seed_e[k] = x >= 0 ? e : -1 - e;                       // entries outside the window are inert
-                if (x >= 0) atomicMax(&rec[x].key, ((unsigned long long)(reg + 1u) << 32) | (uint32_t)e);
-                (void)visit;
-            }
-            ref_seen += tot_ref;
-            alt_seen += tot_alt;
-        }
-        __syncthreads();
-        // pass B: dense ids of the pairs only seeds touch; the last writer's read becomes the primary read
-        for (int base = 0; base < n_seed; base += CH_THREADS) {
-            const int k = base + tid;
-            bool rep = false, fresh = false;
-            int x = -1;
-            int32_t e = -1;
-            if (k < n_seed && (e = seed_e[k]) >= 0) {
-                x = canon(e);
-                rep = rec[x].key == (((unsigned long long)(seed_reg[k] + 1u) << 32) | (uint32_t)e);
-                fresh = rep && rec[x].dense < 0;
-            }
-            int tot;
-            const int id = P + block_prefix(fresh, &tot);
-            if (fresh) { rec[x].dense = id; x_of[id] = x; }
-            if (rep) prim[fresh ? id : rec[x].dense] = e;
-            P += tot;
-        }
-        __syncthreads();
-    }
-    if ((int64_t)P > cap_inc + cap_seed) { P = (int)(cap_inc + cap_seed); T.status |= 8; }     // cannot happen: one id per entry at most
-
-    // the rest of the set-up is the same code over either view
-    int n_front0 = 0;
-    auto setup = [&](auto& V) {
-        using PT = typename std::remove_reference<decltype(V.inc_px[0])>::type;
-        using ST = typename std::remove_reference<decltype(V.inc_site[0])>::type;
-        __shared__ int s_front;
-        for (int p = tid; p < P; p += CH_THREADS) {
-            V.ord[p] = 0xffffffffu; V.fpos[p] = -1; V.tmp[p] = 0; V.minkey[p] = KEY_NONE; V.label[p] = 0;
-        }
-        if (tid == 0) s_front = 0;
-        // incidences: window slot -> dense pair (in global mode the column is rewritten in place)
-        for (int k = tid; k < n_inc; k += CH_THREADS) {
-            const int px = rec[inc_x[k]].dense;
-            const int st = inc_site[k];
-            V.inc_px[k] = (PT)px;
-            V.inc_site[k] = (ST)st;
-        }
-        __syncthreads();
-        // pass C over the seed entries: labels, visit order, level-0 frontier, seed incidences
-        int ref_seen = 0, alt_seen = 0, ns_total = 0;
-        for (int base = 0; base < n_seed; base += CH_THREADS) {
-            const int k = base + tid;
-            const bool live = k < n_seed;
-            const int hap = live ? seed_hap[k] : 0;
-            int tot_ref, tot_alt;
-            const int pr = block_prefix(hap == 1, &tot_ref);
-            const int pa = block_prefix(hap == 2, &tot_alt);
-            int n_match = 0, piv = -1, px = -1;
-            int32_t st = 0, en = 0;
-            unsigned reg = 0;
-            if (live && seed_e[k] >= 0) {
-                const int32_t e = seed_e[k];
-                const int x = canon(e);
-                px = rec[x].dense;
-                reg = seed_reg[k];
-                const unsigned visit = hap == 2 ? (unsigned)(alt_seen + pa) : (unsigned)(ref_seen + pr);
-                atomicMin(V.ord + px, (hap == 2 ? 0u : (1u << 24)) | (visit & 0xffffffu));
-                atomicOr(V.tmp + px, hap);                          // haplotype bits gather in tmp (word atomics), see below
-                if (rec[x].key == (((unsigned long long)(reg + 1u) << 32) | (uint32_t)e))     // once per pair
-                    V.front[0][atomicAdd(&s_front, 1)] = (PT)px;
-                if (nh_reg > 0) {
-                    st = rs_start(A.rsum, e);
-                    en = A.rsum[e].end;
-                    piv = bisect_pivot(spos, nh_reg, st, en);
-                    if (piv >= 0) {
-                        n_match = 1;
-                        for (int j = piv + 1; j < nh_reg && st <= spos[j] && spos[j] <= en; ++j) ++n_match;
-                        for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) ++n_match;
-                    }
-                }
-            }
-            // seed incidences may be stored in any order: their position in read_sites[x] is carried by
-            // the order key (after all registered sites, then by registration order, then by the
-            // pivot / right / left order of binary_search, Q16)
-            int tm;
-            const int off_m = block_prefix_sum(n_match, &tm);
-            if (n_match > 0) {
-                int w = 0;
-                const unsigned keybase = (unsigned)nh + reg * (unsigned)(nh + 1);
-                const int dst0 = ns_total + off_m;
-                auto push = [&](int i) {
-                    const int dst = dst0 + w;
-                    if (dst < cap_sinc) { V.sinc_px[dst] = (PT)px; V.sinc_site[dst] = (ST)i; V.sinc_sidx[dst] = keybase + (unsigned)w; }
-                    ++w;
-                };
-                push(piv);
-                for (int j = piv + 1; j < nh_reg && st <= spos[j] && spos[j] <= en; ++j) push(j);
-                for (int j = piv - 1; j >= 0 && st <= spos[j] && spos[j] <= en; --j) push(j);
-            }
-            ref_seen += tot_ref;
-            alt_seen += tot_alt;
-            ns_total += tm;
-        }
-        n_sinc = ns_total;
-        if (n_sinc > cap_sinc) { n_sinc = (int)cap_sinc; T.status |= 4; }
-        __syncthreads();
-        n_front0 = s_front;
-        for (int p = tid; p < P; p += CH_THREADS) { V.label[p] = (uint8_t)V.tmp[p]; V.tmp[p] = 0; }
-        __syncthreads();
-        if (A.no_extended) return;
-    CH_MARK(5);
-        // -------------------------------------------------------- phase 3.5: allele codes + pair-major adjacency
-        // tmp[p] counts the entries where pair p can read an allele (finder role), then serves as the fill cursor
-        for (int k = tid; k < n_inc; k += CH_THREADS) {
-            const int i = (int)V.inc_site[k], px = (int)V.inc_px[k];
-            const uint8_t al = allele_info(A, S0, (int64_t)prim[px], (int64_t)H[i], (char)sref[i], (char)salt[i]);
-            V.inc_al[k] = al;
-            if (al & 3) atomicAdd(V.tmp + px, 1);
-        }
-        for (int k = tid; k < n_sinc; k += CH_THREADS) {
-            const int i = (int)V.sinc_site[k], px = (int)V.sinc_px[k];
-            const uint8_t al = allele_info(A, S0, (int64_t)prim[px], (int64_t)H[i], (char)sref[i], (char)salt[i]);
-            V.sinc_al[k] = al;
-            if (al & 3) atomicAdd(V.tmp + px, 1);
-        }
-        __syncthreads();
-        int run = 0;
-        for (int base = 0; base < P; base += CH_THREADS) {
-            const int p = base + tid;
-            const int c = p < P ? V.tmp[p] : 0;
-            int tot;
-            const int o = run + block_prefix_sum(c, &tot);
-            if (p < P) { V.adj_off[p] = (PT)o; V.tmp[p] = 0; }
-            run += tot;
-        }
-        if (tid == 0) V.adj_off[P] = (PT)run;
-        __syncthreads();
-        for (int k = tid; k < n_inc; k += CH_THREADS)
-            if (V.inc_al[k] & 3) { const int px = (int)V.inc_px[k]; V.adj[(int)V.adj_off[px] + atomicAdd(V.tmp + px, 1)] = (PT)k; }
-        for (int k = tid; k < n_sinc; k += CH_THREADS)
-            if (V.sinc_al[k] & 3) { const int px = (int)V.sinc_px[k]; V.adj[(int)V.adj_off[px] + atomicAdd(V.tmp + px, 1)] = (PT)(n_inc + k); }
-        __syncthreads();
-        for (int p = tid; p < P; p += CH_THREADS) V.tmp[p] = 0;
-        __syncthreads();
-    };
-    BfsView<int32_t, int32_t> VG;
-    VG.ord = S0.p_ord + o_pair; VG.fpos = S0.p_fpos + o_pair; VG.tmp = S0.p_tmp + o_pair; VG.minkey = S0.p_minkey + o_pair;
-    VG.label = S0.p_label + o_pair;
-    VG.inc_px = inc_x; VG.inc_site = inc_site; VG.inc_al = S0.inc_al + o_inc;          // the slot column becomes the pair column
-    VG.sinc_px = S0.sinc_px + o_sinc; VG.sinc_site = S0.sinc_site + o_sinc;
-    VG.sinc_sidx = S0.sinc_sidx + o_sinc; VG.sinc_al = S0.sinc_al + o_sinc;
-    VG.adj = S0.adj + o_adj; VG.adj_off = S0.adj_off + o_pair + 2 * (int64_t)d;
-    VG.front[0] = S0.front0 + o_pair; VG.front[1] = S0.front1 + o_pair;
-    VG.spos = spos; VG.site_off = site_off; VG.bestkey = nullptr; VG.site_cnt = site_cnt; VG.site_base = site_base;
-    VG.active = S0.active + o_het;
-
-    setup(VG);
-    __syncthreads();
-    // hand-over: what the next two kernels need and only shared memory holds
-    if (small_sites) {
-        int32_t* g_spos = S0.spos + o_het;
-        int32_t* g_off = S0.site_off + o_het + d;
-        for (int i = tid; i < nh; i += CH_THREADS) g_spos[i] = spos[i];
-        for (int i = tid; i <= nh; i += CH_THREADS) g_off[i] = A.no_extended ? 0 : site_off[i];
-    }
-    if (tid == 0) {
-        int32_t* m = S0.meta + (int64_t)d * META_INTS;
-        m[0] = P; m[1] = n_inc; m[2] = n_sinc; m[3] = n_front0; m[4] = T.status;
-    }
-    CH_MARK(6);
-}
-
-// per-pair state, incidence views and adjacency of the shared-memory mode
-constexpr int SM_P = 512;                 // dense pairs
-constexpr int SM_I = 768;                 // het-site incidences
-constexpr int SM_SI = 256;                // seed incidences
 #ifndef CH_BFS_MINB
 #define CH_BFS_MINB 8
 #endif
+#define CH_NS cta_small
+#include "chain_cta.inc"
+#undef CH_NS
+#undef CH_THREADS_N
+#undef CH_MINB
+#undef CH_BFS_MINB
+#define CH_NS cta_wide
+#define CH_THREADS_N 512
+#define CH_MINB 4
+#define CH_BFS_MINB 2
+#include "chain_cta.inc"
+#undef CH_NS
+#undef CH_THREADS_N
+#undef CH_MINB
+#undef CH_BFS_MINB
 
-__global__ void __launch_bounds__(CH_THREADS, CH_BFS_MINB)
-chain_bfs_kernel(ChainArgs A) {
-    UNFZ_GUARD(A.guard);
-    const int d = blockIdx.x;
-    const int tid = threadIdx.x;
-    const Scratch& S0 = A.S;
-    const int32_t* meta = S0.meta + (int64_t)d * META_INTS;
-    const int P = meta[0], n_inc = meta[1], n_sinc = meta[2], n_front0 = meta[3];
-    if (P <= 0 || n_front0 <= 0 || A.no_extended) return;          // nothing can spread (labels of the seeds are final)
-    const int nh = A.n_het[d];
-    const int64_t* off = A.off;
-    const int64_t n1 = (int64_t)A.n_dnms + 1;
-    const int64_t o_inc = off[1 * n1 + d], o_seed = off[2 * n1 + d], o_sinc = off[3 * n1 + d], o_het = off[4 * n1 + d];
-    const int64_t o_pair = o_inc + o_seed, o_adj = o_inc + o_sinc;
-    BfsView<int32_t, int32_t> G;
-    G.ord = S0.p_ord + o_pair; G.fpos = S0.p_fpos + o_pair; G.tmp = S0.p_tmp + o_pair; G.minkey = S0.p_minkey + o_pair;
-    G.label = S0.p_label + o_pair;
-    G.inc_px = S0.inc_x + o_inc; G.inc_site = S0.inc_site + o_inc; G.inc_al = S0.inc_al + o_inc;
-    G.sinc_px = S0.sinc_px + o_sinc; G.sinc_site = S0.sinc_site + o_sinc;
-    G.sinc_sidx = S0.sinc_sidx + o_sinc; G.sinc_al = S0.sinc_al + o_sinc;
-    G.adj = S0.adj + o_adj; G.adj_off = S0.adj_off + o_pair + 2 * (int64_t)d;
-    G.front[0] = S0.front0 + o_pair; G.front[1] = S0.front1 + o_pair;
-    G.spos = S0.spos + o_het; G.site_off = S0.site_off + o_het + d; G.bestkey = S0.bestkey + o_het;
-    G.site_cnt = S0.site_cnt + o_het; G.site_base = S0.site_base + o_het; G.active = S0.active + o_het;
-    const int n_adj = G.adj_off[P];
-    if (!(nh <= CH_SMEM_SITES && P <= SM_P && n_inc <= SM_I && n_sinc <= SM_SI)) {
-        bfs_levels(G, nh, n_inc, n_front0);                        // wide window: the state stays in global scratch
-        return;
-    }
-    // stage the DNM's chaining state (a few KB, contiguous arrays) into shared memory, colour there, write the labels back
-    __shared__ __align__(8) unsigned long long sm_minkey[SM_P], sm_bestkey[CH_SMEM_SITES];
-    __shared__ uint32_t sm_ord[SM_P], sm_sinc_sidx[SM_SI];
-    __shared__ int32_t sm_fpos[SM_P], sm_tmp[SM_P], sm_spos[CH_SMEM_SITES], sm_site_off[CH_SMEM_SITES + 1];
-    __shared__ int32_t sm_site_cnt[CH_SMEM_SITES], sm_site_base[CH_SMEM_SITES];
-    __shared__ uint16_t sm_inc_px[SM_I], sm_sinc_px[SM_SI], sm_adj[SM_I + SM_SI], sm_adj_off[SM_P + 2], sm_front[2][SM_P];
-    __shared__ uint8_t sm_label[SM_P], sm_inc_site[SM_I], sm_inc_al[SM_I], sm_sinc_site[SM_SI], sm_sinc_al[SM_SI];
-    __shared__ uint8_t sm_active[CH_SMEM_SITES];
-    for (int p = tid; p < P; p += CH_THREADS) {
-        sm_ord[p] = G.ord[p]; sm_label[p] = G.label[p]; sm_adj_off[p] = (uint16_t)G.adj_off[p];
-        sm_fpos[p] = -1; sm_tmp[p] = 0; sm_minkey[p] = KEY_NONE;
-    }
-    if (tid == 0) sm_adj_off[P] = (uint16_t)n_adj;
-    for (int k = tid; k < n_inc; k += CH_THREADS) {
-        sm_inc_px[k] = (uint16_t)G.inc_px[k]; sm_inc_site[k] = (uint8_t)G.inc_site[k]; sm_inc_al[k] = G.inc_al[k];
-    }
-    for (int k = tid; k < n_sinc; k += CH_THREADS) {
-        sm_sinc_px[k] = (uint16_t)G.sinc_px[k]; sm_sinc_site[k] = (uint8_t)G.sinc_site[k];
-        sm_sinc_sidx[k] = G.sinc_sidx[k]; sm_sinc_al[k] = G.sinc_al[k];
-    }
-    for (int q = tid; q < n_adj; q += CH_THREADS) sm_adj[q] = (uint16_t)G.adj[q];
-    for (int f = tid; f < n_front0; f += CH_THREADS) sm_front[0][f] = (uint16_t)G.front[0][f];
-    for (int i = tid; i < nh; i += CH_THREADS) sm_spos[i] = G.spos[i];
-    for (int i = tid; i <= nh; i += CH_THREADS) sm_site_off[i] = G.site_off[i];
-    __syncthreads();
-    BfsView<uint16_t, uint8_t> V;
-    V.ord = sm_ord; V.fpos = sm_fpos; V.tmp = sm_tmp; V.minkey = sm_minkey; V.label = sm_label;
-    V.inc_px = sm_inc_px; V.inc_site = sm_inc_site; V.inc_al = sm_inc_al;
-    V.sinc_px = sm_sinc_px; V.sinc_site = sm_sinc_site; V.sinc_sidx = sm_sinc_sidx; V.sinc_al = sm_sinc_al;
-    V.adj = sm_adj; V.adj_off = sm_adj_off; V.front[0] = sm_front[0]; V.front[1] = sm_front[1];
-    V.spos = sm_spos; V.site_off = sm_site_off; V.bestkey = sm_bestkey; V.site_cnt = sm_site_cnt; V.site_base = sm_site_base;
-    V.active = sm_active;
-    bfs_levels(V, nh, n_inc, n_front0);
-    for (int p = tid; p < P; p += CH_THREADS) G.label[p] = sm_label[p];
-}
-
-__global__ void __launch_bounds__(CH_THREADS, CH_MINB)
-chain_evidence_kernel(ChainArgs A) {
-    UNFZ_GUARD(A.guard);
-#ifdef CH_DEBUG
-    long long ch_t0 = clock64();
-#endif
-    const int d = blockIdx.x;
-    const int tid = threadIdx.x;
-    const Scratch& S0 = A.S;
-    const int32_t* meta = S0.meta + (int64_t)d * META_INTS;
-    const int P = meta[0];
-    if (P < 0) return;                                 // skipped by the set-up kernel (tally already written)
-    const UnfzDnm dn = A.dnms[d];
-    UnfzTally T;
-    T.n_dad_sites = T.n_mom_sites = T.n_dad_reads = T.n_mom_reads = 0;
-    T.cnv_dad = T.cnv_mom = 0;
-    T.has_record = 0;
-    T.status = meta[4];
-    const int nc = A.n_cand[d];
-    const int64_t lbase = A.seg_pair_off[dn.seg_lo];
-    const uint32_t* C = A.cand_list + lbase;
-    const int64_t* off = A.off;
-    const int64_t n1 = (int64_t)A.n_dnms + 1;
-    const int64_t o_slot = off[0 * n1 + d], o_inc = off[1 * n1 + d], o_seed = off[2 * n1 + d], o_cand = off[5 * n1 + d];
-    const int64_t o_pair = o_inc + o_seed;
-    uint8_t* label_out = A.slot_label + o_slot; uint8_t* evid_out = A.slot_evid + o_slot;
-    const int32_t* x_of = S0.x_of + o_pair; const int32_t* prim = S0.prim + o_pair;
-    const int32_t* cpos = S0.cpos + o_cand;
-    uint8_t* cev = A.cand_evid + lbase;
-
-    CH_MARK(7);
-    // ---------------------------------------------------------------- phase 5: matching + evidence
-    int has_rec = 0, dr = 0, mr = 0;
-    const uint8_t* final_label = S0.p_label + o_pair;
-    for (int p = tid; p < P; p += CH_THREADS) {
-        const uint8_t lab = final_label[p];
-        if (!lab) continue;
-        const int64_t e0 = prim[p];
-        const int64_t ents[2] = {e0, (int64_t)rs_mate(A.rsum, e0)};
-        uint8_t ev = 0;
-        for (int t = 0; t < 2; ++t) {
-            const int64_t e = ents[t];
-            if (e < 0) continue;
-            const int32_t st = rs_start(A.rsum, e), en = A.rsum[e].end;
-            int lb = 0, hi = nc;
-            while (lb < hi) { const int mid = (lb + hi) >> 1; if (cpos[mid] < st) lb = mid + 1; else hi = mid; }
-            if (lb >= nc || cpos[lb] >= en) continue;           // binary_search finds nothing
-            int ub = lb;
-            while (ub < nc && cpos[ub] <= en) ++ub;              // neighbour rule (Q16)
-            bool consistent = true;
-            for (int j = lb + 1; j < ub; ++j)
-                if ((C[j] ^ C[lb]) & 0x80000000u) { consistent = false; break; }
-            if (!consistent) continue;
-            has_rec = 1;
-            for (int j = lb; j < ub; ++j) {
-                const uint32_t cw = C[j];
-                const int64_t row = cw & 0x3fffffffu;
-                const uint32_t h = hit_lookup(A, e, row);
-                if (!(h & 0xffffu)) continue;
-                const char c = hit_char(h);
-                bool origin_ref;
-                if (c == (char)__ldg(A.sites.ref + row)) origin_ref = true;
-                else if (c == (char)__ldg(A.sites.alt + row)) origin_ref = false;
-                else continue;
-                const bool alt_is_dad = (cw & 0x80000000u) != 0;
-                uint8_t bits = 0;
-                for (int hp = 1; hp <= 2; ++hp) {
-                    if (!(lab & hp)) continue;
-                    const bool to_alt = origin_ref == (hp == 1);
-                    bits |= (to_alt == alt_is_dad) ? 1 : 2;       // 1: dad, 2: mom
-                }
-                ev |= bits;
-                unsigned* wp = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(cev + j) & ~(uintptr_t)3);
-                atomicOr(wp, (unsigned)bits << (8 * (reinterpret_cast<uintptr_t>(cev + j) & 3)));
-            }
-        }
-        const int x = x_of[p];
-        label_out[x] = lab;                                      // zero-filled by the caller: only labelled pairs are written
-        evid_out[x] = ev;
-        dr += ev & 1;
-        mr += (ev >> 1) & 1;
-    }
-    __syncthreads();
-
-    CH_MARK(8);
-    // ---------------------------------------------------------------- phase 6: tally
-    int ds = 0, ms = 0, esd = 0, esm = 0;
-    for (int j = tid; j < nc; j += CH_THREADS) {
-        const uint8_t b = cev[j];
-        esd += b & 1;
-        esm += (b >> 1) & 1;
-        for (int bit = 1; bit <= 2; ++bit) {
-            if (!(b & bit)) continue;
-            bool first = true;                      // unique str(pos): count the first duplicate only
-            for (int j2 = j - 1; j2 >= 0 && cpos[j2] == cpos[j]; --j2)
-                if (cev[j2] & bit) { first = false; break; }
-            if (first) { if (bit == 1) ++ds; else ++ms; }
-        }
-    }
-    if (A.ev_need) { esd = block_sum(esd); esm = block_sum(esm); }
-    ds = block_sum(ds); ms = block_sum(ms); dr = block_sum(dr); mr = block_sum(mr);
-    has_rec = block_sum(has_rec);
-    if (tid == 0) {
-        T.n_dad_sites = ds; T.n_mom_sites = ms; T.n_dad_reads = dr; T.n_mom_reads = mr;
-        T.has_record = has_rec > 0;
-        A.tally[d] = T;
-        if (A.ev_need) {                        // list lengths of unfz_evidence_lists (site entries keep duplicates)
-            const int64_t n = A.n_dnms;
-            A.ev_need[d] = dr; A.ev_need[n + d] = mr; A.ev_need[2 * n + d] = esd; A.ev_need[3 * n + d] = esm;
-        }
-    }
-    CH_MARK(9);
-}
 
 // ------------------------------------------------------------------------------------------------
 // evidence lists: the pairs and informative sites behind the tallies, per DNM and per parent, in
@@ -1606,14 +722,30 @@ extern "C" int unfz_chain_tally(UnfzCtx* ctx, const UnfzDnm* dnms, int32_t n_dnm
     if ((int64_t)(base - (uintptr_t)scratch) + total > scratch_bytes) return unfz_fail(ctx, -20, "chain scratch too small");
     A.guard = ctx->guard;
     if (!ctx->chain_carveout_set) {           // 8 CTAs x 25 KB of static shared memory per SM need the large carve-out
-        UNFZ_CHECK(ctx, cudaFuncSetAttribute(chain_bfs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        UNFZ_CHECK(ctx, cudaFuncSetAttribute(cta_small::chain_bfs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        UNFZ_CHECK(ctx, cudaFuncSetAttribute(cta_wide::chain_bfs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         ctx->chain_carveout_set = true;
     }
-    chain_setup_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    // CTA shape: h_totals[1] is the incidence capacity of the batch (exact, or the engine's speculative bound).  A DNM with
+    // thousands of (het site x read) incidences keeps 512 threads busy; measured on the 50 kb / 60x stress (about 20 k
+    // incidences per DNM, 500 DNMs): 1.03 ms with 128-thread CTAs, 0.58 ms with 512; on 5 kb / 30x windows (450 per DNM,
+    // 10 k DNMs) the small shape wins (0.56 vs 0.63 ms at 256 threads).
+    bool wide = h_totals[1] / n_dnms >= UNFZ_CHAIN_WIDE_MIN_INC;
+    if (const char* force = getenv("UNFZ_CHAIN_SHAPE")) wide = force[0] == 'w' ? true : (force[0] == 's' ? false : wide);   // tests
+    if (wide) {
+        cta_wide::chain_setup_kernel<<<n_dnms, cta_wide::CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+        UNFZ_LAUNCH_CHECK(ctx);
+        cta_wide::chain_bfs_kernel<<<n_dnms, cta_wide::CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+        UNFZ_LAUNCH_CHECK(ctx);
+        cta_wide::chain_evidence_kernel<<<n_dnms, cta_wide::CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+        UNFZ_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    cta_small::chain_setup_kernel<<<n_dnms, cta_small::CH_THREADS, 0, (cudaStream_t)stream>>>(A);
     UNFZ_LAUNCH_CHECK(ctx);
-    chain_bfs_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    cta_small::chain_bfs_kernel<<<n_dnms, cta_small::CH_THREADS, 0, (cudaStream_t)stream>>>(A);
     UNFZ_LAUNCH_CHECK(ctx);
-    chain_evidence_kernel<<<n_dnms, CH_THREADS, 0, (cudaStream_t)stream>>>(A);
+    cta_small::chain_evidence_kernel<<<n_dnms, cta_small::CH_THREADS, 0, (cudaStream_t)stream>>>(A);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

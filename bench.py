@@ -72,6 +72,9 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=0, help="DNMs in the CPU-baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-parity", action="store_true",
+                    help="after the timed legs, phase EVERY DNM of the workload with the oracle port (all host cores) and compare "
+                         "all record dicts of the timed end-to-end batch with it (N=1; adds about a minute)")
     ap.add_argument("--no-saturating", action="store_true", help="skip the 2^25-pair classifier measurement")
     return ap.parse_args()
 
@@ -117,8 +120,9 @@ def make_ds(args, rank, world, n_dnms=None):
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a
-    thread (the timed region of this benchmark is tens of milliseconds, too short for nvidia-smi -lms)."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 5 ms from a
+    thread (the timed region of this benchmark is tens of milliseconds, too short for nvidia-smi -lms; a
+    tighter poll showed up in the measurement -- NVML queries take driver locks the launches also need)."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -159,7 +163,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def stop(self):
         self.stop_flag = True
@@ -222,6 +226,39 @@ def cpu_sample_run(ds, dnms, args):
         port.find(snv, ds.pedigrees, ds.sites, p, p.search_dist, whole_region=False)
     t_find = time.perf_counter() - t0
     return recs, cold, warm, t_find
+
+
+def _port_shard(idx):
+    from oracle import port
+    ds, p, shard = _W["ds"], _W["params"], _W["shards"][idx]
+    return port.Phaser(ds.sites, ds.reads, ds.pedigrees, p).phase(copy.deepcopy(shard))
+
+
+def port_all(ds, args):
+    """The oracle port over EVERY DNM of the workload, sharded by kid and contiguous genomic runs over all host cores
+    (forked workers: the tables are shared copy-on-write).  The checker of --full-parity, never the thing measured."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    by_kid = {}
+    for d in ds.dnms:
+        by_kid.setdefault(d["kid"], []).append(d)
+    shards = []
+    per = max(1, (len(ds.dnms) + 4 * cores - 1) // (4 * cores))
+    many = len(ds.dnms) >= config_of(args)["run"]["multiread_proc_min"]
+    for lst in by_kid.values():
+        # per-DNM find windows: DNMs of a kid do not interact and a kid may be cut; in find_many mode (window
+        # multiplicities count the kid's other DNMs, informative_site_finder.py:392-395) a kid stays whole and the
+        # mode switch is kept by handing every shard the whole run's decision
+        shards += [lst] if many else [lst[i: i + per] for i in range(0, len(lst), per)]
+    prm = port_params(args)
+    if many:
+        prm.multiread_proc_min = 0
+    _W["ds"], _W["shards"], _W["params"] = ds, shards, prm
+    out = {}
+    with mp.get_context("fork").Pool(cores) as pool:
+        for part in pool.imap_unordered(_port_shard, range(len(shards))):
+            out.update(part)
+    return out
 
 
 def threads_arm(ds, dnms, args):
@@ -381,16 +418,18 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
     gc.collect()
     gc.freeze()
     def steps_resident(k):
-        """k steps, software-pipelined two deep like BatchPhaser.phase_stream: the launches of step i+1 are queued
-        before the host waits for the download of step i (double-buffered arenas and pinned result blocks), so the
+        """k steps, software-pipelined like BatchPhaser.phase_stream: the launches of the next steps are queued before
+        the host waits for the download of step i (the engine rotates its arenas and pinned result blocks), so the
         host round trip of one step hides under the kernels of the next.  Every step's results reach the host."""
-        pend, out = None, None
+        from collections import deque
+        pend, out = deque(), None
         for _ in range(k):
-            h = eng.run(bp.dsites, bp.dreads, plan, params, blk_cul=cul, download=True, keep_device=False, defer=True)
-            if pend is not None:
-                out = pend.finish()
-            pend = h
-        return pend.finish() if pend is not None else out
+            pend.append(eng.run(bp.dsites, bp.dreads, plan, params, blk_cul=cul, download=True, keep_device=False, defer=True))
+            if len(pend) > 2:                              # at most two batches queued behind the one being waited for
+                out = pend.popleft().finish()
+        while pend:
+            out = pend.popleft().finish()
+        return out
 
     res = step_resident()                                  # first run sizes the capacities (two host syncs)
     res = steps_resident(max(args.warmup, 3))
@@ -585,6 +624,7 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
                     "one_off_pack_note": "reduction of the synthetic quality bytes to the 1-bit plane + pinning; a BAM packer "
                                          "writes the plane directly"},
             "gpu_launches": int(launches_per_step * args.steps),
+            "spec_fallbacks": int(getattr(eng, "spec_fallbacks", 0)),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -607,6 +647,15 @@ def _run_b200_on_stream(args, eng, ds, t_gen, conf, runkw, cohort, rank, local_r
                    if k not in want or k not in got or _norm(want[k]) != _norm(got[k])]
             line["parity"] = len(bad) == 0
             line["parity_detail"] = {"dnms_compared": len(sample), "records_compared": len(want), "mismatches": bad[:5]}
+            if args.full_parity:
+                t_fp = time.perf_counter()
+                want_all = port_all(ds, args)
+                bad = [k for k in sorted(set(want_all) | set(recs))
+                       if k not in want_all or k not in recs or _norm(want_all[k]) != _norm(recs[k])]
+                line["parity_full"] = {"ok": len(bad) == 0, "dnms_compared": n_dnms, "records_compared": len(want_all),
+                                       "gpu_records": len(recs), "mismatches": bad[:5],
+                                       "oracle_wall_s": round(time.perf_counter() - t_fp, 1)}
+                line["parity"] = line["parity"] and len(bad) == 0
         print(json.dumps(line))
 
 

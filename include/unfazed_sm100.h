@@ -100,7 +100,8 @@ typedef struct {
     uint16_t flag;
     uint16_t n_cigar;
     uint8_t  mapq;
-    uint8_t  aux;         /* bit0 next_ref==ref, bit1 has SA tag, bit2 (device only) a base of the read is not ACGT */
+    uint8_t  aux;         /* bit0 next_ref==ref, bit1 has SA tag; device only: bit6 the CIGAR is one M/= operation of l_seq bases (set by
+                             unfz_read_starts), bit7 a base of the read is not ACGT (set by unfz_expand_nlist) */
     uint8_t  qoff_hi;
     uint8_t  pad;
 } UnfzRead;
@@ -122,7 +123,7 @@ typedef struct {
                                     host packs the comparison, not the byte: 8x fewer bytes over PCIe and through the
                                     scan.  16-byte aligned, readable for 48 bytes past ceil(n_qual/8) */
     const uint32_t* nmask;       /* 1 bit per query base: the base is not A/C/G/T (built on the device from the sparse
-                                    index list by unfz_expand_nlist; reads that own such a base carry aux bit2) */
+                                    index list by unfz_expand_nlist; reads that own such a base carry aux bit7) */
     const uint8_t*  seq2;        /* 2-bit bases, base i at bits 2*(i&3) of byte i>>2; a masked base has code 0 for N */
     int64_t         n_qual;      /* number of query bases */
     int64_t         n_cigar;
@@ -262,11 +263,13 @@ int unfz_pack_site_rows(UnfzCtx*, int64_t n_rows, const int32_t* pos, const uint
 
 /* Device-side completion of the read columns after an upload: the host ships the positions of the (rare)
  * non-ACGT bases as a sorted list of base indices; this sets their bits in `nmask` (zeroed by the caller,
- * ceil(n_qual/32)+12 words) and bit2 of hdr[].aux of the reads that own them.  No reference counterpart
+ * ceil(n_qual/32)+12 words) and bit7 of hdr[].aux of the reads that own them.  No reference counterpart
  * (pysam hands out query_sequence as a string). */
 int unfz_expand_nlist(UnfzCtx*, const UnfzReadCols* reads, UnfzRead* hdr_rw, uint32_t* nmask_rw,
                       const int64_t* nidx, int64_t n_idx, void* stream);
-/* ... and the dense start column of UnfzReadCols out of the headers. */
+/* ... and the dense start column of UnfzReadCols out of the headers.  The same pass marks the reads whose CIGAR is a
+ * single M or = operation covering all l_seq bases (bit6 of hdr[].aux, written in place): for those, query index q
+ * sits at reference position start + q and the allele lookup and the seed tests skip the CIGAR gather. */
 int unfz_read_starts(UnfzCtx*, const UnfzReadCols* reads, int32_t* start_rw, void* stream);
 
 /* Read scan: goodread :28-53, insert-size / None-count / CIGAR-op filters :181-203 :395-408,

@@ -1,0 +1,18 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -q -x -m gpu 2>&1 | tail -3
+for i in 1 2; do
+timeout 900 python bench.py --steps 20 --warmup 5 --no-saturating --cpu-sample 30 2>gpurun_out/r2aa.err | tail -1 > gpurun_out/r2aa_c2.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2aa_c2.json'))
+print(round(d['value']), d['ms_per_step'], d['parity'], d['spec_fallbacks'], round(d['e2e']['value']), d['e2e']['breakdown_ms'], d['clocks'])
+PY
+done
+timeout 900 python bench.py --config c2_many --steps 20 --warmup 5 --no-saturating --cpu-sample 30 2>gpurun_out/r2aa.err | tail -1 > gpurun_out/r2aa_c2m.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2aa_c2m.json'))
+print(round(d['value']), d['ms_per_step'], d['parity'], d['spec_fallbacks'], round(d['e2e']['value']), d['e2e']['breakdown_ms'], d['clocks'])
+PY
+tail -3 gpurun_out/r2aa.err

@@ -21,6 +21,7 @@ extern "C" int unfz_ctx_create(int device, UnfzCtx** out) {
     c->scan_smem_attr = 0;
     c->chain_carveout_set = false;
     c->cls_params = nullptr;
+    c->cls_tab_dev = nullptr;
     memset(c->graphs, 0, sizeof(c->graphs));
     c->graph_tick = 0;
     c->err[0] = 0;
@@ -33,6 +34,7 @@ extern "C" void unfz_ctx_destroy(UnfzCtx* ctx) {
     for (auto& g : ctx->graphs)
         if (g.key) cudaGraphExecDestroy(g.exec);
     free(ctx->cls_params);
+    if (ctx->cls_tab_dev) cudaFree(ctx->cls_tab_dev);
     delete ctx;
 }
 
@@ -176,6 +178,7 @@ extern "C" int unfz_run_batch_graph(UnfzCtx* ctx, const UnfzBatch* b, const Unfz
     }
     if (!slot) {
         cudaGraph_t graph = nullptr;
+        { const int rc0 = unfz_classify_prepare(ctx, b->h_params); if (rc0) return rc0; }   // a synchronous copy: not under capture
         UNFZ_CHECK(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
         for (int i = 0; i < n_zero && rc == 0; ++i)

@@ -146,21 +146,33 @@ __device__ bool pair_ok(const ChainArgs& A, int64_t r, bool ext) {
     return ok_r && (sm.flags & needm) == needm && !((m0 <= r0 && r0 <= m1) || (m0 <= r1 && r1 <= m1));
 }
 
+// query index of reference position p in read e, the offset of the read's first base and its length.  A single-M read
+// (aux bit6, set at upload: nine reads in ten) answers out of its header; the CIGAR gather is skipped
+struct QPos { int q; int l_seq; int64_t g0; int32_t mate; };
+__device__ __forceinline__ QPos qpos_of(const ChainArgs& A, int64_t e, int32_t p) {
+    const UnfzRead h = load_read(A.reads.hdr + e);
+    QPos o;
+    if (h.aux & 0x40u) o.q = (p >= h.start && p < h.start + h.l_seq) ? (int)(p - h.start) : -1;
+    else o.q = cigar_qpos2(A.reads.cigar + h.cigar_off, h.n_cigar, h.start, p);
+    o.l_seq = h.l_seq;
+    o.g0 = read_qoff(h);
+    o.mate = h.mate;
+    return o;
+}
+
 // snv_match_alleles (:296-336) through get_allele_at (:56-73): 0 none, 1 ref, 2 alt
 __device__ int seed_snv(const ChainArgs& A, const UnfzDnm& dn, int64_t r) {
-    int64_t e = r;
-    UnfzRead h = load_read(A.reads.hdr + e);
-    int q = cigar_qpos2(A.reads.cigar + h.cigar_off, h.n_cigar, h.start, dn.pos);
+    QPos h = qpos_of(A, r, dn.pos);
+    int q = h.q;
     if (q < 0) {
-        e = h.mate;
-        h = load_read(A.reads.hdr + e);
-        q = cigar_qpos2(A.reads.cigar + h.cigar_off, h.n_cigar, h.start, dn.pos);
+        h = qpos_of(A, h.mate, dn.pos);
+        q = h.q;
         if (q < 0) return 0;
     }
     if (q < 4 || q > A.readlen - 4) return 0;
     const int n = dn.ref_len > dn.alt_len ? dn.ref_len : dn.alt_len;
     if (!(h.l_seq > q + n)) return 0;
-    const int64_t g = read_qoff(h) + q;
+    const int64_t g = h.g0 + q;
     bool is_ref = true;
     for (int i = 0; i < dn.ref_len; ++i)
         if (base_char(A.reads, g + i) != (char)A.alleles[dn.ref_off + i]) { is_ref = false; break; }
@@ -175,12 +187,15 @@ __device__ int seed_snv(const ChainArgs& A, const UnfzDnm& dn, int64_t r) {
 __device__ int seed_indel(const ChainArgs& A, const UnfzDnm& dn, int64_t r) {
     const UnfzRead h = load_read(A.reads.hdr + r);
     const uint32_t* cg = A.reads.cigar + h.cigar_off;
-    const int q = cigar_qpos2(cg, h.n_cigar, h.start, dn.pos);
+    const bool simple = (h.aux & 0x40u) != 0;            // one M operation: no I/D, only the "ref" outcome is possible
+    const int q = simple ? ((dn.pos >= h.start && dn.pos < h.start + h.l_seq) ? (int)(dn.pos - h.start) : -1)
+                         : cigar_qpos2(cg, h.n_cigar, h.start, dn.pos);
     if (q < 0) return 0;
     const int n = dn.ref_len > dn.alt_len ? dn.ref_len : dn.alt_len;
     const int64_t g0 = read_qoff(h);
     for (int i = q; i < q + n && i < h.l_seq; ++i)
         if (plane_bit(A.reads.lowq, g0 + i)) return 0;
+    if (simple) return (7 < q && q < h.l_seq - 7) ? 1 : 0;
     bool has_id = false;
     int64_t eo = 0, npos = 0;
     for (int k = 0; k < h.n_cigar; ++k) {

@@ -20,6 +20,7 @@ struct UnfzCtx {
     bool chain_carveout_set;  // shared-memory carve-out preference of the chaining kernel set on THIS device
     size_t scan_smem_attr;    // opt-in dynamic shared memory already granted to the read scan on THIS device
     void* cls_params;         // classifier thresholds + allele-balance interval table of cls_key (sites.cu), malloc'ed
+    uint32_t* cls_tab_dev;    // the same table on the device (cudaMalloc'ed with the first classification)
     double cls_key[8];        // ab_homref, ab_het, ab_homalt, min_gt_qual, min_depth the table was made for
     UnfzGraphSlot graphs[8];  // instantiated batch graphs (unfz_run_batch_graph)
     uint64_t graph_tick;
@@ -40,6 +41,10 @@ struct UnfzCtx {
     } while (0)
 
 #define UNFZ_LAUNCH_CHECK(ctx) UNFZ_CHECK(ctx, cudaGetLastError())
+
+// internal: makes sure the classifier's interval table for these thresholds is on the device (synchronous copy when the
+// thresholds change: must run outside stream capture -- unfz_run_batch_graph calls it before it starts capturing)
+extern "C" int unfz_classify_prepare(UnfzCtx* ctx, const UnfzParams* hp);
 
 static inline int unfz_fail(UnfzCtx* ctx, int code, const char* msg) {
     snprintf(ctx->err, sizeof(ctx->err), "%s", msg);

@@ -465,12 +465,15 @@ __device__ __forceinline__ void read_alleles_one(const UnfzReadCols& reads, cons
     const UnfzReadSum s = load_rsum(rsum + r);
     const UnfzRead h = load_read(reads.hdr + r);           // independent of the summary: both sectors fly together
     if (s.cnt == 0) return;
+    // nine reads in ten are one M operation covering every base (aux bit6, set at upload by unfz_read_starts): their
+    // only CIGAR word is known without fetching it -- one gathered sector less per read
+    const bool simple = (h.aux & 0x40u) != 0;
     // The scan counted s.cnt marked rows with start <= pos < end from row_lb on, all inside the read's site block:
     // the walk ends when they are written, so the block's end is never consulted (n_rows only bounds the prefetch)
     const int64_t n_rows = sites.n_rows;
     int64_t row = s.row_lb;                                // first site row with pos >= start (from read_scan)
     const uint32_t* cg = reads.cigar + h.cigar_off;
-    const uint32_t cg0 = h.n_cigar > 0 ? __ldg(cg) : 0u;
+    const uint32_t cg0 = simple ? ((uint32_t)h.l_seq << 4) : (h.n_cigar > 0 ? __ldg(cg) : 0u);   // a simple read IS "l_seq M"
     int32_t p = row < n_rows ? __ldg(sites.pos + row) : 0x7fffffff;
     int mp0 = __ldg(mark_prefix + min(row, n_rows));
     int mp1 = __ldg(mark_prefix + min(row + 1, n_rows));
@@ -488,7 +491,7 @@ __device__ __forceinline__ void read_alleles_one(const UnfzReadCols& reads, cons
             if (q >= 0 && q < 0xffff) {
                 const int64_t g = q0 + q;
                 const uint32_t lq = (__ldg(reads.lowq + (g >> 5)) >> (g & 31)) & 1u;
-                const uint32_t nb = (h.aux & 4u) ? ((__ldg(reads.nmask + (g >> 5)) >> (g & 31)) & 1u) : 0u;
+                const uint32_t nb = (h.aux & 0x80u) ? ((__ldg(reads.nmask + (g >> 5)) >> (g & 31)) & 1u) : 0u;
                 const uint32_t code = (__ldg(reads.seq2 + (g >> 2)) >> ((g & 3) << 1)) & 3u;
                 word = (uint32_t)(q + 1) | (lq << 16) | (nb << 23) | (code << 24) | ((q + 1 < h.l_seq) ? (1u << 26) : 0u);
             }
@@ -610,22 +613,36 @@ __global__ void expand_nlist_kernel(UnfzReadCols reads, UnfzRead* __restrict__ h
     int64_t r = lo - 1;
     while (r >= 0 && hdr[r].l_seq == 0) --r;
     if (r < 0 || read_qoff(hdr[r]) + hdr[r].l_seq <= g) return;     // a base index between two reads: nobody owns it
-    // aux is byte 29 of the 32-byte header: set bit2 with a word-wide atomic (the neighbours are mapq, qoff_hi, pad)
+    // aux is byte 29 of the 32-byte header: set bit7 with a word-wide atomic (the neighbours are mapq, qoff_hi, pad)
     unsigned* w = reinterpret_cast<unsigned*>(hdr + r) + 7;
-    atomicOr(w, 4u << 8);
+    atomicOr(w, 0x80u << 8);
 }
 }  // namespace
 
 namespace {
-__global__ void read_starts_kernel(const UnfzRead* __restrict__ hdr, int64_t n, int32_t* __restrict__ out) {
+__global__ void read_starts_kernel(UnfzRead* __restrict__ hdr, const uint32_t* __restrict__ cigar, int64_t n_cigar_words,
+                                   int64_t n, int32_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = hdr[i].start;
+    if (i >= n) return;
+    const UnfzRead h = hdr[i];
+    out[i] = h.start;
+    // one M or = operation covering every base: mark the read (aux bit6) -- query index q is at start + q.  The two
+    // device-only bits are (re)written here, whatever the host table carried; unfz_expand_nlist runs after this kernel
+    bool simple = false;
+    if (h.n_cigar == 1 && h.l_seq > 0 && (int64_t)h.cigar_off < n_cigar_words) {
+        const uint32_t w = cigar[h.cigar_off];
+        const uint32_t op = w & 15u;
+        simple = (op == 0u || op == 7u) && (w >> 4) == (uint32_t)h.l_seq;
+    }
+    unsigned* wp = reinterpret_cast<unsigned*>(hdr + i) + 7;        // mapq | aux << 8 | qoff_hi << 16 | pad << 24
+    *wp = (*wp & ~(0xc0u << 8)) | (simple ? (0x40u << 8) : 0u);
 }
 }  // namespace
 
 extern "C" int unfz_read_starts(UnfzCtx* ctx, const UnfzReadCols* reads, int32_t* start_rw, void* stream) {
     if (reads->n_reads <= 0) return 0;
-    read_starts_kernel<<<(unsigned)((reads->n_reads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reads->hdr, reads->n_reads, start_rw);
+    read_starts_kernel<<<(unsigned)((reads->n_reads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        const_cast<UnfzRead*>(reads->hdr), reads->cigar, reads->n_cigar, reads->n_reads, start_rw);
     UNFZ_LAUNCH_CHECK(ctx);
     return 0;
 }

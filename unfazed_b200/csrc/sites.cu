@@ -38,17 +38,21 @@ __global__ void window_search_kernel(UnfzSiteCols sites, const UnfzSegIn* __rest
 // for every (genotype class, tot) the passing ad form one interval [min_ad, max_ad]; the host works the intervals
 // out ONCE with the very IEEE double division the reference performs (unfz_classify_sites) for every tot below
 // CLS_TAB_TOT, folds "genotype is known" and "tot >= min_depth" into them (empty interval) and hands the table to the
-// kernel, which stages it in shared memory: one LDS + two integer compares per member instead of a reciprocal, a
+// kernel (16 KB in device memory, copied into shared memory by every CTA with coalesced 16-byte loads): one LDS + two integer compares per member instead of a reciprocal, a
 // multiply, six float compares and a guard band.  Depths of CLS_TAB_TOT and more, and negative counts, take the exact
 // fp64 division (ab_exact) as before.
 constexpr int CLS_TAB_TOT = 1024;
 constexpr int CLS_TAB_ROWS = 4;           // homref, het, homalt, unknown/invalid (always empty)
 
 struct ClsParams {
-    uint32_t tab[CLS_TAB_ROWS * CLS_TAB_TOT];   // min_ad | max_ad << 16; empty: min 1, max 0
+    const uint32_t* tab;                  // device, [CLS_TAB_ROWS][CLS_TAB_TOT]: min_ad | max_ad << 16; empty: min 1, max 0
     double lo[4], hi[4];                  // fp64 thresholds per table row for the exact path (row 3: NaN, never true)
     float min_gq_f;       // smallest float >= min_gq: for a float gq, (double)gq < min_gq <=> gq < min_gq_f
     int32_t min_depth;
+};
+struct ClsHost {                          // what the context keeps per set of thresholds
+    ClsParams P;
+    uint32_t tab[CLS_TAB_ROWS * CLS_TAB_TOT];
 };
 
 // exact: min_ab <= float(ad / float(rd+ad)) <= max_ab, informative_site_finder.py:69-71
@@ -145,7 +149,7 @@ constexpr int CLS_SMEM_SEGS = 512;
 // inclusive prefix is the index of the last segment starting at or before the pair).
 __global__ void __launch_bounds__(CLS_THREADS, CLS_MINB)
 classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const int32_t* __restrict__ seg_row_lo,
-                const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs_cap, const __grid_constant__ ClsParams P,
+                const int64_t* __restrict__ seg_pair_off, int32_t n_segs, int64_t n_pairs_cap, ClsParams P,
                 uint8_t* __restrict__ out, const int32_t* __restrict__ guard) {
     UNFZ_GUARD(guard);
     // the launch is sized for n_pairs_cap (the caller's buffer); the batch's own total is on the device
@@ -154,7 +158,7 @@ classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const in
     __shared__ int4 s_seg[CLS_SMEM_SEGS];            // row_lo, mult | mode << 24, excl_lo, excl_hi
     __shared__ int32_t s_map[CLS_TILE];
     __shared__ int32_t s_warp[CLS_THREADS / 32];
-    __shared__ uint32_t s_tab[CLS_TAB_ROWS * CLS_TAB_TOT];
+    __shared__ __align__(16) uint32_t s_tab[CLS_TAB_ROWS * CLS_TAB_TOT];
     __shared__ double s_lohi[8];
     __shared__ uint8_t s_lut[64];
     __shared__ int32_t s_seg0;
@@ -162,7 +166,8 @@ classify_kernel(UnfzSiteCols sites, const UnfzSegIn* __restrict__ segs, const in
     const int64_t tpc = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * tpc, t1 = min(t0 + tpc, n_tiles);
     if (t0 >= t1) return;
-    for (int i = threadIdx.x; i < CLS_TAB_ROWS * CLS_TAB_TOT; i += CLS_THREADS) s_tab[i] = P.tab[i];
+    for (int i = threadIdx.x; i < CLS_TAB_ROWS * CLS_TAB_TOT / 4; i += CLS_THREADS)
+        reinterpret_cast<uint4*>(s_tab)[i] = __ldg(reinterpret_cast<const uint4*>(P.tab) + i);
     if (threadIdx.x < 8) s_lohi[threadIdx.x] = threadIdx.x < 4 ? P.lo[threadIdx.x] : P.hi[threadIdx.x - 4];
     if (threadIdx.x < 64) {
         const int gk = threadIdx.x >> 4, gd = (threadIdx.x >> 2) & 3, gm = threadIdx.x & 3;
@@ -384,9 +389,11 @@ extern "C" int unfz_window_search(UnfzCtx* ctx, const UnfzSiteCols* sites, const
 static ClsParams* cls_params_for(UnfzCtx* ctx, const UnfzParams* hp) {
     const double key[8] = {hp->ab_homref[0], hp->ab_homref[1], hp->ab_het[0], hp->ab_het[1], hp->ab_homalt[0], hp->ab_homalt[1],
                            hp->min_gt_qual, (double)hp->min_depth};
-    if (ctx->cls_params && memcmp(key, ctx->cls_key, sizeof(key)) == 0) return static_cast<ClsParams*>(ctx->cls_params);
-    if (!ctx->cls_params) ctx->cls_params = malloc(sizeof(ClsParams));
-    ClsParams& P = *static_cast<ClsParams*>(ctx->cls_params);
+    if (ctx->cls_params && memcmp(key, ctx->cls_key, sizeof(key)) == 0) return &static_cast<ClsHost*>(ctx->cls_params)->P;
+    if (!ctx->cls_params) ctx->cls_params = malloc(sizeof(ClsHost));
+    if (!ctx->cls_tab_dev && cudaMalloc(&ctx->cls_tab_dev, sizeof(uint32_t) * CLS_TAB_ROWS * CLS_TAB_TOT) != cudaSuccess) return nullptr;
+    ClsHost& H = *static_cast<ClsHost*>(ctx->cls_params);
+    ClsParams& P = H.P;
     const double ab[3][2] = {{hp->ab_homref[0], hp->ab_homref[1]}, {hp->ab_het[0], hp->ab_het[1]}, {hp->ab_homalt[0], hp->ab_homalt[1]}};
     for (int r = 0; r < CLS_TAB_ROWS; ++r) {
         P.lo[r] = r < 3 ? ab[r][0] : NAN;
@@ -404,21 +411,32 @@ static ClsParams* cls_params_for(UnfzCtx* ctx, const UnfzParams* hp) {
                 while (a1 >= 0 && !pass(a1)) --a1;
                 if (a0 <= a1) e = (uint32_t)a0 | ((uint32_t)a1 << 16);
             }
-            P.tab[r * CLS_TAB_TOT + tot] = e;
+            H.tab[r * CLS_TAB_TOT + tot] = e;
         }
     }
+    P.tab = ctx->cls_tab_dev;
     P.min_gq_f = (float)hp->min_gt_qual;
     if ((double)P.min_gq_f < hp->min_gt_qual) P.min_gq_f = nextafterf(P.min_gq_f, INFINITY);
     P.min_depth = hp->min_depth;
+    // synchronous on purpose: the table is read by launches on any stream from now on (thresholds change once per run)
+    memset(ctx->cls_key, 0xff, sizeof(ctx->cls_key));
+    if (cudaMemcpy(ctx->cls_tab_dev, H.tab, sizeof(H.tab), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
     memcpy(ctx->cls_key, key, sizeof(key));
     return &P;
+}
+
+extern "C" int unfz_classify_prepare(UnfzCtx* ctx, const UnfzParams* hp) {
+    if (!cls_params_for(ctx, hp)) { UNFZ_CHECK(ctx, cudaGetLastError()); return unfz_fail(ctx, -22, "classifier table upload failed"); }
+    return 0;
 }
 
 extern "C" int unfz_classify_sites(UnfzCtx* ctx, const UnfzSiteCols* sites, const UnfzSegIn* segs,
                                    const int32_t* seg_row_lo, const int64_t* seg_pair_off, int32_t n_segs,
                                    int64_t n_pairs, const UnfzParams* hp, uint8_t* out_class, void* stream) {
     if (n_pairs <= 0) return 0;
-    ClsParams& P = *cls_params_for(ctx, hp);
+    ClsParams* Pp = cls_params_for(ctx, hp);
+    if (!Pp) { UNFZ_CHECK(ctx, cudaGetLastError()); return unfz_fail(ctx, -22, "classifier table upload failed (thresholds changed under stream capture?)"); }
+    const ClsParams& P = *Pp;
     const int64_t n_tiles = (n_pairs + CLS_TILE - 1) / CLS_TILE;
     // persistent grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
     int64_t grid = (int64_t)ctx->sm_count * 8;

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import collections
 import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
@@ -270,6 +271,8 @@ class Engine:
         self.stream2 = torch.cuda.Stream(self.device)      # late downloads of a deferred batch (see PendingBatch)
         self.use_graph = not os.environ.get("UNFZ_NO_GRAPH")
         self._caps = None                                  # capacities seen so far (speculative sizing)
+        self.spec_fallbacks = 0                            # batches re-run with exact sizes because a capacity was exceeded
+        self._pool_limit = int(0.35 * torch.cuda.get_device_properties(self.device).total_memory)   # recycled arena bytes
 
     def on_stream(self):
         """Context: torch's current stream is the engine's (uploads, runs, events recorded by callers)."""
@@ -445,7 +448,10 @@ class Engine:
                 # a run that keeps nothing on the device hands its buffers back (see the end of run());
                 # the next run with the same layout reuses them and only clears the zero-initialised ones
                 self_.key = (self_.zero, tuple(self_.items))
-                buf = pool.pop(self_.key, None) if reuse else None
+                # one FIFO per layout: with several deferred batches in flight the buffer sets rotate in a fixed order,
+                # so a batch meets the same addresses (and its instantiated CUDA graph) every time it comes round
+                q_ = pool.get(self_.key) if reuse else None
+                buf = q_.popleft() if q_ else None
                 if buf is None:
                     fn = torch.zeros if self_.zero else torch.empty
                     buf = fn((max(self_.size, 256),), dtype=torch.uint8, device=dev)
@@ -779,6 +785,7 @@ class Engine:
                     actual = g_[64: 64 + 64].view(np.int64)
                     if int(g_[:4].view(np.int32)[0]) != 0:
                         # a capacity was exceeded: nothing was written out of bounds, run again with exact sizes
+                        self.spec_fallbacks += 1
                         self._caps = None
                         dv.clear()
                         return self.run(dsites, dreads, plan, params, blk_cul=blk_cul, time_stages=time_stages,
@@ -836,10 +843,12 @@ class Engine:
                     res.timings_ms[n1] = res.timings_ms.get(n1, 0.0) + e0.elapsed_time(e1_)
             if not keep_device:
                 dv.clear()
-                if len(pool) > 12:
+                # stale layouts are dropped by size, not by count: a few batches in flight times six arenas is dozens of
+                # live buffers, and clearing them mid-stream would cost every batch a fresh allocation and graph
+                if len(pool) > 48 or sum(b_.numel() for q_ in pool.values() for b_ in q_) > self._pool_limit:
                     pool.clear()
                 for a_ in arenas:
-                    pool[a_.key] = a_.buf
+                    pool.setdefault(a_.key, collections.deque()).append(a_.buf)
             return res
 
         if defer:

@@ -362,18 +362,18 @@ def plan_find_fast(dnms: List[dict], pedigrees: dict, sidx: SiteIndex, reads: Op
         # find_many: only the start window; the VCF's contig name must equal the DNM's spelling (Q11); a site is appended
         # once per occurrence of the kid in the location list of the DNM's start -- DNM starts, and ends of events
         # longer than 2 bp (:392-395) -- of every non-autophased DNM
-        from collections import Counter
         single = np.ones(n, dtype=bool)
         g_same = np.array([g_contig[g] == groups[g][1] for g in range(G)], dtype=bool)
         has_win = found & g_same[gids]
-        cnt = Counter()
-        for g, s_, e_, a_ in zip(gids.tolist(), start.tolist(), end.tolist(), auto.tolist()):
-            if a_:
-                continue
-            cnt[(g, s_)] += 1
-            if e_ - s_ > 2:
-                cnt[(g, e_)] += 1
-        mult1 = np.fromiter((cnt[(g, s_)] for g, s_ in zip(gids.tolist(), start.tolist())), dtype=np.int64, count=n)
+        # multiset of (group, location) keys over the non-autophased DNMs, counted with one sort
+        live = ~np.asarray(auto, dtype=bool)
+        key_s = (gids.astype(np.int64) << 33) + start.astype(np.int64)
+        key_e = (gids.astype(np.int64) << 33) + end.astype(np.int64)
+        locs = np.concatenate([key_s[live], key_e[live & ((end - start) > 2)]])
+        uniq, counts = np.unique(locs, return_counts=True)
+        at_ = np.searchsorted(uniq, key_s)
+        at_c = np.minimum(at_, max(len(uniq) - 1, 0))
+        mult1 = np.where((at_ < len(uniq)) & (uniq[at_c] == key_s) if len(uniq) else np.zeros(n, dtype=bool), counts[at_c] if len(uniq) else 0, 0).astype(np.int64)
         has_win &= mult1 > 0
     nseg = np.where(has_win, np.where(single, 1, 0), 0).astype(np.int64)
     multi_idx = np.nonzero(has_win & ~single)[0]

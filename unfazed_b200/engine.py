@@ -272,6 +272,9 @@ class Engine:
         self.use_graph = not os.environ.get("UNFZ_NO_GRAPH")
         self._caps = None                                  # capacities seen so far (speculative sizing)
         self.spec_fallbacks = 0                            # batches re-run with exact sizes because a capacity was exceeded
+        self._pinned_free: Dict[int, list] = {}            # recycled pinned download blocks by size class
+        self._stage_new: list = []                         # pinned upload staging blocks handed out, no event yet
+        self._stage_busy: list = []                        # (block, event recorded after its copy)
         self._pool_limit = int(0.35 * torch.cuda.get_device_properties(self.device).total_memory)   # recycled arena bytes
 
     def on_stream(self):
@@ -372,16 +375,44 @@ class Engine:
         return PackedReads(table, min_base_qual(min_gt_qual), pin)
 
     def _pinned(self, a: np.ndarray) -> torch.Tensor:
-        """Small host array -> pinned staging tensor.  A copy out of PAGEABLE memory makes the host wait for everything
-        queued on the stream before it (the driver stages it in order), which would serialise a deferred batch behind
-        the previous batch's 2 GB of uploads; a pinned source keeps the call asynchronous.  The last few staging
-        buffers are kept alive until their copies are certainly done."""
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        keep = self.__dict__.setdefault("_staging", [])
-        keep.append(t)
-        if len(keep) > 64:
-            del keep[:32]
-        return t
+        """Small host array -> pinned staging tensor (the caller copies it to the device right away, on the current
+        stream).  A copy out of PAGEABLE memory makes the host wait for everything queued on the stream before it (the
+        driver stages it in order), which would serialise a deferred batch behind the previous batch's 2 GB of uploads; a
+        pinned source keeps the call asynchronous.  The blocks are recycled by size class once an event recorded after
+        their copy has completed: allocating pinned memory is a slow, device-synchronising call, so a steady-state batch
+        must not make one."""
+        a = np.ascontiguousarray(a)
+        nb = int(a.nbytes)
+        st = torch.cuda.current_stream(self.device)
+        if self._stage_new:                     # handed out by earlier calls: their copies are on the stream by now
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self._stage_busy += [(blk, ev) for blk in self._stage_new]
+            self._stage_new = []
+        size = 4096
+        while size < nb:
+            size *= 2
+        blk = None
+        for i, (b_, ev) in enumerate(self._stage_busy):
+            if b_.numel() == size and ev.query():
+                blk = b_
+                del self._stage_busy[i]
+                break
+        if blk is None:
+            blk = torch.empty((size,), dtype=torch.uint8, pin_memory=True)
+        host = blk[:nb]
+        if nb:
+            host.numpy()[:] = a.reshape(-1).view(np.uint8)
+        self._stage_new.append(blk)
+        return host.view(torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype).reshape(a.shape)
+
+    def _pinned_block(self, nbytes: int) -> torch.Tensor:
+        """A pinned uint8 block of at least ``nbytes`` (power-of-two size classes), recycled through ``_pinned_free``."""
+        size = 4096
+        while size < nbytes:
+            size *= 2
+        free = self._pinned_free.get(size)
+        return free.pop() if free else torch.empty((size,), dtype=torch.uint8, pin_memory=True)
 
     def _h2d(self, a: np.ndarray) -> torch.Tensor:
         return self._pinned(a).to(self.device, non_blocking=True)
@@ -764,9 +795,13 @@ class Engine:
             lib.unfz_ctx_set_guard(ctx, None)
         front_buf, done = None, None
         if download:
-            # pinned target (torch's caching host allocator recycles the buffers; a pageable D2H copy is several times
-            # slower and serialises with the driver); the arrays of the result are views of it
-            front_buf = torch.empty((dl_end,), dtype=torch.uint8, pin_memory=True)
+            # pinned target (a pageable D2H copy is several times slower and serialises with the driver).  With recycled
+            # arenas the pinned block rotates with them: allocating pinned memory is a slow, device-synchronising call
+            # (tens of milliseconds on an 8-GPU box), so a steady-state batch must not make one; the result arrays are
+            # then copied out of the block in finish(), before the set is handed back
+            pkey = ("pinned", int(dl_end))
+            q_ = pool.get(pkey) if reuse else None
+            front_buf = q_.popleft() if q_ else torch.empty((dl_end,), dtype=torch.uint8, pin_memory=True)
             front_buf.copy_(z1.buf[:dl_end], non_blocking=True)
             done = torch.cuda.Event()
             done.record(st)
@@ -775,7 +810,7 @@ class Engine:
             nonlocal res
             if download:
                 done.synchronize()
-                front = front_buf.numpy()
+                front = front_buf.numpy().copy() if reuse else front_buf.numpy()
                 self.last_d2h_bytes = int(dl_end)
                 item = {nm: (off, nb) for nm, off, nb in z1.items}
                 sect = lambda nm: front[item[nm][0]: item[nm][0] + item[nm][1]]
@@ -825,14 +860,19 @@ class Engine:
                     tot = [int(eo[q, n]) for q in range(4)]
                     parts = [(e3.view["ev_read_dad"], 4 * tot[0]), (e3.view["ev_read_mom"], 4 * tot[1]),
                              (e2.view["ev_pos_dad"], 4 * tot[2]), (e2.view["ev_pos_mom"], 4 * tot[3])]
-                    bufs = []
+                    # pinned blocks come from the engine's own size-class lists (no pinned allocation in steady state,
+                    # see above) and go back as soon as the lists are copied out
+                    bufs, blocks = [], []
                     with torch.cuda.stream(self.stream2):
                         for t_, nb_ in parts:
-                            hb = torch.empty((max(nb_, 4),), dtype=torch.uint8, pin_memory=True)
+                            hb = self._pinned_block(nb_)
                             if nb_:
                                 hb[:nb_].copy_(t_[:nb_], non_blocking=True)
-                            bufs.append(hb.numpy()[:nb_].view(np.int32))
+                            blocks.append(hb)
                     self.stream2.synchronize()
+                    for hb, (t_, nb_) in zip(blocks, parts):
+                        bufs.append(hb.numpy()[:nb_].copy().view(np.int32))
+                        self._pinned_free.setdefault(int(hb.numel()), []).append(hb)
                     res.ev = {"off": eo, "read_dad": bufs[0], "read_mom": bufs[1], "pos_dad": bufs[2], "pos_mom": bufs[3]}
                     self.last_d2h_bytes += 4 * sum(tot)
             mark("download")
@@ -849,6 +889,8 @@ class Engine:
                     pool.clear()
                 for a_ in arenas:
                     pool.setdefault(a_.key, collections.deque()).append(a_.buf)
+                if download and reuse:
+                    pool.setdefault(pkey, collections.deque()).append(front_buf)
             return res
 
         if defer:

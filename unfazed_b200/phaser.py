@@ -39,7 +39,17 @@ class CompactRecords:
         return len(self.entries)
 
     def to_records(self, out: Optional[Dict[str, dict]] = None) -> Dict[str, dict]:
+        import gc
         out = {} if out is None else out
+        was_on = gc.isenabled()
+        gc.disable()                    # thousands of small containers, no cycles: a collection in the middle only costs time
+        try:
+            return self._to_records(out)
+        finally:
+            if was_on:
+                gc.enable()
+
+    def _to_records(self, out: Dict[str, dict]) -> Dict[str, dict]:
         k = len(self.entries)
         n_r = len(self.names) if self.names is not None else int(self.pair_ids.shape[0])
         idx = np.arange(n_r, dtype=np.int32)

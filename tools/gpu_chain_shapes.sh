@@ -1,3 +1,4 @@
+# Chaining time for the two compiled CTA shapes (UNFZ_CHAIN_SHAPE=small|wide) over window sizes: where the switch sits.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/r2w_pytest.log

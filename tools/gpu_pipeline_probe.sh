@@ -1,3 +1,5 @@
+# Per-step host issue / wait times of the pipelined resident loop (find and find_many plans): the probe that showed
+# the resident step is stable at 1.4 ms when nothing allocates in the loop.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 python - <<'PY'

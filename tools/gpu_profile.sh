@@ -1,3 +1,5 @@
+# ncu launch list (default graph path), ncu --set full of the main kernels on c2 and c4 (per-call path), and
+# compute-sanitizer memcheck / racecheck.  Summaries: tools/ncu_summary.py -> profiles/.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-saturating"

@@ -1,3 +1,5 @@
+# The 1-GPU measurement suite of a round (run on a B200 box through gpurun): GPU tests, every bench config with
+# --full-parity where the oracle finishes in a minute, the reference arm.  Outputs under gpurun_out/.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 nproc; free -g | head -2 | tail -1

@@ -1,3 +1,4 @@
+# gpu_suite_ngpu.sh N [configs...]: bench.py under an N-rank torchrun (default configs: c2 c5).
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=$1

@@ -106,3 +106,44 @@ def test_phase_by_reads_and_phase_by_snvs_random():
         for ref_mod in (mods["snv_phaser"], mods["sv_phaser"]):
             assert new_snv.phase_by_reads(matches) == ref_mod.phase_by_reads(matches)
         assert new_sv.phase_by_snvs(sites) == mods["sv_phaser"].phase_by_snvs(sites)
+
+
+def test_autophase_and_get_refalt_match_the_reference():
+    """The remaining per-variant callables of the phaser modules: ``autophase`` (snv_phaser.py:302-352 returns True and
+    writes the SEX-CHROM record, sv_phaser.py:304-354 writes it and returns None) and ``get_refalt``
+    (snv_phaser.py:73-84) over the in-memory cyvcf2 stand-in."""
+    import copy
+    mods = ref_driver.modules()
+    from oracle import fakes
+    from unfazed_b200 import snv_phaser as new_snv, sv_phaser as new_sv
+    from unfazed_b200.synth import SynthConfig, make_dataset
+    peds = {"boy": {"kid": "boy", "dad": "d", "mom": "m", "sex": "1"}, "girl": {"kid": "girl", "dad": "d", "mom": "m", "sex": "2"}}
+    rng = random.Random(17)
+    starts = [10000, 10001, 60001, 2699520, 2699521, 2781479, 154931044, 155260560, 156030895, 59363566] + \
+             [rng.randint(1, 160000000) for _ in range(10)]
+    for build in ("37", "38", "19", 38):
+        for chrom in ("X", "chrY", "y", "7"):
+            for kid in ("boy", "girl"):
+                for start in starts:
+                    dn = {"chrom": chrom, "start": start, "end": start + 1, "kid": kid, "vartype": rng.choice(["POINT", "DEL"])}
+                    for new_mod, ref_mod in ((new_snv, mods["snv_phaser"]), (new_sv, mods["sv_phaser"])):
+                        want_rec, got_rec = {}, {}
+                        want = ref_mod.autophase(copy.deepcopy(dn), peds, want_rec, "d", "m", build)
+                        got = new_mod.autophase(copy.deepcopy(dn), peds, got_rec, "d", "m", build)
+                        assert got == want and got_rec == want_rec, (build, chrom, kid, start, new_mod.__name__)
+                        if want_rec:
+                            assert list(got_rec.values())[0].keys() == list(want_rec.values())[0].keys()
+    ds = make_dataset(SynthConfig(dnms_per_trio=30, n_trios=2, seed=23, coverage=1.0, chr_prefix="chr"))
+    fakes.install()
+    fakes.register_vcf("mem://refalt.vcf", ds.sites)
+    import cyvcf2
+    s = ds.sites
+    probes = [(s.contigs[int(s.blk_contig[b])], int(s.pos[int(s.blk_off[b]) + k])) for b in range(s.n_blocks)
+              for k in range(0, int(s.blk_off[b + 1] - s.blk_off[b]), 97)][:60]
+    for contig, pos in probes:
+        for chrom in (contig, contig.replace("chr", "")):
+            for p in (pos, pos + 1, pos - 1, str(pos + 1)):
+                want = mods["snv_phaser"].get_refalt(chrom, p, cyvcf2.VCF("mem://refalt.vcf"), 0)
+                got = new_snv.get_refalt(chrom, p, cyvcf2.VCF("mem://refalt.vcf"), 0)
+                assert got == want, (chrom, p)
+    assert any(new_snv.get_refalt(c.replace("chr", ""), p + 1, cyvcf2.VCF("mem://refalt.vcf"), 0)[0] is not None for c, p in probes)

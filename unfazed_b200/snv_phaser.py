@@ -47,6 +47,32 @@ def phase_by_reads(matches):
     return credit
 
 
+def get_refalt(chrom, pos, vcf_filehandle, kid_idx):
+    """``snv_phaser.py:73-84``: REF of the first record the sites VCF returns for ``chrom:pos-(pos+1)`` (contig spelled
+    with the VCF's own prefix) and the ALT alleles of ALL records there, other trios' included (Q22); ``kid_idx`` is not
+    used by the reference either.  The batched path takes both from the site table (``plan.SiteIndex.refalt``); this is
+    the per-variant mirror for callers that hold a cyvcf2 handle."""
+    from .utils import get_prefix
+    region = "{}{}:{}-{}".format(get_prefix(vcf_filehandle), chrom.strip("chr"), pos, int(pos) + 1)
+    ref, alts = None, []
+    for record in vcf_filehandle(region):
+        ref = record.REF if ref is None else ref
+        alts.extend(record.ALT)
+    return ref, alts
+
+
+def autophase(denovo, pedigrees, records, dad_id, mom_id, build):
+    """``snv_phaser.py:302-352``: a DNM of a male kid on X or Y outside the pseudoautosomal regions needs no evidence;
+    its SEX-CHROM record is written into ``records`` and True is returned.  The batched path flags these entries in
+    the plan (``plan.is_autophaseable``) and emits the same record (``phaser.BatchPhaser._auto_record``)."""
+    from .phaser import BatchPhaser, dnm_key
+    from .plan import is_autophaseable
+    if not is_autophaseable(denovo, pedigrees, build):
+        return False
+    records[dnm_key(denovo)] = BatchPhaser._auto_record(denovo, dad_id, mom_id)
+    return True
+
+
 def run_batch(snvs, svs, pedigrees, sites, threads, build, no_extended, multiread_proc_min, ab_homref, ab_homalt,
               ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample, stdevs, min_map_qual, readlen,
               split_error_margin, compact=False):

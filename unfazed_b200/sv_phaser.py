@@ -19,6 +19,13 @@ def phase_by_snvs(informative_sites):
         votes[site[site["kid_allele"]]].append(site)
     return votes
 
+def autophase(denovo, pedigrees, records, dad_id, mom_id, build):
+    """``sv_phaser.py:304-354``: as ``snv_phaser.autophase`` -- the SEX-CHROM record is written -- but the reference's SV
+    variant falls off its end and returns None where the SNV one returns True (False on the early exits), so its caller
+    goes on to phase the event as well."""
+    return None if snv_phaser.autophase(denovo, pedigrees, records, dad_id, mom_id, build) else False
+
+
 def phase_svs(dnms, kids, pedigrees, sites, threads, build, no_extended, multiread_proc_min, quiet_mode,
               ab_homref, ab_homalt, ab_het, min_gt_qual, min_depth, search_dist, insert_size_max_sample,
               stdevs, min_map_qual, readlen, split_error_margin):
